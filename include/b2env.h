@@ -1,0 +1,97 @@
+/* b2env.h -- C-ABI of the B200 batched physics-and-task engine (libb2env.so).
+ *
+ * The reference (hasnainfarid/Mujoco_Gymnasium_Environments) has no FFI of its own: its hot path is Python calling
+ * the `mujoco` bindings.  Each entry point below names the reference call it stands in for, so that a maintainer can
+ * bind it with ctypes from the reference's env classes (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 on success or a negative code and never throws across the ABI;
+ * b2_last_error() gives the message.  Pointers named *_dev are CUDA device pointers owned by the caller (e.g. torch
+ * tensors); the library borrows them for the duration of the stream-ordered call.  `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  One host thread per B2Batch.  No global mutable state besides the error string.
+ */
+#ifndef B2ENV_H
+#define B2ENV_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct B2Model B2Model;
+typedef struct B2Batch B2Batch;
+
+enum { B2_OK = 0, B2_ERR_ARG = -1, B2_ERR_CUDA = -2, B2_ERR_LAYOUT = -3, B2_ERR_UNSUPPORTED = -4 };
+enum { B2_TASK_NONE = 0, B2_TASK_QUADRUPED_PARKOUR = 1 };
+
+/* Replaces mujoco.MjModel.from_xml_string(...) (quadruped_parkour_env/parkour_env.py:100 and the six sibling call
+ * sites): takes the packed device tables produced by the Python-side compiler (device_pack.pack_device_model) and
+ * uploads them (fp64 -> fp32) to `device`. */
+int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_flts, int device, B2Model** out);
+void b2_model_destroy(B2Model* m);
+
+/* Task description resolved by the host from names (the reference's mj_name2id lookups, parkour_env.py:181-232). */
+typedef struct B2TaskDesc {
+  int task;            /* B2_TASK_* */
+  int ids[16];
+  float act_lo[40], act_hi[40];
+} B2TaskDesc;
+
+/* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global
+ * index of this shard's env 0 so RNG streams do not depend on the number of GPUs.  threads_per_env in {32,64,128}. */
+int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, int threads_per_env,
+                    B2Batch** out);
+void b2_batch_destroy(B2Batch* b);
+
+/* dims (16 ints): [nq, nv, nu, nbody, obs_dim, act_dim, n_envs, nti, ntf, ncon_cap, smem_bytes, threads_per_env,
+ * row_cap, nM, 0, 0] */
+int b2_dims(const B2Batch* b, int* out16);
+
+/* Env.reset() for the envs whose mask byte is non-zero (NULL = all): mj_resetData + task reset + randomisation +
+ * settle steps + first observation (parkour_env.py:314-354).  inject_dev (nullable, [n_envs][4]) overrides the
+ * random draws so parity tests can reproduce the oracle's reset exactly. */
+int b2_reset(B2Batch* b, const uint8_t* mask_dev, const float* inject_dev, float* obs_dev, void* stream);
+
+/* Env.step(action) for all envs (parkour_env.py:356-394): clip, ctrl, frame_skip x mj_step, obs, reward,
+ * terminated, truncated, and same-step auto-reset; final_obs_dev (nullable) receives the pre-reset observation. */
+int b2_step(B2Batch* b, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* term_dev, uint8_t* trunc_dev,
+            float* final_obs_dev, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies actions in, steps, copies results out, synchronises.
+ * This is the end-to-end path a CPU-side caller of env.step would use. */
+int b2_step_host(B2Batch* b, const float* act, float* obs, float* rew, uint8_t* term, uint8_t* trunc);
+
+/* nsub x mujoco.mj_step(model, data) on the raw state, no task logic (parkour_env.py:348,368). */
+int b2_physics_step(B2Batch* b, int nsub, void* stream);
+/* mujoco.mj_forward(model, data) (humanoid_martial_arts_env/martial_arts_env.py:481): refreshes contacts / xpos. */
+int b2_forward(B2Batch* b, void* stream);
+
+/* data.qpos / qvel / ctrl / qacc_warmstart / time access (dense row-major [n_envs][dim] fp32 device arrays; any
+ * pointer may be NULL).  Doubles as checkpoint/restore. */
+int b2_get_state(B2Batch* b, float* qpos_dev, float* qvel_dev, float* ctrl_dev, float* warm_dev, float* time_dev, void* stream);
+int b2_set_state(B2Batch* b, const float* qpos_dev, const float* qvel_dev, const float* ctrl_dev, const float* warm_dev,
+                 const float* time_dev, void* stream);
+int b2_get_task_state(B2Batch* b, int32_t* ti_dev, float* tf_dev, void* stream);
+int b2_set_task_state(B2Batch* b, const int32_t* ti_dev, const float* tf_dev, void* stream);
+
+/* data.ncon / data.contact[i].geom1,geom2,dist of the last forward pass: ncon_dev [n_envs], geom_dev
+ * [n_envs][cap][2] (model geom ids), dist_dev [n_envs][cap]. */
+int b2_get_contacts(B2Batch* b, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int cap, void* stream);
+/* data.xpos of the last forward pass, [n_envs][nbody][3]. */
+int b2_get_xpos(B2Batch* b, float* xpos_dev, void* stream);
+
+/* Bring-up / test hook: mj_forward, then dump per env [qfrc_smooth|qacc_smooth|qfrc_constraint|qacc (nv each)|
+ * M (nM, sparse)|ncon nefc solver_iter 0|efc_force|efc_b|efc_R|efc_pos (row_cap each, island-major row order)]. */
+int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream);
+
+/* Episode statistics and engine counters summed over this shard into out_dev[16] (fp64), ready for an NCCL
+ * all-reduce: [episodes, return_sum, length_sum, nan_resets, contacts_dropped, rows_dropped, arena_overflows,
+ * solver_iters, substeps, 0...]. */
+int b2_stats(B2Batch* b, double* out_dev16, void* stream);
+
+/* kernels launched by this library since load (the bench's gpu_launches claim) */
+unsigned long long b2_launch_count(void);
+const char* b2_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

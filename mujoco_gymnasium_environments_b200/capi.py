@@ -1,0 +1,216 @@
+"""ctypes binding of libb2env.so (the C-ABI in include/b2env.h) plus a thin torch-tensor wrapper.
+
+The product path fails loudly when the CUDA library is missing or no GPU is present: there is no CPU fallback
+and nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libb2env.so")
+_LIB = None
+
+SYMBOLS = ["b2_model_create", "b2_model_destroy", "b2_batch_create", "b2_batch_destroy", "b2_dims", "b2_reset",
+           "b2_step", "b2_step_host", "b2_physics_step", "b2_forward", "b2_get_state", "b2_set_state",
+           "b2_get_task_state", "b2_set_task_state", "b2_get_contacts", "b2_get_xpos", "b2_debug_forward", "b2_stats",
+           "b2_launch_count", "b2_last_error"]
+
+TASK_NONE, TASK_QUADRUPED_PARKOUR = 0, 1
+
+
+class B2TaskDesc(ctypes.Structure):
+    _fields_ = [("task", ctypes.c_int), ("ids", ctypes.c_int * 16), ("act_lo", ctypes.c_float * 40),
+                ("act_hi", ctypes.c_float * 40)]
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ into libb2env.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("b2env.h", "b2_device_layout.h")]
+    stale = force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", src_dir, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise B2Error(f"{_SO} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(_SO)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.b2_model_create.argtypes = [vp, ci, vp, ci, ci, ctypes.POINTER(vp)]
+        L.b2_model_destroy.argtypes = [vp]; L.b2_model_destroy.restype = None
+        L.b2_batch_create.argtypes = [vp, ctypes.POINTER(B2TaskDesc), ci, ctypes.c_uint64, ci, ci, ctypes.POINTER(vp)]
+        L.b2_batch_destroy.argtypes = [vp]; L.b2_batch_destroy.restype = None
+        L.b2_dims.argtypes = [vp, vp]
+        L.b2_reset.argtypes = [vp, vp, vp, vp, vp]
+        L.b2_step.argtypes = [vp] * 8
+        L.b2_step_host.argtypes = [vp] * 6
+        L.b2_physics_step.argtypes = [vp, ci, vp]
+        L.b2_forward.argtypes = [vp, vp]
+        L.b2_get_state.argtypes = [vp] * 7; L.b2_set_state.argtypes = [vp] * 7
+        L.b2_get_task_state.argtypes = [vp] * 4; L.b2_set_task_state.argtypes = [vp] * 4
+        L.b2_get_contacts.argtypes = [vp, vp, vp, vp, ci, vp]
+        L.b2_get_xpos.argtypes = [vp, vp, vp]
+        L.b2_debug_forward.argtypes = [vp, vp, ci, vp]
+        L.b2_stats.argtypes = [vp, vp, vp]
+        L.b2_launch_count.restype = ctypes.c_ulonglong
+        L.b2_last_error.restype = ctypes.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _ck(rc: int):
+    if rc != 0:
+        raise B2Error(f"libb2env error {rc}: {lib().b2_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().b2_launch_count())
+
+
+class DeviceModel:
+    """``mujoco.MjModel`` stand-in living on one GPU."""
+
+    def __init__(self, tables, device: int = 0):
+        from .device_pack import pack_device_model
+        self.tables = tables
+        ints, flts = pack_device_model(tables)
+        self._ints = np.ascontiguousarray(ints, np.int32); self._flts = np.ascontiguousarray(flts, np.float64)
+        self.device = device
+        h = ctypes.c_void_p()
+        _ck(lib().b2_model_create(self._ints.ctypes.data, self._ints.size, self._flts.ctypes.data, self._flts.size,
+                                  device, ctypes.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().b2_model_destroy(self.handle); self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0) if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Batch:
+    """``mujoco.MjData`` x n_envs stand-in; all tensors are torch CUDA tensors on the model's device."""
+
+    def __init__(self, model: DeviceModel, task: Optional[B2TaskDesc], n_envs: int, seed: int = 0, env_offset: int = 0,
+                 threads_per_env: int = 128):
+        import torch
+        self.torch = torch
+        self.model = model
+        self.device = torch.device("cuda", model.device)
+        h = ctypes.c_void_p()
+        _ck(lib().b2_batch_create(model.handle, ctypes.byref(task) if task is not None else None, n_envs,
+                                  ctypes.c_uint64(seed & (2**64 - 1)), env_offset, threads_per_env, ctypes.byref(h)))
+        self.handle = h
+        d = (ctypes.c_int * 16)()
+        _ck(lib().b2_dims(self.handle, d))
+        (self.nq, self.nv, self.nu, self.nbody, self.obs_dim, self.act_dim, self.n_envs, self.nti, self.ntf, self.con_cap,
+         self.smem_bytes, self.threads_per_env, self.row_cap, self.nM) = [int(x) for x in d[:14]]
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new(self, shape, dtype=None):
+        return self.torch.empty(shape, dtype=dtype or self.torch.float32, device=self.device)
+
+    # ---- hot path
+    def reset(self, obs, mask=None, inject=None):
+        _ck(lib().b2_reset(self.handle, _ptr(mask), _ptr(inject), _ptr(obs), self._stream()))
+
+    def step(self, act, obs, rew, term, trunc, final_obs=None):
+        _ck(lib().b2_step(self.handle, _ptr(act), _ptr(obs), _ptr(rew), _ptr(term), _ptr(trunc), _ptr(final_obs), self._stream()))
+
+    def step_host(self, act: np.ndarray, obs: np.ndarray, rew: np.ndarray, term: np.ndarray, trunc: np.ndarray):
+        _ck(lib().b2_step_host(self.handle, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data))
+
+    def physics_step(self, nsub: int = 1):
+        _ck(lib().b2_physics_step(self.handle, nsub, self._stream()))
+
+    def forward(self):
+        _ck(lib().b2_forward(self.handle, self._stream()))
+
+    # ---- state access
+    def get_state(self):
+        q, v, c, w, t = (self._new((self.n_envs, self.nq)), self._new((self.n_envs, self.nv)),
+                         self._new((self.n_envs, max(self.nu, 1))), self._new((self.n_envs, self.nv)), self._new((self.n_envs,)))
+        _ck(lib().b2_get_state(self.handle, _ptr(q), _ptr(v), _ptr(c) if self.nu else None, _ptr(w), _ptr(t), self._stream()))
+        return dict(qpos=q, qvel=v, ctrl=c[:, :self.nu], qacc_warmstart=w, time=t)
+
+    def set_state(self, qpos=None, qvel=None, ctrl=None, qacc_warmstart=None, time=None):
+        f = lambda x: None if x is None else x.to(self.device, self.torch.float32).contiguous()
+        q, v, c, w, t = f(qpos), f(qvel), f(ctrl), f(qacc_warmstart), f(time)
+        _ck(lib().b2_set_state(self.handle, _ptr(q), _ptr(v), _ptr(c), _ptr(w), _ptr(t), self._stream()))
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def get_task_state(self):
+        ti = self._new((self.n_envs, max(self.nti, 1)), self.torch.int32); tf = self._new((self.n_envs, max(self.ntf, 1)))
+        _ck(lib().b2_get_task_state(self.handle, _ptr(ti), _ptr(tf), self._stream()))
+        return ti, tf
+
+    def set_task_state(self, ti=None, tf=None):
+        ti = None if ti is None else ti.to(self.device, self.torch.int32).contiguous()
+        tf = None if tf is None else tf.to(self.device, self.torch.float32).contiguous()
+        _ck(lib().b2_set_task_state(self.handle, _ptr(ti), _ptr(tf), self._stream()))
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def contacts(self, cap: Optional[int] = None):
+        cap = cap or self.con_cap
+        ncon = self._new((self.n_envs,), self.torch.int32); geom = self._new((self.n_envs, cap, 2), self.torch.int32)
+        dist = self._new((self.n_envs, cap))
+        geom.fill_(-1); dist.zero_()
+        _ck(lib().b2_get_contacts(self.handle, _ptr(ncon), _ptr(geom), _ptr(dist), cap, self._stream()))
+        return ncon, geom, dist
+
+    def xpos(self):
+        x = self._new((self.n_envs, self.nbody, 3))
+        _ck(lib().b2_get_xpos(self.handle, _ptr(x), self._stream()))
+        return x
+
+    def debug_forward(self):
+        n = 4 * self.nv + self.nM + 4 + 4 * self.row_cap
+        out = self._new((self.n_envs, n)); out.zero_()
+        _ck(lib().b2_debug_forward(self.handle, _ptr(out), n, self._stream()))
+        nv, nM, rc = self.nv, self.nM, self.row_cap
+        o = out
+        k = 4 * nv + nM
+        return dict(qfrc_smooth=o[:, 0:nv], qacc_smooth=o[:, nv:2 * nv], qfrc_constraint=o[:, 2 * nv:3 * nv],
+                    qacc=o[:, 3 * nv:4 * nv], M=o[:, 4 * nv:k], ncon=o[:, k].int(), nefc=o[:, k + 1].int(),
+                    solver_iter=o[:, k + 2].int(), efc_force=o[:, k + 4:k + 4 + rc], efc_b=o[:, k + 4 + rc:k + 4 + 2 * rc],
+                    efc_R=o[:, k + 4 + 2 * rc:k + 4 + 3 * rc], efc_pos=o[:, k + 4 + 3 * rc:k + 4 + 4 * rc])
+
+    def stats(self):
+        out = self._new((16,), self.torch.float64)
+        _ck(lib().b2_stats(self.handle, _ptr(out), self._stream()))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().b2_batch_destroy(self.handle); self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,425 @@
+// b2_api.cu -- the step kernel and the C-ABI declared in include/b2env.h (libb2env.so).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+#include "../../include/b2env.h"
+#include "b2_engine.cuh"
+#include "b2_tasks.cuh"
+
+using namespace b2;
+
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(B2_ERR_CUDA, std::string(#x ": ") + cudaGetErrorString(e_)); } while (0)
+
+struct B2Model {
+  int device; DevModel dm; int* d_ints; float* d_flts;
+  std::vector<int> h_ints;
+};
+struct B2Batch {
+  B2Model* m; int n_envs, T; TaskParams tp; BatchView v; size_t smem;
+  float* epstat;      // [N][4] episodes, return_sum, length_sum, (spare)
+  double* d_stats;
+  float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
+  float *d_act, *d_obs, *d_rew, *d_inject; uint8_t *d_term, *d_trunc;
+  cudaStream_t own_stream;
+  int obs_dim, act_dim, nti, ntf;
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int T, class Task>
+__global__ void __launch_bounds__(T) b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B,
+                                                   const __grid_constant__ TaskParams tp, int mode, float* epstat,
+                                                   const float* inject, size_t bar_off) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  int env = blockIdx.x;
+  if (env >= B.n_envs) return;
+  Engine<T> E(P);
+  ws_layout(P.dim, B.con_cap, B.row_cap, B.arena_floats, P.n_ints, P.n_flts, &E.w, smem);
+  E.conCap = B.con_cap; E.rowCap = B.row_cap; E.arenaFloats = B.arena_floats;
+  if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
+  E.stage_model(smem, bar_off);
+  const int tid = E.tid;
+  const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
+  unsigned long long* ctr = B.counters + (size_t)env * CTR_COUNT;
+  // ---- load the env's state rows (coalesced: consecutive threads read consecutive floats of one row)
+  {
+    const float* gq = B.qpos + (size_t)env * B.nqp; const float* gv = B.qvel + (size_t)env * B.nvp;
+    const float* gw = B.warm + (size_t)env * B.nvp; const float* gc = B.ctrl + (size_t)env * B.nup;
+    const float* ga = B.qfrc_applied + (size_t)env * B.nvp;
+    for (int i = tid; i < nq; i += T) E.w.qpos[i] = gq[i];
+    for (int i = tid; i < nv; i += T) { E.w.qvel[i] = gv[i]; E.w.warm[i] = gw[i]; E.w.qapp[i] = ga[i]; }
+    for (int i = tid; i < nu; i += T) E.w.ctrl[i] = gc[i];
+    if (tid == 0) { *E.w.time = B.time[env]; E.w.misc[MISC_NCON] = 0; E.w.misc[MISC_NEFC] = 0; E.w.misc[MISC_FLAG] = 0; }
+  }
+  __shared__ int s_ti[16]; __shared__ float s_tf[8]; __shared__ float s_act[40]; __shared__ int s_done[2]; __shared__ float s_rew;
+  if (Task::NTI > 0) {
+    if (tid < Task::NTI) s_ti[tid] = B.ti[(size_t)env * B.nti + tid];
+    if (tid < Task::NTF) s_tf[tid] = B.tf[(size_t)env * B.ntf + tid];
+  }
+  E.sync();
+
+  if (mode == MODE_PHYS) {
+    for (int s = 0; s < B.nsub; s++) E.step_euler(ctr);
+  } else if (mode == MODE_FORWARD) {
+    E.forward(ctr);
+  } else if (mode == MODE_RESET) {
+    Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr);
+    for (int s = 0; s < Task::SETTLE; s++) E.step_euler(ctr);
+    Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+  } else {  // MODE_STEP
+    Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act);
+    for (int s = 0; s < Task::FRAME_SKIP; s++) E.step_euler(ctr);
+    Task::post_physics(E, tp, s_ti);
+    Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+    E.sync();
+    if (tid == 0) {
+      int term = 0, trunc = 0;
+      s_rew = Task::reward_and_done(E, tp, s_act, s_ti, s_tf, &term, &trunc);
+      s_done[0] = term; s_done[1] = trunc;
+      B.reward[env] = s_rew; B.term[env] = (uint8_t)term; B.trunc[env] = (uint8_t)trunc;
+    }
+    E.sync();
+    if (s_done[0] || s_done[1]) {
+      // same-step auto-reset: keep the terminal observation, account the episode, start the next one
+      if (B.final_obs) for (int i = tid; i < Task::OBS; i += T) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
+      if (tid == 0) {
+        epstat[4 * env + 0] += 1.f; epstat[4 * env + 1] += s_tf[0]; epstat[4 * env + 2] += (float)s_ti[0];
+        atomicAdd(&ctr[CTR_EPISODES], 1ull);
+      }
+      E.sync();
+      Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
+      for (int s = 0; s < Task::SETTLE; s++) E.step_euler(ctr);
+      Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+    }
+  }
+  E.sync();
+  // ---- optional exports of the last forward pass
+  if (B.c_ncon) {
+    int ncon = E.w.misc[MISC_NCON];
+    const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+    if (tid == 0) B.c_ncon[env] = ncon;
+    for (int c = tid; c < ncon && c < B.c_cap; c += T) {
+      int p = __float_as_int(E.w.con[B2_CON_STRIDE * c + 13]);
+      B.c_geom[((size_t)env * B.c_cap + c) * 2] = gid[pc1[p]]; B.c_geom[((size_t)env * B.c_cap + c) * 2 + 1] = gid[pc2[p]];
+      B.c_dist[(size_t)env * B.c_cap + c] = E.w.con[B2_CON_STRIDE * c];
+    }
+  }
+  if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = tid; i < n; i += T) B.xpos_out[(size_t)env * n + i] = E.w.xpos[i]; }
+  if (B.debug_out) {
+    // layout: qfs | qas | qfc | qacc (nv each) | M (nM) | ncon nefc iters 0 | row_f | row_b | row_R | row_pos (row_cap each)
+    float* o = B.debug_out + (size_t)env * B.debug_n; int nM = P.dim[DD_nM], k = 0;
+    auto put = [&](const float* src, int n) { for (int i = tid; i < n; i += T) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
+    put(E.w.qfs, nv); put(E.w.qas, nv); put(E.w.qfc, nv); put(E.w.qacc, nv); put(E.w.M, nM);
+    if (tid == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.w.misc[MISC_NCON]; o[k + 1] = (float)E.w.misc[MISC_NEFC]; o[k + 2] = (float)E.w.misc[MISC_ITERS]; o[k + 3] = 0.f; }
+    k += 4;
+    put(E.w.row_f, B.row_cap); put(E.w.row_b, B.row_cap); put(E.w.row_R, B.row_cap); put(E.w.row_pos, B.row_cap);
+  }
+  // ---- store state
+  if (mode != MODE_FORWARD) {
+    float* gq = B.qpos + (size_t)env * B.nqp; float* gv = B.qvel + (size_t)env * B.nvp;
+    float* gw = B.warm + (size_t)env * B.nvp; float* gc = B.ctrl + (size_t)env * B.nup;
+    float* ga = B.qfrc_applied + (size_t)env * B.nvp;
+    for (int i = tid; i < nq; i += T) gq[i] = E.w.qpos[i];
+    for (int i = tid; i < nv; i += T) { gv[i] = E.w.qvel[i]; gw[i] = E.w.warm[i]; ga[i] = E.w.qapp[i]; }
+    for (int i = tid; i < nu; i += T) gc[i] = E.w.ctrl[i];
+    if (tid == 0) B.time[env] = *E.w.time;
+    if (Task::NTI > 0) {
+      if (tid < Task::NTI) B.ti[(size_t)env * B.nti + tid] = s_ti[tid];
+      if (tid < Task::NTF) B.tf[(size_t)env * B.ntf + tid] = s_tf[tid];
+    }
+  }
+}
+
+// a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
+struct NoTask {
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0;
+  template <int T> __device__ static void apply_action(Engine<T>&, const TaskParams&, const float*, float*) {}
+  template <int T> __device__ static void reset_state(Engine<T>& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
+    E.reset_data(); if (E.tid == 0) *E.w.time = 0.f; E.sync();
+  }
+  template <int T> __device__ static void observe(Engine<T>&, const TaskParams&, float*) {}
+  template <int T> __device__ static float reward_and_done(Engine<T>&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
+  template <int T> __device__ static void post_physics(Engine<T>&, const TaskParams&, const int*) {}
+};
+
+__global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
+  __shared__ double acc[16];
+  if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  double loc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    loc[0] += epstat[4 * e]; loc[1] += epstat[4 * e + 1]; loc[2] += epstat[4 * e + 2];
+    const unsigned long long* c = counters + (size_t)e * CTR_COUNT;
+    loc[3] += (double)c[CTR_NAN_RESET]; loc[4] += (double)c[CTR_CON_DROPPED]; loc[5] += (double)c[CTR_ROW_DROPPED];
+    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS];
+  }
+  for (int k = 0; k < 9; k++) atomicAdd(&acc[k], loc[k]);
+  __syncthreads();
+  if (threadIdx.x < 16) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int T, class Task>
+static int launch_T(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  auto kern = b2_env_kernel<T, Task>;
+  static thread_local size_t configured = 0;
+  if (configured < b->smem) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)); configured = b->smem; }
+  kern<<<b->n_envs, T, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject, b->smem - 16);
+  g_launches++;
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+template <class Task>
+static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  switch (b->T) {
+    case 32: return launch_T<32, Task>(b, mode, inject, s);
+    case 64: return launch_T<64, Task>(b, mode, inject, s);
+    case 128: return launch_T<128, Task>(b, mode, inject, s);
+  }
+  return fail(B2_ERR_ARG, "threads_per_env must be 32, 64 or 128");
+}
+static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  CK(cudaSetDevice(b->m->device));
+  switch (b->tp.task) {
+    case TASK_NONE: return launch_task<NoTask>(b, mode, inject, s);
+    case TASK_QUADRUPED_PARKOUR: return launch_task<QuadrupedTask>(b, mode, inject, s);
+  }
+  return fail(B2_ERR_UNSUPPORTED, "unknown task id");
+}
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+unsigned long long b2_launch_count(void) { return g_launches.load(); }
+
+int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_flts, int device, B2Model** out) {
+  if (!ints || !flts || !out) return fail(B2_ERR_ARG, "null argument");
+  if (n_ints < 4 || ints[0] != (int)B2DEV_MAGIC || ints[1] != B2DEV_N_INT_FIELDS || ints[2] != B2DEV_N_FLT_FIELDS)
+    return fail(B2_ERR_LAYOUT, "packed device model does not match include/b2_device_layout.h");
+  if ((n_ints & 3) || (n_flts & 3)) return fail(B2_ERR_LAYOUT, "buffers must be padded to 4 elements");
+  int ndev = 0; CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B2_ERR_ARG, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  B2Model* m = new B2Model(); m->device = device; m->h_ints.assign(ints, ints + n_ints);
+  DevModel& dm = m->dm; memset(&dm, 0, sizeof(dm));
+  for (int k = 0; k < B2DEV_N_INT_FIELDS; k++) dm.ioff[k] = ints[4 + 2 * k];
+  for (int k = 0; k < B2DEV_N_FLT_FIELDS; k++) dm.foff[k] = ints[4 + 2 * (B2DEV_N_INT_FIELDS + k)];
+  const int* dims = ints + dm.ioff[DI_dims];
+  int ndims = ints[5 + 2 * DI_dims];
+  if (ndims != DD_COUNT) { delete m; return fail(B2_ERR_LAYOUT, "dims field has the wrong length"); }
+  for (int k = 0; k < DD_COUNT; k++) dm.dim[k] = dims[k];
+  const double* opt = flts + dm.foff[DF_opt];
+  for (int k = 0; k < DO_COUNT; k++) dm.opt[k] = (float)opt[k];
+  if (dm.dim[DD_integrator] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the Euler integrator is built in this round"); }
+  if (dm.dim[DD_solver] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the PGS solver is built in this round"); }
+  if (dm.dim[DD_nisland] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "too many islands"); }
+  std::vector<float> f32(n_flts);
+  for (int i = 0; i < n_flts; i++) f32[i] = (float)flts[i];
+  CK(cudaMalloc(&m->d_ints, sizeof(int) * n_ints)); CK(cudaMalloc(&m->d_flts, sizeof(float) * n_flts));
+  CK(cudaMemcpy(m->d_ints, ints, sizeof(int) * n_ints, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(m->d_flts, f32.data(), sizeof(float) * n_flts, cudaMemcpyHostToDevice));
+  dm.ints = m->d_ints; dm.flts = m->d_flts; dm.n_ints = n_ints; dm.n_flts = n_flts;
+  *out = m;
+  return B2_OK;
+}
+void b2_model_destroy(B2Model* m) { if (!m) return; cudaSetDevice(m->device); cudaFree(m->d_ints); cudaFree(m->d_flts); delete m; }
+
+int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, int threads_per_env,
+                    B2Batch** out) {
+  if (!m || !out || n_envs <= 0) return fail(B2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(m->device));
+  B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
+  b->m = m; b->n_envs = n_envs; b->T = threads_per_env > 0 ? threads_per_env : 128;
+  memset(&b->tp, 0, sizeof(b->tp));
+  if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
+  switch (b->tp.task) {
+    case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
+    case TASK_QUADRUPED_PARKOUR: b->obs_dim = QuadrupedTask::OBS; b->act_dim = QuadrupedTask::ACT; b->nti = QuadrupedTask::NTI; b->ntf = QuadrupedTask::NTF; break;
+    default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
+  }
+  const int* dim = m->dm.dim;
+  BatchView& v = b->v; memset(&v, 0, sizeof(v));
+  v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
+  v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
+  v.seed = seed; v.env_offset = env_offset;
+  // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped; rows: 4 per contact + limits)
+  v.con_cap = dim[DD_maxraw] < 48 ? dim[DD_maxraw] : 48; if (v.con_cap < 1) v.con_cap = 1;
+  v.row_cap = 4 * v.con_cap + 2 * dim[DD_nlim]; if (v.row_cap > 256) v.row_cap = 256; if (v.row_cap < 4) v.row_cap = 4;
+  int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
+  for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
+  int raw_need = r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
+  int arena = 15360 + (b->T / 32) * 33 * maxspan;
+  if (arena < raw_need) arena = raw_need;
+  v.arena_floats = r4(arena);
+  b->smem = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, m->dm.n_ints, m->dm.n_flts, nullptr, nullptr);
+  if (b->smem > 227 * 1024) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
+  size_t N = n_envs;
+  CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));
+  CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
+  CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
+  CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 4)); CK(cudaMalloc(&b->d_stats, 16 * 8));
+  CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));
+  CK(cudaMemset(v.ctrl, 0, N * v.nup * 4)); CK(cudaMemset(v.time, 0, N * 4)); CK(cudaMemset(v.ti, 0, N * v.nti * 4));
+  CK(cudaMemset(v.tf, 0, N * v.ntf * 4)); CK(cudaMemset(v.counters, 0, N * CTR_COUNT * 8)); CK(cudaMemset(b->epstat, 0, N * 16));
+  // qpos <- qpos0
+  {
+    std::vector<float> q((size_t)N * v.nqp, 0.f);
+    std::vector<float> q0(dim[DD_nq]);
+    CK(cudaMemcpy(q0.data(), m->d_flts + m->dm.foff[DF_qpos0], sizeof(float) * dim[DD_nq], cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < N; e++) memcpy(&q[e * v.nqp], q0.data(), sizeof(float) * dim[DD_nq]);
+    CK(cudaMemcpy(v.qpos, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // staging for the host-buffer entry point
+  size_t od = b->obs_dim > 0 ? b->obs_dim : 1, ad = b->act_dim > 0 ? b->act_dim : 1;
+  CK(cudaMallocHost(&b->h_act, N * ad * 4)); CK(cudaMallocHost(&b->h_obs, N * od * 4)); CK(cudaMallocHost(&b->h_rew, N * 4));
+  CK(cudaMallocHost(&b->h_term, N)); CK(cudaMallocHost(&b->h_trunc, N));
+  CK(cudaMalloc(&b->d_act, N * ad * 4)); CK(cudaMalloc(&b->d_obs, N * od * 4)); CK(cudaMalloc(&b->d_rew, N * 4));
+  CK(cudaMalloc(&b->d_term, N)); CK(cudaMalloc(&b->d_trunc, N)); CK(cudaMalloc(&b->d_inject, N * 4 * 4));
+  CK(cudaStreamCreate(&b->own_stream));
+  *out = b;
+  return B2_OK;
+}
+void b2_batch_destroy(B2Batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->m->device);
+  BatchView& v = b->v;
+  cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
+  cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
+  cudaFreeHost(b->h_act); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_rew); cudaFreeHost(b->h_term); cudaFreeHost(b->h_trunc);
+  cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term); cudaFree(b->d_trunc); cudaFree(b->d_inject);
+  cudaStreamDestroy(b->own_stream);
+  delete b;
+}
+
+int b2_dims(const B2Batch* b, int* o) {  /* o has 16 entries */
+  if (!b || !o) return fail(B2_ERR_ARG, "null argument");
+  const int* d = b->m->dm.dim;
+  o[0] = d[DD_nq]; o[1] = d[DD_nv]; o[2] = d[DD_nu]; o[3] = d[DD_nbody]; o[4] = b->obs_dim; o[5] = b->act_dim; o[6] = b->n_envs;
+  o[7] = b->nti; o[8] = b->ntf; o[9] = b->v.con_cap; o[10] = (int)b->smem; o[11] = b->T; o[12] = b->v.row_cap; o[13] = b->m->dm.dim[DD_nM];
+  return B2_OK;
+}
+
+int b2_reset(B2Batch* b, const uint8_t* mask_dev, const float* inject_dev, float* obs_dev, void* stream) {
+  if (!b || !obs_dev) return fail(B2_ERR_ARG, "null argument");
+  if (b->tp.task == TASK_NONE) return fail(B2_ERR_UNSUPPORTED, "batch has no task; use b2_set_state");
+  b->v.reset_mask = mask_dev; b->v.obs = obs_dev; b->v.final_obs = nullptr; b->v.c_ncon = nullptr; b->v.xpos_out = nullptr;
+  return launch(b, MODE_RESET, inject_dev, (cudaStream_t)stream);
+}
+int b2_step(B2Batch* b, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* term_dev, uint8_t* trunc_dev,
+            float* final_obs_dev, void* stream) {
+  if (!b || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(B2_ERR_ARG, "null argument");
+  if (b->tp.task == TASK_NONE) return fail(B2_ERR_UNSUPPORTED, "batch has no task; use b2_physics_step");
+  BatchView& v = b->v;
+  v.action = act_dev; v.obs = obs_dev; v.reward = rew_dev; v.term = term_dev; v.trunc = trunc_dev; v.final_obs = final_obs_dev;
+  v.reset_mask = nullptr; v.c_ncon = nullptr; v.xpos_out = nullptr;
+  return launch(b, MODE_STEP, nullptr, (cudaStream_t)stream);
+}
+int b2_step_host(B2Batch* b, const float* act, float* obs, float* rew, uint8_t* term, uint8_t* trunc) {
+  if (!b || !act || !obs || !rew || !term || !trunc) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  size_t N = b->n_envs; cudaStream_t s = b->own_stream;
+  memcpy(b->h_act, act, N * b->act_dim * 4);
+  CK(cudaMemcpyAsync(b->d_act, b->h_act, N * b->act_dim * 4, cudaMemcpyHostToDevice, s));
+  int rc = b2_step(b, b->d_act, b->d_obs, b->d_rew, b->d_term, b->d_trunc, nullptr, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(b->h_obs, b->d_obs, N * b->obs_dim * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(b->h_rew, b->d_rew, N * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(b->h_term, b->d_term, N, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(b->h_trunc, b->d_trunc, N, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(obs, b->h_obs, N * b->obs_dim * 4); memcpy(rew, b->h_rew, N * 4); memcpy(term, b->h_term, N); memcpy(trunc, b->h_trunc, N);
+  return B2_OK;
+}
+int b2_physics_step(B2Batch* b, int nsub, void* stream) {
+  if (!b || nsub < 0) return fail(B2_ERR_ARG, "bad argument");
+  b->v.nsub = nsub; b->v.c_ncon = nullptr; b->v.xpos_out = nullptr;
+  return launch(b, MODE_PHYS, nullptr, (cudaStream_t)stream);
+}
+int b2_forward(B2Batch* b, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  b->v.c_ncon = nullptr; b->v.xpos_out = nullptr;
+  return launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+}
+
+static int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t s) {
+  CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, s));
+  return B2_OK;
+}
+int b2_get_state(B2Batch* b, float* q, float* qv, float* c, float* wm, float* t, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  const int* d = b->m->dm.dim; BatchView& v = b->v; cudaStream_t s = (cudaStream_t)stream; size_t N = b->n_envs; int rc = 0;
+  if (q) rc |= copy2d(q, d[DD_nq] * 4, v.qpos, v.nqp * 4, d[DD_nq] * 4, N, s);
+  if (qv) rc |= copy2d(qv, d[DD_nv] * 4, v.qvel, v.nvp * 4, d[DD_nv] * 4, N, s);
+  if (c && d[DD_nu]) rc |= copy2d(c, d[DD_nu] * 4, v.ctrl, v.nup * 4, d[DD_nu] * 4, N, s);
+  if (wm) rc |= copy2d(wm, d[DD_nv] * 4, v.warm, v.nvp * 4, d[DD_nv] * 4, N, s);
+  if (t) CK(cudaMemcpyAsync(t, v.time, N * 4, cudaMemcpyDeviceToDevice, s));
+  return rc ? B2_ERR_CUDA : B2_OK;
+}
+int b2_set_state(B2Batch* b, const float* q, const float* qv, const float* c, const float* wm, const float* t, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  const int* d = b->m->dm.dim; BatchView& v = b->v; cudaStream_t s = (cudaStream_t)stream; size_t N = b->n_envs; int rc = 0;
+  if (q) rc |= copy2d(v.qpos, v.nqp * 4, q, d[DD_nq] * 4, d[DD_nq] * 4, N, s);
+  if (qv) rc |= copy2d(v.qvel, v.nvp * 4, qv, d[DD_nv] * 4, d[DD_nv] * 4, N, s);
+  if (c && d[DD_nu]) rc |= copy2d(v.ctrl, v.nup * 4, c, d[DD_nu] * 4, d[DD_nu] * 4, N, s);
+  if (wm) rc |= copy2d(v.warm, v.nvp * 4, wm, d[DD_nv] * 4, d[DD_nv] * 4, N, s);
+  if (t) CK(cudaMemcpyAsync(v.time, t, N * 4, cudaMemcpyDeviceToDevice, s));
+  return rc ? B2_ERR_CUDA : B2_OK;
+}
+int b2_get_task_state(B2Batch* b, int32_t* ti, float* tf, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  size_t N = b->n_envs; cudaStream_t s = (cudaStream_t)stream;
+  if (ti && b->nti) CK(cudaMemcpyAsync(ti, b->v.ti, N * b->v.nti * 4, cudaMemcpyDeviceToDevice, s));
+  if (tf && b->ntf) CK(cudaMemcpyAsync(tf, b->v.tf, N * b->v.ntf * 4, cudaMemcpyDeviceToDevice, s));
+  return B2_OK;
+}
+int b2_set_task_state(B2Batch* b, const int32_t* ti, const float* tf, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  size_t N = b->n_envs; cudaStream_t s = (cudaStream_t)stream;
+  if (ti && b->nti) CK(cudaMemcpyAsync(b->v.ti, ti, N * b->v.nti * 4, cudaMemcpyDeviceToDevice, s));
+  if (tf && b->ntf) CK(cudaMemcpyAsync(b->v.tf, tf, N * b->v.ntf * 4, cudaMemcpyDeviceToDevice, s));
+  return B2_OK;
+}
+int b2_get_contacts(B2Batch* b, int32_t* ncon, int32_t* geom, float* dist, int cap, void* stream) {
+  if (!b || !ncon || !geom || !dist || cap <= 0) return fail(B2_ERR_ARG, "bad argument");
+  b->v.c_ncon = ncon; b->v.c_geom = geom; b->v.c_dist = dist; b->v.c_cap = cap; b->v.xpos_out = nullptr;
+  int rc = launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+  b->v.c_ncon = nullptr;
+  return rc;
+}
+int b2_get_xpos(B2Batch* b, float* xpos, void* stream) {
+  if (!b || !xpos) return fail(B2_ERR_ARG, "bad argument");
+  b->v.c_ncon = nullptr; b->v.xpos_out = xpos;
+  int rc = launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+  b->v.xpos_out = nullptr;
+  return rc;
+}
+int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream) {
+  if (!b || !out_dev || n_per_env <= 0) return fail(B2_ERR_ARG, "bad argument");
+  b->v.c_ncon = nullptr; b->v.xpos_out = nullptr; b->v.debug_out = out_dev; b->v.debug_n = n_per_env;
+  int rc = launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+  b->v.debug_out = nullptr;
+  return rc;
+}
+int b2_stats(B2Batch* b, double* out, void* stream) {
+  if (!b || !out) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(out, 0, 16 * 8, s));
+  int blocks = (b->n_envs + 255) / 256; if (blocks > 148) blocks = 148;
+  b2_stats_kernel<<<blocks, 256, 0, s>>>(b->v.counters, b->epstat, b->n_envs, out);
+  g_launches++;
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+}  // extern "C"

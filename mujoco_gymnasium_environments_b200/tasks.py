@@ -1,0 +1,84 @@
+"""Host-side task registry: model tables + the name lookups each reference env performs in its constructor.
+
+For every task this resolves the reference's ``mj_name2id`` calls into integer ids once
+and fills the ``B2TaskDesc`` the kernels read, so no string ever reaches the device.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Callable, Dict, List
+
+import numpy as np
+
+from . import capi
+from .mjcf import ModelTables, compile_mjcf
+from .spaces import Box
+
+_TABLES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tables")
+
+
+@dataclass
+class TaskSpec:
+    name: str
+    task_id: int
+    obs_dim: int
+    act_dim: int
+    max_episode_steps: int
+    frame_skip: int
+    render_fps: int
+    bytes_per_env_step: int          # SURVEY 8(d) algorithmic HBM bytes
+    describe: Callable[[ModelTables], capi.B2TaskDesc]
+    action_space: Callable[[ModelTables], Box]
+    observation_space: Callable[[ModelTables], Box]
+    info_keys: List[str]
+
+
+def load_tables(task: str, assets_root: str | None = None) -> ModelTables:
+    """Committed tables by default; recompile from the reference's assets when ``assets_root`` is given."""
+    if assets_root is not None:
+        from .compose import COMPOSERS
+        return compile_mjcf(COMPOSERS[task](assets_root), name=task)
+    return ModelTables.load(os.path.join(_TABLES, task + ".npz"))
+
+
+# ---------------------------------------------------------------------------------------------- quadruped parkour
+def _quad_limits(t: ModelTables) -> np.ndarray:
+    # parkour_env.py:236-249: +-80 for names containing "hip", 60 "knee", 40 "ankle"
+    lim = []
+    for n in t.names["joint"][1:17]:
+        lim.append(80.0 if "hip" in n else 60.0 if "knee" in n else 40.0)
+    return np.array(lim, np.float32)
+
+
+def _quad_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_QUADRUPED_PARKOUR
+    ids = [t.name2id("body", "torso")] + [t.name2id("body", n) for n in ("fl_foot", "fr_foot", "bl_foot", "br_foot")]
+    ids += [t.name2id("joint", "platform_slide"), t.name2id("joint", "pendulum_swing"),
+            t.name2id("actuator", "platform_motor"), t.name2id("actuator", "pendulum_motor")]
+    for k, v in enumerate(ids):
+        d.ids[k] = v
+    lim = _quad_limits(t)
+    for k in range(16):
+        d.act_lo[k] = -lim[k]; d.act_hi[k] = lim[k]
+    return d
+
+
+def _quad_obs_space(t: ModelTables) -> Box:
+    # parkour_env.py:260-287
+    lo = np.full(95, -np.inf, np.float32); hi = np.full(95, np.inf, np.float32)
+    lo[0:16] = -np.pi; hi[0:16] = np.pi; lo[16:32] = -20.0; hi[16:32] = 20.0; lo[32:36] = -1.0; hi[32:36] = 1.0
+    lo[48:52] = 0.0; hi[48:52] = 1.0; lo[64:88] = 0.0; hi[64:88] = 10.0
+    return Box(lo, hi, dtype=np.float32)
+
+
+TASKS: Dict[str, TaskSpec] = {
+    "quadruped_parkour": TaskSpec(
+        name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
+        frame_skip=10, render_fps=100, bytes_per_env_step=1426, describe=_quad_desc,
+        action_space=lambda t: Box(-_quad_limits(t), _quad_limits(t), dtype=np.float32),
+        observation_space=_quad_obs_space,
+        info_keys=["step_count", "episode_reward", "max_forward_progress", "checkpoints_reached", "fall_count",
+                   "course_completion"]),
+}
