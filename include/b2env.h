@@ -35,14 +35,24 @@ typedef struct B2TaskDesc {
   float act_lo[40], act_hi[40];
 } B2TaskDesc;
 
+/* Fixed capacities of the per-env on-chip buffers; 0 = library default.  Contacts / rows beyond a capacity are
+ * dropped and counted (b2_stats), never silently. */
+typedef struct B2BatchOpts {
+  int envs_per_block;  /* warps (= envs) per CTA sharing one staged model copy */
+  int arena_floats;    /* per-env shared-memory arena holding J and the packed A of every island */
+  int con_cap;         /* contact buffer capacity per env */
+  int row_cap;         /* constraint-row capacity per env */
+  int reserved[4];
+} B2BatchOpts;
+
 /* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global
- * index of this shard's env 0 so RNG streams do not depend on the number of GPUs.  threads_per_env in {32,64,128}. */
-int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, int threads_per_env,
+ * index of this shard's env 0 so RNG streams do not depend on the number of GPUs.  opts may be NULL. */
+int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, const B2BatchOpts* opts,
                     B2Batch** out);
 void b2_batch_destroy(B2Batch* b);
 
-/* dims (16 ints): [nq, nv, nu, nbody, obs_dim, act_dim, n_envs, nti, ntf, ncon_cap, smem_bytes, threads_per_env,
- * row_cap, nM, 0, 0] */
+/* dims (16 ints): [nq, nv, nu, nbody, obs_dim, act_dim, n_envs, nti, ntf, con_cap, smem_bytes_per_cta, envs_per_block,
+ * row_cap, nM, arena_floats, smem_bytes_per_env] */
 int b2_dims(const B2Batch* b, int* out16);
 
 /* Env.reset() for the envs whose mask byte is non-zero (NULL = all): mj_resetData + task reset + randomisation +
@@ -84,7 +94,7 @@ int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream);
 
 /* Episode statistics and engine counters summed over this shard into out_dev[16] (fp64), ready for an NCCL
  * all-reduce: [episodes, return_sum, length_sum, nan_resets, contacts_dropped, rows_dropped, arena_overflows,
- * solver_iters, substeps, 0...]. */
+ * solver_iters, substeps, arena_spills, 0...]. */
 int b2_stats(B2Batch* b, double* out_dev16, void* stream);
 
 /* kernels launched by this library since load (the bench's gpu_launches claim) */

@@ -29,6 +29,11 @@ class B2TaskDesc(ctypes.Structure):
                 ("act_hi", ctypes.c_float * 40)]
 
 
+class B2BatchOpts(ctypes.Structure):
+    _fields_ = [("envs_per_block", ctypes.c_int), ("arena_floats", ctypes.c_int), ("con_cap", ctypes.c_int),
+                ("row_cap", ctypes.c_int), ("reserved", ctypes.c_int * 4)]
+
+
 class B2Error(RuntimeError):
     pass
 
@@ -53,7 +58,7 @@ def lib():
         vp, ci = ctypes.c_void_p, ctypes.c_int
         L.b2_model_create.argtypes = [vp, ci, vp, ci, ci, ctypes.POINTER(vp)]
         L.b2_model_destroy.argtypes = [vp]; L.b2_model_destroy.restype = None
-        L.b2_batch_create.argtypes = [vp, ctypes.POINTER(B2TaskDesc), ci, ctypes.c_uint64, ci, ci, ctypes.POINTER(vp)]
+        L.b2_batch_create.argtypes = [vp, ctypes.POINTER(B2TaskDesc), ci, ctypes.c_uint64, ci, ctypes.POINTER(B2BatchOpts), ctypes.POINTER(vp)]
         L.b2_batch_destroy.argtypes = [vp]; L.b2_batch_destroy.restype = None
         L.b2_dims.argtypes = [vp, vp]
         L.b2_reset.argtypes = [vp, vp, vp, vp, vp]
@@ -115,19 +120,22 @@ class Batch:
     """``mujoco.MjData`` x n_envs stand-in; all tensors are torch CUDA tensors on the model's device."""
 
     def __init__(self, model: DeviceModel, task: Optional[B2TaskDesc], n_envs: int, seed: int = 0, env_offset: int = 0,
-                 threads_per_env: int = 128):
+                 envs_per_block: int = 0, arena_floats: int = 0, con_cap: int = 0, row_cap: int = 0):
         import torch
         self.torch = torch
         self.model = model
         self.device = torch.device("cuda", model.device)
         h = ctypes.c_void_p()
+        opts = B2BatchOpts()
+        opts.envs_per_block = int(os.environ.get("B2_EPB", envs_per_block)); opts.arena_floats = int(os.environ.get("B2_ARENA", arena_floats))
+        opts.con_cap = int(os.environ.get("B2_CON_CAP", con_cap)); opts.row_cap = int(os.environ.get("B2_ROW_CAP", row_cap))
         _ck(lib().b2_batch_create(model.handle, ctypes.byref(task) if task is not None else None, n_envs,
-                                  ctypes.c_uint64(seed & (2**64 - 1)), env_offset, threads_per_env, ctypes.byref(h)))
+                                  ctypes.c_uint64(seed & (2**64 - 1)), env_offset, ctypes.byref(opts), ctypes.byref(h)))
         self.handle = h
         d = (ctypes.c_int * 16)()
         _ck(lib().b2_dims(self.handle, d))
         (self.nq, self.nv, self.nu, self.nbody, self.obs_dim, self.act_dim, self.n_envs, self.nti, self.ntf, self.con_cap,
-         self.smem_bytes, self.threads_per_env, self.row_cap, self.nM) = [int(x) for x in d[:14]]
+         self.smem_bytes, self.envs_per_block, self.row_cap, self.nM, self.arena_floats, self.ws_bytes) = [int(x) for x in d[:16]]
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

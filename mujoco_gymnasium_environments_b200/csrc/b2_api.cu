@@ -22,7 +22,7 @@ struct B2Model {
   std::vector<int> h_ints;
 };
 struct B2Batch {
-  B2Model* m; int n_envs, T; TaskParams tp; BatchView v; size_t smem;
+  B2Model* m; int n_envs; TaskParams tp; BatchView v; size_t smem;
   float* epstat;      // [N][4] episodes, return_sum, length_sum, (spare)
   double* d_stats;
   float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
@@ -32,106 +32,107 @@ struct B2Batch {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int T, class Task>
-__global__ void __launch_bounds__(T) b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B,
-                                                   const __grid_constant__ TaskParams tp, int mode, float* epstat,
-                                                   const float* inject, size_t bar_off) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  int env = blockIdx.x;
+// grid = ceil(n_envs / E) CTAs of E warps; warp w of CTA c steps env c*E + w.  Shared memory: [model | E workspaces | mbarrier].
+template <class Task>
+__global__ void __launch_bounds__(256, 1) b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B,
+                                                     const __grid_constant__ TaskParams tp, int mode, float* epstat,
+                                                     const float* inject) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
+  stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints), bar);
+  const int env = blockIdx.x * B.envs_per_block + warp;
   if (env >= B.n_envs) return;
-  Engine<T> E(P);
-  ws_layout(P.dim, B.con_cap, B.row_cap, B.arena_floats, P.n_ints, P.n_flts, &E.w, smem);
-  E.conCap = B.con_cap; E.rowCap = B.row_cap; E.arenaFloats = B.arena_floats;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  E.stage_model(smem, bar_off);
-  const int tid = E.tid;
+  Engine E(P, B, B.model_floats + warp * B.ws_floats);
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
   unsigned long long* ctr = B.counters + (size_t)env * CTR_COUNT;
-  // ---- load the env's state rows (coalesced: consecutive threads read consecutive floats of one row)
+  int* s_ti = E.p_ti(); float* s_tf = E.p_tf(); float* s_act = E.p_act();
+  // ---- load the env's state rows (coalesced: the warp's lanes read consecutive floats of one row)
   {
     const float* gq = B.qpos + (size_t)env * B.nqp; const float* gv = B.qvel + (size_t)env * B.nvp;
     const float* gw = B.warm + (size_t)env * B.nvp; const float* gc = B.ctrl + (size_t)env * B.nup;
     const float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = tid; i < nq; i += T) E.w.qpos[i] = gq[i];
-    for (int i = tid; i < nv; i += T) { E.w.qvel[i] = gv[i]; E.w.warm[i] = gw[i]; E.w.qapp[i] = ga[i]; }
-    for (int i = tid; i < nu; i += T) E.w.ctrl[i] = gc[i];
-    if (tid == 0) { *E.w.time = B.time[env]; E.w.misc[MISC_NCON] = 0; E.w.misc[MISC_NEFC] = 0; E.w.misc[MISC_FLAG] = 0; }
-  }
-  __shared__ int s_ti[16]; __shared__ float s_tf[8]; __shared__ float s_act[40]; __shared__ int s_done[2]; __shared__ float s_rew;
-  if (Task::NTI > 0) {
-    if (tid < Task::NTI) s_ti[tid] = B.ti[(size_t)env * B.nti + tid];
-    if (tid < Task::NTF) s_tf[tid] = B.tf[(size_t)env * B.ntf + tid];
+    for (int i = lane; i < nq; i += 32) E.p_qpos()[i] = gq[i];
+    for (int i = lane; i < nv; i += 32) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
+    for (int i = lane; i < nu; i += 32) E.p_ctrl()[i] = gc[i];
+    if (lane == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; }
+    if (Task::NTI > 0) {
+      if (lane < Task::NTI) s_ti[lane] = B.ti[(size_t)env * B.nti + lane];
+      if (lane < Task::NTF) s_tf[lane] = B.tf[(size_t)env * B.ntf + lane];
+    }
   }
   E.sync();
 
-  if (mode == MODE_PHYS) {
-    for (int s = 0; s < B.nsub; s++) E.step_euler(ctr);
-  } else if (mode == MODE_FORWARD) {
-    E.forward(ctr);
-  } else if (mode == MODE_RESET) {
-    Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr);
-    for (int s = 0; s < Task::SETTLE; s++) E.step_euler(ctr);
-    Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
-  } else {  // MODE_STEP
-    Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act);
-    for (int s = 0; s < Task::FRAME_SKIP; s++) E.step_euler(ctr);
-    Task::post_physics(E, tp, s_ti);
-    Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
-    E.sync();
-    if (tid == 0) {
-      int term = 0, trunc = 0;
-      s_rew = Task::reward_and_done(E, tp, s_act, s_ti, s_tf, &term, &trunc);
-      s_done[0] = term; s_done[1] = trunc;
-      B.reward[env] = s_rew; B.term[env] = (uint8_t)term; B.trunc[env] = (uint8_t)trunc;
-    }
-    E.sync();
-    if (s_done[0] || s_done[1]) {
+  // one loop, one call site of the physics: [reset ->] n sub-steps -> task epilogue [-> auto-reset -> settle steps]
+  int nsub = 0, stage = 0;
+  if (mode == MODE_PHYS) nsub = B.nsub;
+  else if (mode == MODE_FORWARD) nsub = 1;
+  else if (mode == MODE_RESET) { Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr); nsub = Task::SETTLE; stage = 1; }
+  else { Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act); nsub = Task::FRAME_SKIP; }
+  while (true) {
+    if (nsub > 0) { E.step_euler(ctr, mode != MODE_FORWARD); nsub--; continue; }
+    if (mode == MODE_PHYS || mode == MODE_FORWARD) break;
+    if (stage == 0) {   // end of the control step
+      Task::post_physics(E, tp, s_ti);
+      Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+      E.sync();
+      if (lane == 0) {
+        int term = 0, trunc = 0;
+        float rew = Task::reward_and_done(E, tp, s_act, s_ti, s_tf, &term, &trunc);
+        E.p_misc()[MISC_DONE] = term | (trunc << 1);
+        B.reward[env] = rew; B.term[env] = (uint8_t)term; B.trunc[env] = (uint8_t)trunc;
+      }
+      E.sync();
+      if (!E.p_misc()[MISC_DONE]) break;
       // same-step auto-reset: keep the terminal observation, account the episode, start the next one
-      if (B.final_obs) for (int i = tid; i < Task::OBS; i += T) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
-      if (tid == 0) {
+      if (B.final_obs) for (int i = lane; i < Task::OBS; i += 32) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
+      if (lane == 0) {
         epstat[4 * env + 0] += 1.f; epstat[4 * env + 1] += s_tf[0]; epstat[4 * env + 2] += (float)s_ti[0];
         atomicAdd(&ctr[CTR_EPISODES], 1ull);
       }
       E.sync();
       Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
-      for (int s = 0; s < Task::SETTLE; s++) E.step_euler(ctr);
+      nsub = Task::SETTLE; stage = 1;
+      if (nsub == 0) { Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); break; }
+    } else {            // end of the settle steps of a reset
       Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+      break;
     }
   }
   E.sync();
   // ---- optional exports of the last forward pass
   if (B.c_ncon) {
-    int ncon = E.w.misc[MISC_NCON];
+    int ncon = E.p_misc()[MISC_NCON];
     const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
-    if (tid == 0) B.c_ncon[env] = ncon;
-    for (int c = tid; c < ncon && c < B.c_cap; c += T) {
-      int p = __float_as_int(E.w.con[B2_CON_STRIDE * c + 13]);
+    if (lane == 0) B.c_ncon[env] = ncon;
+    for (int c = lane; c < ncon && c < B.c_cap; c += 32) {
+      int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
       B.c_geom[((size_t)env * B.c_cap + c) * 2] = gid[pc1[p]]; B.c_geom[((size_t)env * B.c_cap + c) * 2 + 1] = gid[pc2[p]];
-      B.c_dist[(size_t)env * B.c_cap + c] = E.w.con[B2_CON_STRIDE * c];
+      B.c_dist[(size_t)env * B.c_cap + c] = E.p_con()[B2_CON_STRIDE * c];
     }
   }
-  if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = tid; i < n; i += T) B.xpos_out[(size_t)env * n + i] = E.w.xpos[i]; }
+  if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = lane; i < n; i += 32) B.xpos_out[(size_t)env * n + i] = E.p_xpos()[i]; }
   if (B.debug_out) {
-    // layout: qfs | qas | qfc | qacc (nv each) | M (nM) | ncon nefc iters 0 | row_f | row_b | row_R | row_pos (row_cap each)
+    // layout: qfs | qas | qfc | qacc (nv each) | M (nM) | ncon nefc iters 0 | row_f | row_b | row_R | row_res (row_cap each)
     float* o = B.debug_out + (size_t)env * B.debug_n; int nM = P.dim[DD_nM], k = 0;
-    auto put = [&](const float* src, int n) { for (int i = tid; i < n; i += T) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
-    put(E.w.qfs, nv); put(E.w.qas, nv); put(E.w.qfc, nv); put(E.w.qacc, nv); put(E.w.M, nM);
-    if (tid == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.w.misc[MISC_NCON]; o[k + 1] = (float)E.w.misc[MISC_NEFC]; o[k + 2] = (float)E.w.misc[MISC_ITERS]; o[k + 3] = 0.f; }
+    auto put = [&](const float* src, int n) { for (int i = lane; i < n; i += 32) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
+    put(E.p_qfs(), nv); put(E.p_qas(), nv); put(E.p_qfc(), nv); put(E.p_qacc(), nv); put(E.p_M(), nM);
+    if (lane == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.p_misc()[MISC_NCON]; o[k + 1] = (float)E.p_misc()[MISC_NEFC]; o[k + 2] = (float)E.p_misc()[MISC_ITERS]; o[k + 3] = 0.f; }
     k += 4;
-    put(E.w.row_f, B.row_cap); put(E.w.row_b, B.row_cap); put(E.w.row_R, B.row_cap); put(E.w.row_pos, B.row_cap);
+    put(E.p_row_f(), B.row_cap); put(E.p_row_b(), B.row_cap); put(E.p_row_R(), B.row_cap); put(E.p_row_res(), B.row_cap);
   }
   // ---- store state
   if (mode != MODE_FORWARD) {
     float* gq = B.qpos + (size_t)env * B.nqp; float* gv = B.qvel + (size_t)env * B.nvp;
     float* gw = B.warm + (size_t)env * B.nvp; float* gc = B.ctrl + (size_t)env * B.nup;
     float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = tid; i < nq; i += T) gq[i] = E.w.qpos[i];
-    for (int i = tid; i < nv; i += T) { gv[i] = E.w.qvel[i]; gw[i] = E.w.warm[i]; ga[i] = E.w.qapp[i]; }
-    for (int i = tid; i < nu; i += T) gc[i] = E.w.ctrl[i];
-    if (tid == 0) B.time[env] = *E.w.time;
+    for (int i = lane; i < nq; i += 32) gq[i] = E.p_qpos()[i];
+    for (int i = lane; i < nv; i += 32) { gv[i] = E.p_qvel()[i]; gw[i] = E.p_warm()[i]; ga[i] = E.p_qapp()[i]; }
+    for (int i = lane; i < nu; i += 32) gc[i] = E.p_ctrl()[i];
+    if (lane == 0) B.time[env] = *E.p_time();
     if (Task::NTI > 0) {
-      if (tid < Task::NTI) B.ti[(size_t)env * B.nti + tid] = s_ti[tid];
-      if (tid < Task::NTF) B.tf[(size_t)env * B.ntf + tid] = s_tf[tid];
+      if (lane < Task::NTI) B.ti[(size_t)env * B.nti + lane] = s_ti[lane];
+      if (lane < Task::NTF) B.tf[(size_t)env * B.ntf + lane] = s_tf[lane];
     }
   }
 }
@@ -139,50 +140,42 @@ __global__ void __launch_bounds__(T) b2_env_kernel(const __grid_constant__ DevMo
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0;
-  template <int T> __device__ static void apply_action(Engine<T>&, const TaskParams&, const float*, float*) {}
-  template <int T> __device__ static void reset_state(Engine<T>& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
-    E.reset_data(); if (E.tid == 0) *E.w.time = 0.f; E.sync();
+  __device__ static void apply_action(Engine&, const TaskParams&, const float*, float*) {}
+  __device__ static void reset_state(Engine& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
+    E.reset_data(); if (E.lane == 0) *E.p_time() = 0.f; E.sync();
   }
-  template <int T> __device__ static void observe(Engine<T>&, const TaskParams&, float*) {}
-  template <int T> __device__ static float reward_and_done(Engine<T>&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
-  template <int T> __device__ static void post_physics(Engine<T>&, const TaskParams&, const int*) {}
+  __device__ static void observe(Engine&, const TaskParams&, float*) {}
+  __device__ static float reward_and_done(Engine&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
+  __device__ static void post_physics(Engine&, const TaskParams&, const int*) {}
 };
 
 __global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
   __shared__ double acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
   __syncthreads();
-  double loc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double loc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     loc[0] += epstat[4 * e]; loc[1] += epstat[4 * e + 1]; loc[2] += epstat[4 * e + 2];
     const unsigned long long* c = counters + (size_t)e * CTR_COUNT;
     loc[3] += (double)c[CTR_NAN_RESET]; loc[4] += (double)c[CTR_CON_DROPPED]; loc[5] += (double)c[CTR_ROW_DROPPED];
-    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS];
+    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS]; loc[9] += (double)c[CTR_ARENA_SPILL];
   }
-  for (int k = 0; k < 9; k++) atomicAdd(&acc[k], loc[k]);
+  for (int k = 0; k < 10; k++) atomicAdd(&acc[k], loc[k]);
   __syncthreads();
   if (threadIdx.x < 16) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int T, class Task>
-static int launch_T(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  auto kern = b2_env_kernel<T, Task>;
+template <class Task>
+static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  auto kern = b2_env_kernel<Task>;
   static thread_local size_t configured = 0;
   if (configured < b->smem) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)); configured = b->smem; }
-  kern<<<b->n_envs, T, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject, b->smem - 16);
+  int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
+  kern<<<grid, 32 * E, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject);
   g_launches++;
   CK(cudaGetLastError());
   return B2_OK;
-}
-template <class Task>
-static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  switch (b->T) {
-    case 32: return launch_T<32, Task>(b, mode, inject, s);
-    case 64: return launch_T<64, Task>(b, mode, inject, s);
-    case 128: return launch_T<128, Task>(b, mode, inject, s);
-  }
-  return fail(B2_ERR_ARG, "threads_per_env must be 32, 64 or 128");
 }
 static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   CK(cudaSetDevice(b->m->device));
@@ -230,12 +223,12 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
 }
 void b2_model_destroy(B2Model* m) { if (!m) return; cudaSetDevice(m->device); cudaFree(m->d_ints); cudaFree(m->d_flts); delete m; }
 
-int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, int threads_per_env,
+int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t seed, int env_offset, const B2BatchOpts* opts,
                     B2Batch** out) {
   if (!m || !out || n_envs <= 0) return fail(B2_ERR_ARG, "bad argument");
   CK(cudaSetDevice(m->device));
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
-  b->m = m; b->n_envs = n_envs; b->T = threads_per_env > 0 ? threads_per_env : 128;
+  b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
@@ -248,17 +241,28 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
   v.seed = seed; v.env_offset = env_offset;
-  // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped; rows: 4 per contact + limits)
-  v.con_cap = dim[DD_maxraw] < 48 ? dim[DD_maxraw] : 48; if (v.con_cap < 1) v.con_cap = 1;
-  v.row_cap = 4 * v.con_cap + 2 * dim[DD_nlim]; if (v.row_cap > 256) v.row_cap = 256; if (v.row_cap < 4) v.row_cap = 4;
+  // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped); rows: 4 per contact + limits
+  int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
+  int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
+  v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < 32 ? dim[DD_maxraw] : 32); if (v.con_cap < 1) v.con_cap = 1;
+  v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > 32 * B2_PGS_S * 4) v.row_cap = 32 * B2_PGS_S * 4;
+  v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
   int raw_need = r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
-  int arena = 15360 + (b->T / 32) * 33 * maxspan;
+  int scratch = (32 * maxspan <= dead_block_floats(dim)) ? 0 : 32 * maxspan;
+  int arena = (o_arena > 0 ? o_arena : 4608) + scratch;
   if (arena < raw_need) arena = raw_need;
   v.arena_floats = r4(arena);
-  b->smem = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, m->dm.n_ints, m->dm.n_flts, nullptr, nullptr);
-  if (b->smem > 227 * 1024) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
+  v.ws_floats = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, &v.off);
+  v.model_floats = model_smem_floats(m->dm.n_ints, m->dm.n_flts);
+  const int smem_max = 227 * 1024;
+  int epb = (smem_max - v.model_floats * 4 - 16) / (v.ws_floats * 4);
+  if (epb > 8) epb = 8;
+  if (o_epb > 0 && o_epb < epb) epb = o_epb;
+  if (epb < 1) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
+  v.envs_per_block = epb;
+  b->smem = ((size_t)v.model_floats + (size_t)epb * v.ws_floats) * 4 + 16;
   size_t N = n_envs;
   CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));
   CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
@@ -301,7 +305,7 @@ int b2_dims(const B2Batch* b, int* o) {  /* o has 16 entries */
   if (!b || !o) return fail(B2_ERR_ARG, "null argument");
   const int* d = b->m->dm.dim;
   o[0] = d[DD_nq]; o[1] = d[DD_nv]; o[2] = d[DD_nu]; o[3] = d[DD_nbody]; o[4] = b->obs_dim; o[5] = b->act_dim; o[6] = b->n_envs;
-  o[7] = b->nti; o[8] = b->ntf; o[9] = b->v.con_cap; o[10] = (int)b->smem; o[11] = b->T; o[12] = b->v.row_cap; o[13] = b->m->dm.dim[DD_nM];
+  o[7] = b->nti; o[8] = b->ntf; o[9] = b->v.con_cap; o[10] = (int)b->smem; o[11] = b->v.envs_per_block; o[12] = b->v.row_cap; o[13] = b->m->dm.dim[DD_nM]; o[14] = b->v.arena_floats; o[15] = b->v.ws_floats * 4;
   return B2_OK;
 }
 

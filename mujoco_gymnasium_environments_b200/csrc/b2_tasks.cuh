@@ -33,21 +33,19 @@ struct TaskParams {
 struct QuadrupedTask {
   static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4;
 
-  template <int T>
-  __device__ static void apply_action(Engine<T>& E, const TaskParams& tp, const float* act, float* act_clipped) {
-    for (int i = E.tid; i < ACT; i += T) {
+  __device__ static void apply_action(Engine& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
       float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
-      act_clipped[i] = a; E.w.ctrl[i] = a;
+      act_clipped[i] = a; E.p_ctrl()[i] = a;
     }
     E.sync();
   }
 
-  template <int T>
-  __device__ static void reset_state(Engine<T>& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+  __device__ static void reset_state(Engine& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
                                      const float* inject) {
     E.reset_data();
-    if (E.tid == 0) {
-      float* q = E.w.qpos;
+    if (E.lane == 0) {
+      float* q = E.p_qpos();
       q[0] = 2.0f; q[1] = 0.0f; q[2] = 0.6f; q[3] = 1.f; q[4] = 0.f; q[5] = 0.f; q[6] = 0.f;
       unsigned ep = (unsigned)ti[4];
       float u0 = inject ? inject[0] : -1.5f + 3.0f * rng_uniform(B.seed, (unsigned)(B.env_offset + env), ep, 0);
@@ -56,7 +54,7 @@ struct QuadrupedTask {
       q[tp.ids[6]] = u1;
       ti[0] = 0; ti[1] = 0; ti[2] = 0; ti[3] = 0; ti[4] = (int)(ep + 1);
       tf[0] = 0.f; tf[1] = 2.0f; tf[2] = 0.f;
-      *E.w.time = 0.f;
+      *E.p_time() = 0.f;
     }
     E.sync();
   }
@@ -68,29 +66,27 @@ struct QuadrupedTask {
     x = X[k]; typ = (float)(k + 1); hgt = H[k]; dif = D[k];
   }
 
-  template <int T>
-  __device__ static void observe(Engine<T>& E, const TaskParams& tp, float* obs) {
-    const Ws& w = E.w;
+  __device__ static void observe(Engine& E, const TaskParams& tp, float* obs) {
     int torso = tp.ids[0];
-    for (int i = E.tid; i < OBS; i += T) {
+    for (int i = E.lane; i < OBS; i += 32) {
       float v = 0.f;
-      if (i < 16) v = w.qpos[7 + i];
-      else if (i < 32) v = w.qvel[6 + i - 16];
-      else if (i < 36) v = w.qpos[3 + i - 32];
-      else if (i < 42) v = w.qvel[i - 36];
-      else if (i < 45) v = w.qpos[i - 42];
+      if (i < 16) v = E.p_qpos()[7 + i];
+      else if (i < 32) v = E.p_qvel()[6 + i - 16];
+      else if (i < 36) v = E.p_qpos()[3 + i - 32];
+      else if (i < 42) v = E.p_qvel()[i - 36];
+      else if (i < 45) v = E.p_qpos()[i - 42];
       else if (i < 49) {
         // foot *body* id compared with contact *geom* ids
-        int fid = tp.ids[1 + i - 45]; int ncon = w.misc[MISC_NCON];
+        int fid = tp.ids[1 + i - 45]; int ncon = E.p_misc()[MISC_NCON];
         const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(w.con[B2_CON_STRIDE * c + 13]);
+          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
           if (gid[pc1[p]] == fid || gid[pc2[p]] == fid) { v = 1.f; break; }
         }
-      } else if (i < 61) { int f = (i - 49) / 3, k = (i - 49) % 3; v = w.xpos[3 * tp.ids[1 + f] + k] - w.xpos[3 * torso + k]; }
+      } else if (i < 61) { int f = (i - 49) / 3, k = (i - 49) % 3; v = E.p_xpos()[3 * tp.ids[1 + f] + k] - E.p_xpos()[3 * torso + k]; }
       else if (i < 85) v = 10.0f;
       else if (i < 93) {
-        float x = w.xpos[3 * torso]; int slot = (i - 85) / 4, fld = (i - 85) % 4, found = 0;
+        float x = E.p_xpos()[3 * torso]; int slot = (i - 85) / 4, fld = (i - 85) % 4, found = 0;
         for (int k = 0; k < 12; k++) {
           float ox, ty, hg, df; obstacle(k, ox, ty, hg, df);
           if (ox > x) { if (found == slot) { v = fld == 0 ? ox - x : fld == 1 ? ty : fld == 2 ? hg : df; break; } found++; }
@@ -101,11 +97,10 @@ struct QuadrupedTask {
   }
 
   // returns reward; updates ti/tf; sets *terminated
-  template <int T>
-  __device__ static float reward_and_done(Engine<T>& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+  __device__ static float reward_and_done(Engine& E, const TaskParams& tp, const float* act, int* ti, float* tf,
                                           int* terminated, int* truncated) {
-    const Ws& w = E.w; int torso = tp.ids[0];
-    float x = w.xpos[3 * torso], y = w.xpos[3 * torso + 1], z = w.xpos[3 * torso + 2];
+    int torso = tp.ids[0];
+    float x = E.p_xpos()[3 * torso], y = E.p_xpos()[3 * torso + 1], z = E.p_xpos()[3 * torso + 2];
     float reward = -20.0f;
     float progress = x - tf[1];
     if (progress > 0.f) { reward += progress * 500.0f; tf[2] = fmaxf(tf[2], x); }
@@ -118,15 +113,15 @@ struct QuadrupedTask {
     }
     ti[1] = bits;
     if (x >= 98.0f) reward += 5000.0f;
-    if (fabsf(w.qpos[3]) > 0.7f) reward += 100.0f;
+    if (fabsf(E.p_qpos()[3]) > 0.7f) reward += 100.0f;
     int cc = 0;
     {
-      int ncon = w.misc[MISC_NCON];
+      int ncon = E.p_misc()[MISC_NCON];
       const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
       for (int f = 0; f < 4; f++) {
         int fid = tp.ids[1 + f];
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(w.con[B2_CON_STRIDE * c + 13]);
+          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
           if (gid[pc1[p]] == fid || gid[pc2[p]] == fid) { cc++; break; }
         }
       }
@@ -136,7 +131,7 @@ struct QuadrupedTask {
     for (int i = 0; i < ACT; i++) effort += fabsf(act[i]);
     reward -= effort * 0.1f;
     if (z < 0.2f) { reward -= 2000.0f; ti[2] += 1; }
-    if (w.misc[MISC_NCON] > 8) reward -= 500.0f;
+    if (E.p_misc()[MISC_NCON] > 8) reward -= 500.0f;
     if (fabsf(progress) < 0.01f) { ti[3] += 1; if (ti[3] > 100) reward -= 100.0f; }
     else ti[3] = 0;
     tf[1] = x;
@@ -147,13 +142,12 @@ struct QuadrupedTask {
     return reward;
   }
 
-  template <int T>
-  __device__ static void post_physics(Engine<T>& E, const TaskParams& tp, const int* ti) {
+  __device__ static void post_physics(Engine& E, const TaskParams& tp, const int* ti) {
     // _update_dynamic_obstacles: uses the pre-increment step counter; takes effect on the next step
-    if (E.tid == 0) {
+    if (E.lane == 0) {
       float t = (float)ti[0] * 0.01f;
-      E.w.ctrl[tp.ids[7]] = 50.0f * sinf(0.5f * t);
-      E.w.ctrl[tp.ids[8]] = 100.0f * sinf(0.3f * t);
+      E.p_ctrl()[tp.ids[7]] = 50.0f * sinf(0.5f * t);
+      E.p_ctrl()[tp.ids[8]] = 100.0f * sinf(0.3f * t);
     }
     E.sync();
   }

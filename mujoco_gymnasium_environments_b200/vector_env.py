@@ -19,7 +19,7 @@ class B200VectorEnv:
     metadata = {"autoreset_mode": "same_step", "render_modes": []}
 
     def __init__(self, task: str, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
-                 threads_per_env: int = 128, assets_root: Optional[str] = None):
+                 assets_root: Optional[str] = None, **batch_opts):
         import torch
         if not torch.cuda.is_available():
             raise capi.B2Error("B200VectorEnv needs a CUDA device; there is no CPU fallback")
@@ -27,7 +27,7 @@ class B200VectorEnv:
         self.spec = TASKS[task]
         self.tables = load_tables(task, assets_root)
         self.model = capi.DeviceModel(self.tables, device)
-        self.batch = capi.Batch(self.model, self.spec.describe(self.tables), num_envs, seed, env_offset, threads_per_env)
+        self.batch = capi.Batch(self.model, self.spec.describe(self.tables), num_envs, seed, env_offset, **batch_opts)
         self.num_envs = num_envs
         self.device = self.batch.device
         self.single_action_space = self.spec.action_space(self.tables)

@@ -16,12 +16,11 @@ def relerr(a, b):
 
 
 def main():
-    T = int(os.environ.get("B2_T", "128"))
     t = load_tables("quadruped_parkour")
     dm = capi.DeviceModel(t, 0)
     N = 8
-    b = capi.Batch(dm, None, N, 0, 0, T)
-    print("dims nq nv nu", b.nq, b.nv, b.nu, "smem", b.smem_bytes, "T", b.threads_per_env, "row_cap", b.row_cap, "con_cap", b.con_cap)
+    b = capi.Batch(dm, None, N, 0, 0)
+    print("dims nq nv nu", b.nq, b.nv, b.nu, "smem", b.smem_bytes, "epb", b.envs_per_block, "arena", b.arena_floats, "ws_bytes", b.ws_bytes, "row_cap", b.row_cap, "con_cap", b.con_cap)
     om = ref.load_model(t)
     rng = np.random.default_rng(0)
     # states: oracle rollouts with small random torques
@@ -95,7 +94,7 @@ def main():
     # task-level
     spec = TASKS["quadruped_parkour"]
     N = 4
-    tb = capi.Batch(dm, spec.describe(t), N, 1234, 0, T)
+    tb = capi.Batch(dm, spec.describe(t), N, 1234, 0)
     obs = torch.zeros((N, 95), device="cuda"); rew = torch.zeros(N, device="cuda")
     term = torch.zeros(N, dtype=torch.uint8, device="cuda"); trunc = torch.zeros(N, dtype=torch.uint8, device="cuda")
     inject = torch.tensor([[0.3, -0.2, 0, 0], [1.0, 0.5, 0, 0], [-1.2, 0.9, 0, 0], [0.0, 0.0, 0, 0]], dtype=torch.float32, device="cuda")
@@ -113,7 +112,7 @@ def main():
             print(f"step {s} env {k}: obs err {float(np.max(np.abs(o - obs[k].cpu().numpy()))):.2e} rew {r:.4f}/{float(rew[k]):.4f} term {te}/{int(term[k])} ncon {envs[k].data.ncon}")
     # timing
     for N in (4096,):
-        tb2 = capi.Batch(dm, spec.describe(t), N, 1, 0, T)
+        tb2 = capi.Batch(dm, spec.describe(t), N, 1, 0)
         obs = torch.zeros((N, 95), device="cuda"); rew = torch.zeros(N, device="cuda")
         term = torch.zeros(N, dtype=torch.uint8, device="cuda"); trunc = torch.zeros(N, dtype=torch.uint8, device="cuda")
         tb2.reset(obs); torch.cuda.synchronize()
@@ -131,7 +130,7 @@ def main():
                 tb2.step(a, obs, rew, term, trunc)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / K
-            print(f"N={N} T={T} scale={scale}: {ms:.3f} ms/step -> {N / ms * 1e3:.0f} env-steps/s; stats {tb2.stats().cpu().numpy()[:9]}")
+            print(f"N={N} epb={tb2.envs_per_block} scale={scale}: {ms:.3f} ms/step -> {N / ms * 1e3:.0f} env-steps/s; stats {tb2.stats().cpu().numpy()[:9]}")
         tb2.close()
 
 

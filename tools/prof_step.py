@@ -7,8 +7,7 @@ from mujoco_gymnasium_environments_b200.vector_env import B200VectorEnv
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-T = int(os.environ.get("B2_T", "128"))
-env = B200VectorEnv("quadruped_parkour", N, threads_per_env=T, seed=1)
+env = B200VectorEnv("quadruped_parkour", N, seed=1)
 env.reset()
 hi = torch.tensor(env.single_action_space.high, device="cuda")
 g = torch.Generator(device="cuda"); g.manual_seed(0)
