@@ -115,7 +115,7 @@ def main():
     # ---- CPU baseline first (spawned processes; before CUDA is initialised in this one)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_arm(a.cpu_steps or 150, a.action_scale)
+        cpu = cpu_arm(a.cpu_steps or 6000, a.action_scale)
 
     import numpy as np
     import torch

@@ -42,7 +42,8 @@ typedef struct B2BatchOpts {
   int arena_floats;    /* per-env shared-memory arena holding J and the packed A of every island */
   int con_cap;         /* contact buffer capacity per env */
   int row_cap;         /* constraint-row capacity per env */
-  int reserved[4];
+  int warps_per_env;   /* 1 or 3: warps cooperating on one env (islands / contact chain in parallel) */
+  int reserved[3];
 } B2BatchOpts;
 
 /* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global

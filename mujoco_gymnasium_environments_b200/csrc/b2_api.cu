@@ -22,7 +22,7 @@ struct B2Model {
   std::vector<int> h_ints;
 };
 struct B2Batch {
-  B2Model* m; int n_envs; TaskParams tp; BatchView v; size_t smem;
+  B2Model* m; int n_envs, W; TaskParams tp; BatchView v; size_t smem;
   float* epstat;      // [N][4] episodes, return_sum, length_sum, (spare)
   double* d_stats;
   float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
@@ -32,92 +32,105 @@ struct B2Batch {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-// grid = ceil(n_envs / E) CTAs of E warps; warp w of CTA c steps env c*E + w.  Shared memory: [model | E workspaces | mbarrier].
-template <class Task>
-__global__ void __launch_bounds__(256, 1) b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B,
-                                                     const __grid_constant__ TaskParams tp, int mode, float* epstat,
-                                                     const float* inject) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// grid = ceil(n_envs / E) CTAs of E teams of W warps; team t of CTA c steps env c*E + t.
+// Shared memory: [model | E workspaces | mbarrier].  The task hooks are warp-level code run by warp 0 of the team.
+template <class Task, int W>
+__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W * 6, 1)
+b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B, const __grid_constant__ TaskParams tp,
+              int mode, float* epstat, const float* inject) {
+  const int team = threadIdx.x / (32 * W);
   uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
   stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints), bar);
-  const int env = blockIdx.x * B.envs_per_block + warp;
+  const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine E(P, B, B.model_floats + warp * B.ws_floats);
+  Engine<W> E(P, B, B.model_floats + team * B.ws_floats, team);
+  const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
+  constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
   unsigned long long* ctr = B.counters + (size_t)env * CTR_COUNT;
   int* s_ti = E.p_ti(); float* s_tf = E.p_tf(); float* s_act = E.p_act();
-  // ---- load the env's state rows (coalesced: the warp's lanes read consecutive floats of one row)
+  // ---- load the env's state rows (coalesced: consecutive threads read consecutive floats of one row)
   {
     const float* gq = B.qpos + (size_t)env * B.nqp; const float* gv = B.qvel + (size_t)env * B.nvp;
     const float* gw = B.warm + (size_t)env * B.nvp; const float* gc = B.ctrl + (size_t)env * B.nup;
     const float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = lane; i < nq; i += 32) E.p_qpos()[i] = gq[i];
-    for (int i = lane; i < nv; i += 32) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
-    for (int i = lane; i < nu; i += 32) E.p_ctrl()[i] = gc[i];
-    if (lane == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; }
+    for (int i = tl; i < nq; i += TEAM) E.p_qpos()[i] = gq[i];
+    for (int i = tl; i < nv; i += TEAM) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
+    for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
+    if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; }
     if (Task::NTI > 0) {
-      if (lane < Task::NTI) s_ti[lane] = B.ti[(size_t)env * B.nti + lane];
-      if (lane < Task::NTF) s_tf[lane] = B.tf[(size_t)env * B.ntf + lane];
+      if (tl < Task::NTI) s_ti[tl] = B.ti[(size_t)env * B.nti + tl];
+      if (tl < Task::NTF) s_tf[tl] = B.tf[(size_t)env * B.ntf + tl];
     }
   }
-  E.sync();
+  E.team_sync();
 
   // one loop, one call site of the physics: [reset ->] n sub-steps -> task epilogue [-> auto-reset -> settle steps]
   int nsub = 0, stage = 0;
   if (mode == MODE_PHYS) nsub = B.nsub;
   else if (mode == MODE_FORWARD) nsub = 1;
-  else if (mode == MODE_RESET) { Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr); nsub = Task::SETTLE; stage = 1; }
-  else { Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act); nsub = Task::FRAME_SKIP; }
+  else if (mode == MODE_RESET) {
+    if (w0) Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr);
+    E.team_sync(); nsub = Task::SETTLE; stage = 1;
+  } else {
+    if (w0) Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act);
+    E.team_sync(); nsub = Task::FRAME_SKIP;
+  }
   while (true) {
     if (nsub > 0) { E.step_euler(ctr, mode != MODE_FORWARD); nsub--; continue; }
     if (mode == MODE_PHYS || mode == MODE_FORWARD) break;
     if (stage == 0) {   // end of the control step
-      Task::post_physics(E, tp, s_ti);
-      Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
-      E.sync();
-      if (lane == 0) {
-        int term = 0, trunc = 0;
-        float rew = Task::reward_and_done(E, tp, s_act, s_ti, s_tf, &term, &trunc);
-        E.p_misc()[MISC_DONE] = term | (trunc << 1);
-        B.reward[env] = rew; B.term[env] = (uint8_t)term; B.trunc[env] = (uint8_t)trunc;
+      if (w0) {
+        Task::post_physics(E, tp, s_ti);
+        Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+        E.sync();
+        if (lane == 0) {
+          int term = 0, trunc = 0;
+          float rew = Task::reward_and_done(E, tp, s_act, s_ti, s_tf, &term, &trunc);
+          E.p_misc()[MISC_DONE] = term | (trunc << 1);
+          B.reward[env] = rew; B.term[env] = (uint8_t)term; B.trunc[env] = (uint8_t)trunc;
+        }
       }
-      E.sync();
+      E.team_sync();
       if (!E.p_misc()[MISC_DONE]) break;
       // same-step auto-reset: keep the terminal observation, account the episode, start the next one
-      if (B.final_obs) for (int i = lane; i < Task::OBS; i += 32) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
-      if (lane == 0) {
-        epstat[4 * env + 0] += 1.f; epstat[4 * env + 1] += s_tf[0]; epstat[4 * env + 2] += (float)s_ti[0];
-        atomicAdd(&ctr[CTR_EPISODES], 1ull);
+      if (w0) {
+        if (B.final_obs) for (int i = lane; i < Task::OBS; i += 32) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
+        if (lane == 0) {
+          epstat[4 * env + 0] += 1.f; epstat[4 * env + 1] += s_tf[0]; epstat[4 * env + 2] += (float)s_ti[0];
+          atomicAdd(&ctr[CTR_EPISODES], 1ull);
+        }
+        E.sync();
+        Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
       }
-      E.sync();
-      Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
+      E.team_sync();
       nsub = Task::SETTLE; stage = 1;
-      if (nsub == 0) { Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); break; }
+      if (nsub == 0) { if (w0) Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); break; }
     } else {            // end of the settle steps of a reset
-      Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+      if (w0) Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
       break;
     }
   }
-  E.sync();
+  E.team_sync();
   // ---- optional exports of the last forward pass
   if (B.c_ncon) {
     int ncon = E.p_misc()[MISC_NCON];
     const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
-    if (lane == 0) B.c_ncon[env] = ncon;
-    for (int c = lane; c < ncon && c < B.c_cap; c += 32) {
+    if (tl == 0) B.c_ncon[env] = ncon;
+    for (int c = tl; c < ncon && c < B.c_cap; c += TEAM) {
       int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
       B.c_geom[((size_t)env * B.c_cap + c) * 2] = gid[pc1[p]]; B.c_geom[((size_t)env * B.c_cap + c) * 2 + 1] = gid[pc2[p]];
       B.c_dist[(size_t)env * B.c_cap + c] = E.p_con()[B2_CON_STRIDE * c];
     }
   }
-  if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = lane; i < n; i += 32) B.xpos_out[(size_t)env * n + i] = E.p_xpos()[i]; }
+  if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = tl; i < n; i += TEAM) B.xpos_out[(size_t)env * n + i] = E.p_xpos()[i]; }
   if (B.debug_out) {
     // layout: qfs | qas | qfc | qacc (nv each) | M (nM) | ncon nefc iters 0 | row_f | row_b | row_R | row_res (row_cap each)
     float* o = B.debug_out + (size_t)env * B.debug_n; int nM = P.dim[DD_nM], k = 0;
-    auto put = [&](const float* src, int n) { for (int i = lane; i < n; i += 32) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
+    auto put = [&](const float* src, int n) { for (int i = tl; i < n; i += TEAM) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
     put(E.p_qfs(), nv); put(E.p_qas(), nv); put(E.p_qfc(), nv); put(E.p_qacc(), nv); put(E.p_M(), nM);
-    if (lane == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.p_misc()[MISC_NCON]; o[k + 1] = (float)E.p_misc()[MISC_NEFC]; o[k + 2] = (float)E.p_misc()[MISC_ITERS]; o[k + 3] = 0.f; }
+    if (tl == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.p_misc()[MISC_NCON]; o[k + 1] = (float)E.p_misc()[MISC_NEFC]; o[k + 2] = (float)E.p_misc()[MISC_ITERS]; o[k + 3] = 0.f; }
     k += 4;
     put(E.p_row_f(), B.row_cap); put(E.p_row_b(), B.row_cap); put(E.p_row_R(), B.row_cap); put(E.p_row_res(), B.row_cap);
   }
@@ -126,13 +139,13 @@ __global__ void __launch_bounds__(256, 1) b2_env_kernel(const __grid_constant__ 
     float* gq = B.qpos + (size_t)env * B.nqp; float* gv = B.qvel + (size_t)env * B.nvp;
     float* gw = B.warm + (size_t)env * B.nvp; float* gc = B.ctrl + (size_t)env * B.nup;
     float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = lane; i < nq; i += 32) gq[i] = E.p_qpos()[i];
-    for (int i = lane; i < nv; i += 32) { gv[i] = E.p_qvel()[i]; gw[i] = E.p_warm()[i]; ga[i] = E.p_qapp()[i]; }
-    for (int i = lane; i < nu; i += 32) gc[i] = E.p_ctrl()[i];
-    if (lane == 0) B.time[env] = *E.p_time();
+    for (int i = tl; i < nq; i += TEAM) gq[i] = E.p_qpos()[i];
+    for (int i = tl; i < nv; i += TEAM) { gv[i] = E.p_qvel()[i]; gw[i] = E.p_warm()[i]; ga[i] = E.p_qapp()[i]; }
+    for (int i = tl; i < nu; i += TEAM) gc[i] = E.p_ctrl()[i];
+    if (tl == 0) B.time[env] = *E.p_time();
     if (Task::NTI > 0) {
-      if (lane < Task::NTI) B.ti[(size_t)env * B.nti + lane] = s_ti[lane];
-      if (lane < Task::NTF) B.tf[(size_t)env * B.ntf + lane] = s_tf[lane];
+      if (tl < Task::NTI) B.ti[(size_t)env * B.nti + tl] = s_ti[tl];
+      if (tl < Task::NTF) B.tf[(size_t)env * B.ntf + tl] = s_tf[tl];
     }
   }
 }
@@ -140,13 +153,13 @@ __global__ void __launch_bounds__(256, 1) b2_env_kernel(const __grid_constant__ 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0;
-  __device__ static void apply_action(Engine&, const TaskParams&, const float*, float*) {}
-  __device__ static void reset_state(Engine& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
+  template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
     E.reset_data(); if (E.lane == 0) *E.p_time() = 0.f; E.sync();
   }
-  __device__ static void observe(Engine&, const TaskParams&, float*) {}
-  __device__ static float reward_and_done(Engine&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
-  __device__ static void post_physics(Engine&, const TaskParams&, const int*) {}
+  template <class EN> __device__ static void observe(EN&, const TaskParams&, float*) {}
+  template <class EN> __device__ static float reward_and_done(EN&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
+  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*) {}
 };
 
 __global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
@@ -166,16 +179,24 @@ __global__ void b2_stats_kernel(const unsigned long long* counters, const float*
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <class Task>
-static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  auto kern = b2_env_kernel<Task>;
+template <class Task, int W>
+static int launch_W(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  auto kern = b2_env_kernel<Task, W>;
   static thread_local size_t configured = 0;
   if (configured < b->smem) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)); configured = b->smem; }
   int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
-  kern<<<grid, 32 * E, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject);
+  kern<<<grid, 32 * W * E, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject);
   g_launches++;
   CK(cudaGetLastError());
   return B2_OK;
+}
+template <class Task>
+static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
+  switch (b->W) {
+    case 1: return launch_W<Task, 1>(b, mode, inject, s);
+    case 3: return launch_W<Task, 3>(b, mode, inject, s);
+  }
+  return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3");
 }
 static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   CK(cudaSetDevice(b->m->device));
@@ -190,6 +211,12 @@ extern "C" {
 
 const char* b2_last_error(void) { return g_err.c_str(); }
 unsigned long long b2_launch_count(void) { return g_launches.load(); }
+/* bring-up hook (not in b2env.h): per-phase clock64 sums when the library is built with -DB2_PHASE_TIMING */
+int b2_phase_cycles(B2Batch* b, unsigned long long* out16) {
+  if (!b || !out16) return B2_ERR_ARG;
+  cudaSetDevice(b->m->device); cudaDeviceSynchronize();
+  return cudaMemcpy(out16, b->v.phase_cycles, 16 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? B2_OK : B2_ERR_CUDA;
+}
 
 int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_flts, int device, B2Model** out) {
   if (!ints || !flts || !out) return fail(B2_ERR_ARG, "null argument");
@@ -244,13 +271,16 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped); rows: 4 per contact + limits
   int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
   int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
+  b->W = (opts && opts->warps_per_env > 0) ? opts->warps_per_env : 3;
+  if (b->W != 1 && b->W != 3) { delete b; return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3"); }
   v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < 32 ? dim[DD_maxraw] : 32); if (v.con_cap < 1) v.con_cap = 1;
   v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > 32 * B2_PGS_S * 4) v.row_cap = 32 * B2_PGS_S * 4;
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
   int raw_need = r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
-  int scratch = (32 * maxspan <= dead_block_floats(dim)) ? 0 : 32 * maxspan;
+  int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim)) ? 0 : 32 * dim[DD_nv];
+  (void)maxspan;
   int arena = (o_arena > 0 ? o_arena : 4608) + scratch;
   if (arena < raw_need) arena = raw_need;
   v.arena_floats = r4(arena);
@@ -258,7 +288,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   v.model_floats = model_smem_floats(m->dm.n_ints, m->dm.n_flts);
   const int smem_max = 227 * 1024;
   int epb = (smem_max - v.model_floats * 4 - 16) / (v.ws_floats * 4);
-  if (epb > 8) epb = 8;
+  if (epb > (b->W == 1 ? 8 : 6)) epb = (b->W == 1 ? 8 : 6);
   if (o_epb > 0 && o_epb < epb) epb = o_epb;
   if (epb < 1) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
   v.envs_per_block = epb;
@@ -267,6 +297,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));
   CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
   CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
+  CK(cudaMalloc(&v.phase_cycles, 16 * 8)); CK(cudaMemset(v.phase_cycles, 0, 16 * 8));
   CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 4)); CK(cudaMalloc(&b->d_stats, 16 * 8));
   CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));
   CK(cudaMemset(v.ctrl, 0, N * v.nup * 4)); CK(cudaMemset(v.time, 0, N * 4)); CK(cudaMemset(v.ti, 0, N * v.nti * 4));
@@ -294,7 +325,7 @@ void b2_batch_destroy(B2Batch* b) {
   cudaSetDevice(b->m->device);
   BatchView& v = b->v;
   cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
-  cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
+  cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.phase_cycles); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
   cudaFreeHost(b->h_act); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_rew); cudaFreeHost(b->h_term); cudaFreeHost(b->h_trunc);
   cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term); cudaFree(b->d_trunc); cudaFree(b->d_inject);
   cudaStreamDestroy(b->own_stream);

@@ -74,8 +74,9 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   int nroot = dim[DD_nroot], nlim = dim[DD_nlim];
   WsOff t;
   t.qpos = take(nq); t.qvel = take(nv); t.warm = take(nv); t.ctrl = take(nu > 0 ? nu : 1); t.qapp = take(nv);
-  t.xpos = take(3 * nb); t.xmat = take(9 * nb); t.cdof = take(6 * nv); t.rootcom = take(3 * (nroot > 0 ? nroot : 1));
-  // contiguous block that is dead after the velocity stage and reused as scratch by the A build
+  t.xpos = take(3 * nb);
+  // contiguous block [xmat .. cinert]: dead once the J rows are filled, reused as scratch by the A build
+  t.xmat = take(9 * nb); t.cdof = take(6 * nv); t.rootcom = take(3 * (nroot > 0 ? nroot : 1));
   t.xquat = take(4 * nb); t.xipos = take(3 * nb); t.cvel = take(6 * nb); t.cacc = take(6 * nb); t.cinert = take(10 * nb);
   t.M = take(nM); t.LD = take(nM); t.invD = take(nv); t.qfs = take(nv); t.qas = take(nv); t.qfc = take(nv);
   t.qacc = take(nv); t.tmp = take(nv);
@@ -83,7 +84,7 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   t.row_info = take(row_cap); t.row_R = take(row_cap); t.row_b = take(row_cap); t.row_f = take(row_cap); t.row_res = take(row_cap);
   t.isl_n = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
   t.isl_A = take(B2_MAX_ISLANDS); t.isl_ldj = take(B2_MAX_ISLANDS);
-  t.red = take(8); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(16); t.tf = take(8); t.act = take(40);
+  t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(16); t.tf = take(8); t.act = take(40);
   t.arena = take(arena_floats);
   if (o) *o = t;
   return (off + 31) & ~31;
@@ -100,6 +101,7 @@ struct BatchView {
   float* xpos_out;                                   // optional [N][nbody*3] export of the last forward pass
   float* debug_out; int debug_n;                     // optional [N][debug_n] dump of solver intermediates (bring-up / tests)
   unsigned long long* counters;                      // [N][CTR_COUNT]
+  unsigned long long* phase_cycles;                  // [16] per-phase clock64 sums (only with -DB2_PHASE_TIMING)
   unsigned long long seed;
   int arena_floats, con_cap, row_cap;
   int nsub;                                          // physics sub-steps for MODE_PHYS
@@ -110,20 +112,34 @@ struct BatchView {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PHYS = 2, MODE_FORWARD = 3 };
 
-// floats in the contiguous dead block [xquat .. cinert]
+// floats in the contiguous dead block [xmat .. cinert]
 __host__ __device__ inline int dead_block_floats(const int* dim) {
-  int nb = dim[DD_nbody];
-  return r4(4 * nb) + r4(3 * nb) + r4(6 * nb) + r4(6 * nb) + r4(10 * nb);
+  int nb = dim[DD_nbody], nv = dim[DD_nv], nroot = dim[DD_nroot];
+  return r4(9 * nb) + r4(6 * nv) + r4(3 * (nroot > 0 ? nroot : 1)) + r4(4 * nb) + r4(3 * nb) + r4(6 * nb) + r4(6 * nb) + r4(10 * nb);
 }
 
 // -------------------------------------------------------------------------------------------- engine (one warp)
+// One env is stepped by a team of W warps (W = 1: one warp per env).  Warp-synchronous phases (tree passes, row
+// compaction) run on one warp of the team; the parallel phases (J fill, A build, PGS sweeps) split islands / rows
+// over the team's warps; team_sync() is a named barrier private to the team.
+template <int W>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
-  int wb;      // warp's slice base in b2_smem (floats)
-  int lane;
+  int wb;      // team's slice base in b2_smem (floats)
+  int lane;    // lane in warp
+  int wl;      // warp in team
+  int tl;      // thread in team
+  int barid;   // named barrier of the team (1..15)
+  static constexpr int TEAM = 32 * W;
 
-  __device__ Engine(const DevModel& p, const BatchView& b, int warp_base) : P(p), B(b), wb(warp_base) { lane = threadIdx.x & 31; }
+  __device__ Engine(const DevModel& p, const BatchView& b, int team_base, int team_in_block) : P(p), B(b), wb(team_base) {
+    tl = threadIdx.x % TEAM; lane = tl & 31; wl = tl >> 5; barid = 1 + team_in_block;
+  }
+  __device__ __forceinline__ void team_sync() const {
+    if (W == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(barid), "n"(TEAM) : "memory");
+  }
 
 #define X(n) __device__ __forceinline__ float* p_##n() const { return b2_smem + wb + B.off.n; }
   B2_WS_FLOAT_FIELDS(X)
@@ -345,57 +361,76 @@ struct Engine {
     sync();
   }
 
-  // ---- sparse L'DL factorisation of (M + hdamp*diag(damping)) (mj_factorM)
+  // ---- sparse L'DL factorisation of (M + hdamp*diag(damping)) (mj_factorM).
+  // dofs are eliminated leaves-first; the rank-1 update of dof k touches the (m,n) pairs of its ancestor chain, one
+  // pair per lane (no serial inner loop); the division by D is deferred to one parallel pass at the end, so each
+  // elimination step costs one warp barrier.
   __device__ void factor(float hdamp) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
-    const float* damp = F(DF_dof_damping);
+    const int* pmn = I(DI_pair_mn); const float* damp = F(DF_dof_damping);
+    float* LD = p_LD(); const float* M = p_M(); float* invD = p_invD();
     int nM = dim(DD_nM), nv = dim(DD_nv);
-    for (int k = lane; k < nM; k += 32) p_LD()[k] = p_M()[k];
+    for (int k = lane; k < nM; k += 32) LD[k] = M[k];
     sync();
     if (hdamp != 0.f) {
-      for (int i = lane; i < nv; i += 32) p_LD()[madr[i]] += hdamp * damp[i];
+      for (int i = lane; i < nv; i += 32) LD[madr[i]] += hdamp * damp[i];
       sync();
     }
     for (int k = nv - 1; k >= 0; k--) {
       int ak = madr[k], dk = ddepth[k];
-      float inv = 1.0f / p_LD()[ak];
       if (dk > 0) {
-        // lane m (1..dk) owns row a_m = m-th ancestor of k
-        for (int m = 1 + lane; m <= dk; m += 32) {
-          int am = mcol[ak + m], aa = madr[am];
-          float tk = p_LD()[ak + m] * inv;
-          for (int n = m; n <= dk; n++) p_LD()[aa + (n - m)] -= tk * p_LD()[ak + n];
+        float inv = 1.0f / LD[ak];
+        int npair = (dk * (dk + 1)) >> 1;
+        for (int p = lane; p < npair; p += 32) {
+          int mn = pmn[p], m = mn & 255, n = mn >> 8;
+          int aa = madr[mcol[ak + m]];
+          LD[aa + (n - m)] -= LD[ak + m] * inv * LD[ak + n];
         }
         sync();
-        for (int m = 1 + lane; m <= dk; m += 32) p_LD()[ak + m] *= inv;
       }
-      if (lane == 0) p_invD()[k] = inv;
-      sync();
     }
+    for (int i = lane; i < nv; i += 32) invD[i] = 1.0f / LD[madr[i]];
+    sync();
+    // deferred scaling: L(k, a_m) = LD(k, a_m) / D_k
+    const int* mrow = I(DI_Mcol);
+    (void)mrow;
+    for (int i = lane; i < nv; i += 32) {
+      int a = madr[i], n = ddepth[i]; float inv = invD[i];
+      for (int m = 1; m <= n; m++) LD[a + m] *= inv;
+    }
+    sync();
   }
 
   // ---- x <- M^-1 x with the factor above; level-synchronous over dof depth (mj_solveLD)
   __device__ void solve(float* x) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int* dladr = I(DI_dlevel_adr); const int* dldof = I(DI_dlevel_dof);
-    const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* ddof = I(DI_desc_dof);
-    const int* dmadr = I(DI_desc_madr);
+    const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
+    const float* LD = p_LD(); const float* invD = p_invD();
     int maxd = dim(DD_maxdofdepth), nv = dim(DD_nv);
     for (int l = maxd - 1; l >= 0; l--) {
       for (int idx = dladr[l] + lane; idx < dladr[l + 1]; idx += 32) {
-        int j = dldof[idx]; float s = x[j];
-        for (int k = 0; k < dnum[j]; k++) s -= p_LD()[dmadr[dadr[j] + k]] * x[ddof[dadr[j] + k]];
-        x[j] = s;
+        int j = dldof[idx]; const int* dp = dpack + dadr[j]; int n = dnum[j];
+        float s0 = x[j], s1 = 0.f, s2 = 0.f, s3 = 0.f; int k = 0;
+        for (; k + 4 <= n; k += 4) {
+          int p0 = dp[k], p1 = dp[k + 1], p2 = dp[k + 2], p3 = dp[k + 3];
+          s0 = fmaf(-LD[p0 >> 16], x[p0 & 0xffff], s0); s1 = fmaf(-LD[p1 >> 16], x[p1 & 0xffff], s1);
+          s2 = fmaf(-LD[p2 >> 16], x[p2 & 0xffff], s2); s3 = fmaf(-LD[p3 >> 16], x[p3 & 0xffff], s3);
+        }
+        for (; k < n; k++) { int p0 = dp[k]; s0 = fmaf(-LD[p0 >> 16], x[p0 & 0xffff], s0); }
+        x[j] = (s0 + s1) + (s2 + s3);
       }
       sync();
     }
-    for (int i = lane; i < nv; i += 32) x[i] *= p_invD()[i];
+    for (int i = lane; i < nv; i += 32) x[i] *= invD[i];
     sync();
     for (int l = 1; l <= maxd; l++) {
       for (int idx = dladr[l] + lane; idx < dladr[l + 1]; idx += 32) {
-        int i = dldof[idx], a = madr[i], n = ddepth[i]; float s = x[i];
-        for (int k = 1; k <= n; k++) s -= p_LD()[a + k] * x[mcol[a + k]];
-        x[i] = s;
+        int i = dldof[idx], a = madr[i], n = ddepth[i];
+        float s0 = x[i], s1 = 0.f; int k = 1;
+        for (; k + 2 <= n + 1; k += 2) { s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0); s1 = fmaf(-LD[a + k + 1], x[mcol[a + k + 1]], s1); }
+        for (; k <= n; k++) s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0);
+        x[i] = s0 + s1;
       }
       sync();
     }
@@ -586,13 +621,14 @@ struct Engine {
     sync();
   }
   // column scratch for the A build: 32 * max island dof span floats; lives in the dead block when it fits
-  __device__ __forceinline__ int max_span() const {
-    int m = 0; const int* inum = I(DI_island_dofnum);
-    for (int k = 0; k < dim(DD_nisland); k++) m = max(m, inum[k]);
-    return m;
-  }
+  __device__ __forceinline__ int max_span() const { return dim(DD_maxspan); }
+  // A-build scratch: 32 floats per dof; in the dead block [xmat .. cinert] when it fits, else at the arena tail
   __device__ __forceinline__ int scratch_in_arena() const {
-    return (32 * max_span() <= dead_block_floats(P.dim)) ? 0 : 32 * max_span();
+    return (32 * dim(DD_nv) <= dead_block_floats(P.dim)) ? 0 : 32 * dim(DD_nv);
+  }
+  __device__ __forceinline__ float* scratch_base() const {
+    int sc = scratch_in_arena();
+    return sc ? p_arena() + arenaFloats() - sc : p_xmat();
   }
   __device__ __forceinline__ float* island_A(int k) const { return p_arena() + p_isl_A()[k]; }
 
@@ -608,25 +644,25 @@ struct Engine {
     int nlim = dim(DD_nlim), nisl = dim(DD_nisland), ncon = p_misc()[MISC_NCON], nmw = dim(DD_nmaskw);
     float timestep = P.opt[DO_timestep], impratio = P.opt[DO_impratio];
     // row_info: limits  -> (joint << 2) | side ; contacts -> 0x40000000 | (contact << 2) | dir
-    for (int k = lane; k < 2 * nlim; k += 32) {
+    for (int k = tl; k < 2 * nlim; k += TEAM) {
       int r = p_lim_row()[k]; if (r < 0) continue;
       int j = limj[k >> 1], isl = disl[jd[j]];
       if (r >= p_isl_n()[isl]) continue;
       p_row_info()[p_isl_adr()[isl] + r] = (j << 2) | (k & 1);
     }
-    for (int c = lane; c < ncon; c += 32) {
+    for (int c = tl; c < ncon; c += TEAM) {
       int r = p_con_row()[c]; if (r < 0) continue;
       int isl = contact_island(c);
       if (r + 4 > p_isl_n()[isl]) { p_con_row()[c] = -1; continue; }
       for (int d = 0; d < 4; d++) p_row_info()[p_isl_adr()[isl] + r + d] = 0x40000000 | (c << 2) | d;
     }
-    sync();
+    team_sync();
     // J entries
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n) continue;
       int d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k]; float* J = p_arena() + p_isl_J()[k];
       int e0 = p_isl_adr()[k];
-      for (int item = lane; item < n * nd; item += 32) {
+      for (int item = tl; item < n * nd; item += TEAM) {
         int i = item / nd, c = item - i * nd, d = d0 + c;
         int info = p_row_info()[e0 + i]; float val = 0.f;
         if (info & 0x40000000) {
@@ -652,10 +688,10 @@ struct Engine {
         J[i * ldj + c] = val;
       }
     }
-    sync();
+    team_sync();
     // per-row parameters
     int nefc = p_misc()[MISC_NEFC];
-    for (int e = lane; e < nefc; e += 32) {
+    for (int e = tl; e < nefc; e += TEAM) {
       int info = p_row_info()[e];
       float pos, margin, da, solref0, solref1; const float* simp; int isl; float mu0 = 0.f; bool iscon = info & 0x40000000;
       if (iscon) {
@@ -712,7 +748,7 @@ struct Engine {
       p_row_f()[e] = jar < 0.f ? -jar / R : 0.f;
       p_row_res()[e] = pos;    // efc_pos until the solver overwrites it with the residual (debug export reads it)
     }
-    sync();
+    team_sync();
   }
 
   // packed symmetric index
@@ -723,11 +759,11 @@ struct Engine {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum);
     int nisl = dim(DD_nisland);
-    int sc = scratch_in_arena();
-    float* scratch = sc ? p_arena() + arenaFloats() - sc : p_xquat();
-    for (int k = 0; k < nisl; k++) {
+    // island k is built by warp k % W; its column scratch (32 floats per dof of the island) sits at 32 * dofadr
+    for (int k = wl; k < nisl; k += W) {
       int n = p_isl_n()[k]; if (!n) continue;
       int d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
+      float* scratch = scratch_base() + 32 * d0;
       const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k);
       for (int j0 = 0; j0 < n; j0 += 32) {
         int j = j0 + lane; bool valid = j < n;
@@ -736,93 +772,122 @@ struct Engine {
         // x <- L^-T x ; x <- D^-1 x ; x <- L^-1 x  (per-lane sequential sparse solve, uniform control flow)
         for (int i = nd - 1; i >= 0; i--) {
           float xi = x[32 * i]; int a = madr[d0 + i], dn = ddepth[d0 + i];
+#pragma unroll 4
           for (int m = 1; m <= dn; m++) { int cc = mcol[a + m] - d0; x[32 * cc] -= p_LD()[a + m] * xi; }
         }
         for (int i = 0; i < nd; i++) x[32 * i] *= p_invD()[d0 + i];
         for (int i = 0; i < nd; i++) {
           float s = x[32 * i]; int a = madr[d0 + i], dn = ddepth[d0 + i];
+#pragma unroll 4
           for (int m = 1; m <= dn; m++) { int cc = mcol[a + m] - d0; s -= p_LD()[a + m] * x[32 * cc]; }
           x[32 * i] = s;
         }
         // lower triangle: A[i][j] = J_i . x for i >= j
         for (int i = j0; i < n; i++) {
           const float* Ji = J + i * ldj; float s = 0.f;
+#pragma unroll 4
           for (int c = 0; c < nd; c++) s = fmaf(Ji[c], x[32 * c], s);
           if (valid && i >= j) A[tri(i) + j] = s + (i == j ? p_row_R()[e0 + i] : 0.f);
         }
         sync();
       }
     }
-    sync();
+    team_sync();
   }
 
-  // ---- PGS (mj_solPGS restated; row order = MuJoCo's within each island, islands are exactly decoupled)
+  // ---- PGS (mj_solPGS restated; row order = MuJoCo's within each island, islands are exactly decoupled so each
+  // warp of the team sweeps its own islands; the stopping rule uses the improvement summed over all islands, exchanged
+  // through shared memory once per iteration).  Forces, residuals, 1/A_ii and the packed-A addresses of a sweep live in
+  // registers.  mj_solPGS's "restore if the cost went up by more than 1e-10" guard is dropped: for these scalar row
+  // updates the cost change is <= 0 in exact arithmetic, the guard only ever fires on round-off.
+  struct Chain { int n, e0; const float* A; float f[B2_PGS_S], r[B2_PGS_S], ainv[B2_PGS_S], ad[B2_PGS_S]; int adr[B2_PGS_S]; };
+  __device__ __forceinline__ void chain_load(Chain& c, int k, const float* res) {
+    c.n = p_isl_n()[k]; c.e0 = p_isl_adr()[k]; c.A = island_A(k);
+#pragma unroll
+    for (int s = 0; s < B2_PGS_S; s++) {
+      int i = lane + 32 * s; bool v = i < c.n;
+      c.f[s] = v ? p_row_f()[c.e0 + i] : 0.f; c.r[s] = v ? res[c.e0 + i] : 0.f;
+      c.ad[s] = v ? c.A[tri(i) + i] : 1.f; c.ainv[s] = 1.f / c.ad[s];
+      c.adr[s] = tri(i);            // address of A(row 0, column i) in the packed lower triangle
+    }
+  }
+  __device__ __forceinline__ void chain_store(const Chain& c, float* res) {
+#pragma unroll
+    for (int s = 0; s < B2_PGS_S; s++) { int i = lane + 32 * s; if (i < c.n) { p_row_f()[c.e0 + i] = c.f[s]; res[c.e0 + i] = c.r[s]; } }
+  }
+  template <int S>
+  __device__ __forceinline__ void sweep_slot(Chain& c, float& improvement) {
+    int nn = min(32, c.n - 32 * S);
+    for (int ii = 0; ii < nn; ii++) {
+      const int i = 32 * S + ii;
+      float dl = fmaxf(fmaf(-c.r[S], c.ainv[S], c.f[S]), 0.f) - c.f[S];
+      float dlb = __shfl_sync(B2_FULL, dl, ii);
+      if (lane == ii) { improvement -= dl * fmaf(0.5f * dl, c.ad[S], c.r[S]); c.f[S] += dl; }
+#pragma unroll
+      for (int s2 = 0; s2 < B2_PGS_S; s2++) {
+        const int col = lane + 32 * s2;
+        if (col < c.n) c.r[s2] = fmaf(c.A[c.adr[s2]], dlb, c.r[s2]);
+        // A(i+1, col) - A(i, col) in the packed lower triangle: 1 right of the diagonal, i+1 left of it
+        c.adr[s2] += (s2 > S) ? 1 : (s2 < S) ? i + 1 : ((col > i) ? 1 : i + 1);
+      }
+    }
+  }
   __device__ void solve_pgs(unsigned long long* counters) {
     int nisl = dim(DD_nisland), iters = dim(DD_iterations);
     float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
-    float* res = p_row_res();
+    float* res = p_row_res(); float* red = p_red();
     // residual r = A f + b, and warm-start acceptance: cost(f) = 1/2 f'A f + f'b > 0 -> cold start
     float cost = 0.f;
-    for (int k = 0; k < nisl; k++) {
+    for (int k = wl; k < nisl; k += W) {
       int n = p_isl_n()[k]; if (!n) continue;
-      int e0 = p_isl_adr()[k]; const float* A = island_A(k);
+      int e0 = p_isl_adr()[k]; const float* A = island_A(k); const float* fr = p_row_f() + e0;
       for (int i = lane; i < n; i += 32) {
-        float s = 0.f; int ti = tri(i);
-        for (int j = 0; j < n; j++) s = fmaf(A[j <= i ? ti + j : tri(j) + i], p_row_f()[e0 + j], s);
-        float fi = p_row_f()[e0 + i], b = p_row_b()[e0 + i];
+        float s0 = 0.f, s1 = 0.f; int ti = tri(i), j = 0;
+        for (; j + 2 <= i + 1; j += 2) { s0 = fmaf(A[ti + j], fr[j], s0); s1 = fmaf(A[ti + j + 1], fr[j + 1], s1); }
+        for (; j <= i; j++) s0 = fmaf(A[ti + j], fr[j], s0);
+        for (; j < n; j++) s0 = fmaf(A[tri(j) + i], fr[j], s0);
+        float s = s0 + s1, fi = fr[i], b = p_row_b()[e0 + i];
         cost += fi * (0.5f * s + b);
         res[e0 + i] = s + b;
       }
     }
     cost = warp_sum(cost);
-    sync();
-    if (cost > 0.f) {
-      int nefc = p_misc()[MISC_NEFC];
-      for (int e = lane; e < nefc; e += 32) { p_row_f()[e] = 0.f; res[e] = p_row_b()[e]; }
-      sync();
+    if (lane == 0) red[wl] = cost;
+    team_sync();
+    float total = 0.f;
+#pragma unroll
+    for (int q = 0; q < W; q++) total += red[q];
+    if (total > 0.f) {
+      for (int k = wl; k < nisl; k += W) {
+        int n = p_isl_n()[k], e0 = p_isl_adr()[k];
+        for (int i = lane; i < n; i += 32) { p_row_f()[e0 + i] = 0.f; res[e0 + i] = p_row_b()[e0 + i]; }
+      }
     }
+    sync();
     int it = 0;
     for (; it < iters; it++) {
       float improvement = 0.f;
-      for (int k = 0; k < nisl; k++) {
-        int n = p_isl_n()[k]; if (!n) continue;
-        int e0 = p_isl_adr()[k]; const float* A = island_A(k);
-        float f[B2_PGS_S], r[B2_PGS_S], ad[B2_PGS_S], ainv[B2_PGS_S]; int tc[B2_PGS_S];
-#pragma unroll
-        for (int s = 0; s < B2_PGS_S; s++) {
-          int i = lane + 32 * s; bool v = i < n;
-          tc[s] = tri(i);
-          f[s] = v ? p_row_f()[e0 + i] : 0.f; r[s] = v ? res[e0 + i] : 0.f;
-          ad[s] = v ? A[tc[s] + i] : 1.f; ainv[s] = 1.f / ad[s];
-        }
-#pragma unroll
-        for (int s = 0; s < B2_PGS_S; s++) {
-          int nn = min(32, n - 32 * s);
-          for (int ii = 0; ii < nn; ii++) {
-            float nf = fmaxf(0.f, f[s] - r[s] * ainv[s]);
-            float dl = nf - f[s];
-            float ch = dl * (0.5f * dl * ad[s] + r[s]);
-            if (ch > 1e-10f) { dl = 0.f; ch = 0.f; }
-            if (lane == ii) { improvement -= ch; f[s] += dl; }
-            dl = __shfl_sync(B2_FULL, dl, ii);
-            if (dl != 0.f) {
-              int i = 32 * s + ii, ti = tri(i);
-#pragma unroll
-              for (int s2 = 0; s2 < B2_PGS_S; s2++) {
-                int c = lane + 32 * s2;
-                if (c < n) r[s2] = fmaf(A[c <= i ? ti + c : tc[s2] + i], dl, r[s2]);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < B2_PGS_S; s++) { int i = lane + 32 * s; if (i < n) { p_row_f()[e0 + i] = f[s]; res[e0 + i] = r[s]; } }
+      for (int k = wl; k < nisl; k += W) {
+        if (!p_isl_n()[k]) continue;
+        Chain c; chain_load(c, k, res);
+        sweep_slot<0>(c, improvement);
+        if (B2_PGS_S > 1) sweep_slot<(B2_PGS_S > 1 ? 1 : 0)>(c, improvement);
+        if (B2_PGS_S > 2) sweep_slot<(B2_PGS_S > 2 ? 2 : 0)>(c, improvement);
+        chain_store(c, res);
       }
       improvement = warp_sum(improvement);
+      if (W > 1) {
+        float* slot = red + 8 + (it & 1) * 4;      // double-buffered exchange
+        if (lane == 0) slot[wl] = improvement;
+        team_sync();
+        improvement = 0.f;
+#pragma unroll
+        for (int q = 0; q < W; q++) improvement += slot[q];
+      }
       if (improvement * scale < tol) { it++; break; }
     }
-    if (lane == 0) { p_misc()[MISC_ITERS] = it; if (counters) atomicAdd(&counters[CTR_SOLVER_ITERS], (unsigned long long)it); }
-    sync();
+    if (tl == 0) { p_misc()[MISC_ITERS] = it; if (counters) atomicAdd(&counters[CTR_SOLVER_ITERS], (unsigned long long)it); }
+    team_sync();
   }
 
   // ---- qfrc_constraint = J' f ; qacc = qacc_smooth + M^-1 qfrc_constraint
@@ -844,25 +909,43 @@ struct Engine {
   }
 
   // ---- mj_forward
+#ifdef B2_PHASE_TIMING
+#define B2_TICK(k) do { long long t_ = clock64(); if (tl == 0 && B.phase_cycles) atomicAdd(&B.phase_cycles[k], (unsigned long long)(t_ - tphase)); tphase = t_; } while (0)
+#else
+#define B2_TICK(k) do { } while (0)
+#endif
+  // ---- mj_forward.  Warp 0 runs the dynamics chain (velocities, CRB, M, L'DL, qacc_smooth) while warp 1 % W runs the
+  // contact chain (narrow phase, row compaction); the J fill, A build and PGS sweeps use the whole team.
   __device__ __forceinline__ void forward(unsigned long long* counters) {
     int nv = dim(DD_nv);
-    kinematics(); com_pos(); vel_pass(); backward_pass(); mass_and_smooth();
-    factor(0.f);
-    for (int d = lane; d < nv; d += 32) p_qas()[d] = p_qfs()[d];
-    sync();
-    solve(p_qas());
-    collision(counters);
-    make_rows(counters);
-    if (p_misc()[MISC_NEFC] > 0) {
-      fill_rows(); build_A(); solve_pgs(counters); finish_constraint();
-    } else {
-      for (int d = lane; d < nv; d += 32) { p_qacc()[d] = p_qas()[d]; p_qfc()[d] = 0.f; }
-      if (lane == 0) p_misc()[MISC_ITERS] = 0;
+#ifdef B2_PHASE_TIMING
+    long long tphase = clock64();
+#endif
+    if (wl == 0) { kinematics(); com_pos(); }
+    team_sync(); B2_TICK(0);
+    if (wl == 0) {
+      vel_pass(); backward_pass(); mass_and_smooth();
+      factor(0.f);
+      for (int d = lane; d < nv; d += 32) p_qas()[d] = p_qfs()[d];
       sync();
+      solve(p_qas());
+    }
+    if (wl == (1 % W)) { collision(counters); make_rows(counters); }
+    team_sync(); B2_TICK(1);
+    if (p_misc()[MISC_NEFC] > 0) {
+      fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11);
+      if (wl == 0) finish_constraint();
+      team_sync(); B2_TICK(12);
+    } else {
+      if (wl == 0) {
+        for (int d = lane; d < nv; d += 32) { p_qacc()[d] = p_qas()[d]; p_qfc()[d] = 0.f; }
+        if (lane == 0) p_misc()[MISC_ITERS] = 0;
+      }
+      team_sync();
     }
   }
 
-  __device__ void reset_data() {
+  __device__ void reset_data() {   // warp-level (called by warp 0)
     const float* q0 = F(DF_qpos0);
     int nq = dim(DD_nq), nv = dim(DD_nv), nu = dim(DD_nu);
     for (int i = lane; i < nq; i += 32) p_qpos()[i] = q0[i];
@@ -883,35 +966,49 @@ struct Engine {
     float* time = p_time();
     const int* jtype = I(DI_jnt_type); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
     int nq = dim(DD_nq), nv = dim(DD_nv), njnt = dim(DD_njnt); float h = P.opt[DO_timestep];
-    if (integrate && (bad_state(p_qpos(), nq) | bad_state(p_qvel(), nv))) {
-      reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); }
+    if (integrate && wl == 0) {
+      if (bad_state(p_qpos(), nq) | bad_state(p_qvel(), nv)) {
+        reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); }
+      }
     }
     for (int attempt = 0; attempt < 2; attempt++) {
       forward(counters);
-      if (!integrate || attempt == 1 || !bad_state(p_qacc(), nv)) break;
-      reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); }
+      if (!integrate || attempt == 1) break;
+      if (wl == 0) {
+        bool bad = bad_state(p_qacc(), nv);
+        if (bad) { reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); } }
+        if (lane == 0) p_misc()[MISC_FLAG] = bad ? 1 : 0;
+      }
+      team_sync();
+      if (!p_misc()[MISC_FLAG]) break;
     }
     if (!integrate) return;
-    // (M + h*diag(damping)) qacc' = qfrc_smooth + qfrc_constraint
-    factor(h);
-    for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d];
-    sync();
-    solve(p_tmp());
-    for (int d = lane; d < nv; d += 32) { p_qvel()[d] += h * p_tmp()[d]; p_warm()[d] = p_qacc()[d]; }
-    sync();
-    for (int j = lane; j < njnt; j += 32) {
-      int qa = jq[j], da = jd[j];
-      if (jtype[j] == 0) {
-        for (int k = 0; k < 3; k++) p_qpos()[qa + k] += h * p_qvel()[da + k];
-        V3 om = ld3(p_qvel() + da + 3); float n = norm(om);
-        if (n >= B2_MINVAL) {
-          Q4 q = qnormalize(qmul(ldq(p_qpos() + qa + 3), axisangle(om * (1.f / n), h * n)));
-          stq(p_qpos() + qa + 3, q);
-        }
-      } else p_qpos()[qa] += h * p_qvel()[da];
+#ifdef B2_PHASE_TIMING
+    long long tphase = clock64();
+#endif
+    if (wl == 0) {
+      // (M + h*diag(damping)) qacc' = qfrc_smooth + qfrc_constraint
+      factor(h);
+      for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d];
+      sync();
+      solve(p_tmp());
+      for (int d = lane; d < nv; d += 32) { p_qvel()[d] += h * p_tmp()[d]; p_warm()[d] = p_qacc()[d]; }
+      sync();
+      for (int j = lane; j < njnt; j += 32) {
+        int qa = jq[j], da = jd[j];
+        if (jtype[j] == 0) {
+          for (int k = 0; k < 3; k++) p_qpos()[qa + k] += h * p_qvel()[da + k];
+          V3 om = ld3(p_qvel() + da + 3); float n = norm(om);
+          if (n >= B2_MINVAL) {
+            Q4 q = qnormalize(qmul(ldq(p_qpos() + qa + 3), axisangle(om * (1.f / n), h * n)));
+            stq(p_qpos() + qa + 3, q);
+          }
+        } else p_qpos()[qa] += h * p_qvel()[da];
+      }
+      if (lane == 0) { *time += h; if (counters) atomicAdd(&counters[CTR_SUBSTEPS], 1ull); }
     }
-    if (lane == 0) { *time += h; if (counters) atomicAdd(&counters[CTR_SUBSTEPS], 1ull); }
-    sync();
+    team_sync();
+    B2_TICK(13);
   }
 };
 

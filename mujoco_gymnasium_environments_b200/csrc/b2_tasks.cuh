@@ -33,7 +33,7 @@ struct TaskParams {
 struct QuadrupedTask {
   static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4;
 
-  __device__ static void apply_action(Engine& E, const TaskParams& tp, const float* act, float* act_clipped) {
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
       float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
       act_clipped[i] = a; E.p_ctrl()[i] = a;
@@ -41,7 +41,7 @@ struct QuadrupedTask {
     E.sync();
   }
 
-  __device__ static void reset_state(Engine& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
                                      const float* inject) {
     E.reset_data();
     if (E.lane == 0) {
@@ -66,7 +66,7 @@ struct QuadrupedTask {
     x = X[k]; typ = (float)(k + 1); hgt = H[k]; dif = D[k];
   }
 
-  __device__ static void observe(Engine& E, const TaskParams& tp, float* obs) {
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
     int torso = tp.ids[0];
     for (int i = E.lane; i < OBS; i += 32) {
       float v = 0.f;
@@ -97,7 +97,7 @@ struct QuadrupedTask {
   }
 
   // returns reward; updates ti/tf; sets *terminated
-  __device__ static float reward_and_done(Engine& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
                                           int* terminated, int* truncated) {
     int torso = tp.ids[0];
     float x = E.p_xpos()[3 * torso], y = E.p_xpos()[3 * torso + 1], z = E.p_xpos()[3 * torso + 2];
@@ -142,7 +142,7 @@ struct QuadrupedTask {
     return reward;
   }
 
-  __device__ static void post_physics(Engine& E, const TaskParams& tp, const int* ti) {
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, const int* ti) {
     // _update_dynamic_obstacles: uses the pre-increment step counter; takes effect on the next step
     if (E.lane == 0) {
       float t = (float)ti[0] * 0.01f;

@@ -23,7 +23,7 @@ B2DEV_MAGIC = 0x42324456  # "B2DV"
 
 DIMS = ["nq", "nv", "nu", "nbody", "njnt", "ntree", "nroot", "ncg", "npair", "nM", "nlim", "nisland", "maxdepth",
         "maxdofdepth", "iterations", "integrator", "solver", "nprm", "nmaskw", "ndesc", "maxraw", "nsite",
-        "ls_iterations"]
+        "ls_iterations", "maxspan", "npairtab"]
 OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "impratio", "meaninertia", "pgs_scale", "ls_tolerance"]
 
 INT_FIELDS = [
@@ -33,7 +33,7 @@ INT_FIELDS = [
     "root_bodyadr", "root_bodynum",
     "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid",
     "dof_bodyid", "dof_Madr", "dof_depth", "dof_isrot", "dof_island", "dof_tree", "dof_actadr", "dof_actnum",
-    "dof_jnt", "dofact", "Mcol", "dlevel_adr", "dlevel_dof", "dof_descadr", "dof_descnum", "desc_dof", "desc_madr",
+    "dof_jnt", "dofact", "Mcol", "dlevel_adr", "dlevel_dof", "dof_descadr", "dof_descnum", "desc_pack", "pair_mn",
     "tree_dofadr", "tree_dofnum", "island_dofadr", "island_dofnum",
     "act_dofid", "act_ctrllimited", "act_forcelimited",
     "lim_jnt",
@@ -123,7 +123,15 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
                     desc_dof.append(i); desc_madr.append(a + k)
         desc_num[j] = len(desc_dof) - desc_adr[j]
     T["dof_descadr"] = desc_adr; T["dof_descnum"] = desc_num
-    T["desc_dof"] = i32(desc_dof if desc_dof else [0]); T["desc_madr"] = i32(desc_madr if desc_madr else [0])
+    # one int per (descendant dof, address of L(i,j)) pair: dof | madr << 16
+    assert nM < 65536 and nv < 65536
+    T["desc_pack"] = i32([(d | (a << 16)) for d, a in zip(desc_dof, desc_madr)] if desc_dof else [0])
+    # (m, n) with 1 <= m <= n <= maxdepth enumerated n-major: pair p of the rank-1 update of the L'DL factorisation
+    pair_mn = []
+    for n in range(1, maxdd + 1):
+        for mm in range(1, n + 1):
+            pair_mn.append(mm | (n << 8))
+    T["pair_mn"] = i32(pair_mn if pair_mn else [0])
     ndesc = len(desc_dof)
     T["tree_dofadr"] = i32(D["tree_dofadr"]); T["tree_dofnum"] = i32(D["tree_dofnum"])
     nisland = int(island_of_tree.max()) + 1 if ntree else 0
@@ -213,7 +221,8 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
                     1.0 / (mi * max(1, nv)), float(A["ls_tolerance"])])
     T["dims"] = i32([int(A["nq"]), nv, nu, nbody, njnt, ntree, nroot, ncg, npair, nM, nlim, nisland,
                      int(D["dims"][14]), maxdd, int(A["iterations"]), int(A["integrator"]), int(A["solver"]), nprm,
-                     nmaskw, ndesc, maxraw, int(A["nsite"]), int(A["ls_iterations"])])
+                     nmaskw, ndesc, maxraw, int(A["nsite"]), int(A["ls_iterations"]), int(isl_num.max()) if nisland else 0,
+                     len(pair_mn)])
     return T
 
 
