@@ -361,39 +361,39 @@ struct Engine {
     sync();
   }
 
-  // ---- sparse L'DL factorisation of (M + hdamp*diag(damping)) (mj_factorM).
-  // dofs are eliminated leaves-first; the rank-1 update of dof k touches the (m,n) pairs of its ancestor chain, one
-  // pair per lane (no serial inner loop); the division by D is deferred to one parallel pass at the end, so each
-  // elimination step costs one warp barrier.
-  __device__ void factor(float hdamp) {
-    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
-    const int* pmn = I(DI_pair_mn); const float* damp = F(DF_dof_damping);
+  // ---- sparse L'DL factorisation of (M + hdamp*diag(damping)) (mj_factorM) as a flat op program:
+  // one step per eliminated dof (leaves first); its rank-1 update is a list of independent (tgt, a, b) address
+  // triples, one per lane; the division by D is deferred to one parallel pass, so a step costs one warp barrier and
+  // three shared-memory round trips.
+  __device__ __forceinline__ void factor(float hdamp) {
+    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth);
+    const int* fstep = I(DI_fac_step); const int* fops = I(DI_fac_ops); const float* damp = F(DF_dof_damping);
     float* LD = p_LD(); const float* M = p_M(); float* invD = p_invD();
-    int nM = dim(DD_nM), nv = dim(DD_nv);
+    int nM = dim(DD_nM), nv = dim(DD_nv), nstep = dim(DD_nfacstep);
+#pragma unroll 1
     for (int k = lane; k < nM; k += 32) LD[k] = M[k];
     sync();
     if (hdamp != 0.f) {
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) LD[madr[i]] += hdamp * damp[i];
       sync();
     }
-    for (int k = nv - 1; k >= 0; k--) {
-      int ak = madr[k], dk = ddepth[k];
-      if (dk > 0) {
-        float inv = 1.0f / LD[ak];
-        int npair = (dk * (dk + 1)) >> 1;
-        for (int p = lane; p < npair; p += 32) {
-          int mn = pmn[p], m = mn & 255, n = mn >> 8;
-          int aa = madr[mcol[ak + m]];
-          LD[aa + (n - m)] -= LD[ak + m] * inv * LD[ak + n];
-        }
-        sync();
+#pragma unroll 1
+    for (int st = 0; st < nstep; st++) {
+      int w = fstep[st], cnt = (w >> 10) & 63, oa = w >> 16;
+      float inv = 1.0f / LD[w & 1023];
+#pragma unroll 1
+      for (int p = lane; p < cnt; p += 32) {
+        int op = fops[oa + p];
+        LD[op & 1023] -= LD[(op >> 10) & 1023] * inv * LD[op >> 20];
       }
+      sync();
     }
+#pragma unroll 1
     for (int i = lane; i < nv; i += 32) invD[i] = 1.0f / LD[madr[i]];
     sync();
     // deferred scaling: L(k, a_m) = LD(k, a_m) / D_k
-    const int* mrow = I(DI_Mcol);
-    (void)mrow;
+#pragma unroll 1
     for (int i = lane; i < nv; i += 32) {
       int a = madr[i], n = ddepth[i]; float inv = invD[i];
       for (int m = 1; m <= n; m++) LD[a + m] *= inv;
@@ -401,35 +401,41 @@ struct Engine {
     sync();
   }
 
-  // ---- x <- M^-1 x with the factor above; level-synchronous over dof depth (mj_solveLD)
-  __device__ void solve(float* x) {
-    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
-    const int* dladr = I(DI_dlevel_adr); const int* dldof = I(DI_dlevel_dof);
-    const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
+  // ---- x <- M^-1 x with the factor above; level-synchronous over dof depth (mj_solveLD).
+  // backward (L^-T): every dof gathers from its descendants, deepest level first; forward (D^-1 then L^-1): a dof of
+  // level l has exactly l ancestors, so the trip count is uniform across the level.
+  __device__ __forceinline__ void solve(float* x) {
+    const int* mcol = I(DI_Mcol); const int* dladr = I(DI_dlevel_adr);
+    const int* bwp = I(DI_bw_pack); const int* fwp = I(DI_fw_pack); const int* dpack = I(DI_desc_pack);
     const float* LD = p_LD(); const float* invD = p_invD();
-    int maxd = dim(DD_maxdofdepth), nv = dim(DD_nv);
+    int maxd = dim(DD_maxdofdepth);
+#pragma unroll 1
     for (int l = maxd - 1; l >= 0; l--) {
+#pragma unroll 1
       for (int idx = dladr[l] + lane; idx < dladr[l + 1]; idx += 32) {
-        int j = dldof[idx]; const int* dp = dpack + dadr[j]; int n = dnum[j];
+        int w = bwp[idx], j = w & 255, n = (w >> 8) & 255; const int* dp = dpack + (w >> 16);
         float s0 = x[j], s1 = 0.f, s2 = 0.f, s3 = 0.f; int k = 0;
+#pragma unroll 1
         for (; k + 4 <= n; k += 4) {
           int p0 = dp[k], p1 = dp[k + 1], p2 = dp[k + 2], p3 = dp[k + 3];
           s0 = fmaf(-LD[p0 >> 16], x[p0 & 0xffff], s0); s1 = fmaf(-LD[p1 >> 16], x[p1 & 0xffff], s1);
           s2 = fmaf(-LD[p2 >> 16], x[p2 & 0xffff], s2); s3 = fmaf(-LD[p3 >> 16], x[p3 & 0xffff], s3);
         }
+#pragma unroll 1
         for (; k < n; k++) { int p0 = dp[k]; s0 = fmaf(-LD[p0 >> 16], x[p0 & 0xffff], s0); }
         x[j] = (s0 + s1) + (s2 + s3);
       }
       sync();
     }
-    for (int i = lane; i < nv; i += 32) x[i] *= invD[i];
-    sync();
-    for (int l = 1; l <= maxd; l++) {
+#pragma unroll 1
+    for (int l = 0; l <= maxd; l++) {
+#pragma unroll 1
       for (int idx = dladr[l] + lane; idx < dladr[l + 1]; idx += 32) {
-        int i = dldof[idx], a = madr[i], n = ddepth[i];
-        float s0 = x[i], s1 = 0.f; int k = 1;
-        for (; k + 2 <= n + 1; k += 2) { s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0); s1 = fmaf(-LD[a + k + 1], x[mcol[a + k + 1]], s1); }
-        for (; k <= n; k++) s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0);
+        int w = fwp[idx], i = w & 255, a = w >> 8;
+        float s0 = x[i] * invD[i], s1 = 0.f; int k = 1;
+#pragma unroll 1
+        for (; k + 1 <= l; k += 2) { s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0); s1 = fmaf(-LD[a + k + 1], x[mcol[a + k + 1]], s1); }
+        if (k <= l) s0 = fmaf(-LD[a + k], x[mcol[a + k]], s0);
         x[i] = s0 + s1;
       }
       sync();
@@ -724,8 +730,8 @@ struct Engine {
           float y;
           if (power == 1.f) y = x;
           else if (power == 2.f) y = (x <= mid) ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-          else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
-          else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+          else if (x <= mid) y = __powf(x, power) / __powf(mid, power - 1.f);
+          else y = 1.f - __powf(1.f - x, power) / __powf(1.f - mid, power - 1.f);
           imp = dmin + y * (dmax - dmin);
         }
       }
@@ -758,6 +764,8 @@ struct Engine {
   __device__ void build_A() {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum);
+    const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
+    const float* LDp = p_LD();
     int nisl = dim(DD_nisland);
     // island k is built by warp k % W; its column scratch (32 floats per dof of the island) sits at 32 * dofadr
     for (int k = wl; k < nisl; k += W) {
@@ -769,18 +777,26 @@ struct Engine {
         int j = j0 + lane; bool valid = j < n;
         float* x = scratch + lane;   // column, stride 32: lane-contiguous, conflict-free
         for (int c = 0; c < nd; c++) x[32 * c] = valid ? J[j * ldj + c] : 0.f;
-        // x <- L^-T x ; x <- D^-1 x ; x <- L^-1 x  (per-lane sequential sparse solve, uniform control flow)
-        for (int i = nd - 1; i >= 0; i--) {
-          float xi = x[32 * i]; int a = madr[d0 + i], dn = ddepth[d0 + i];
-#pragma unroll 4
-          for (int m = 1; m <= dn; m++) { int cc = mcol[a + m] - d0; x[32 * cc] -= p_LD()[a + m] * xi; }
+        // x <- L^-T x (gather from descendants, highest dof first), then x <- L^-1 D^-1 x (gather from ancestors):
+        // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent
+        for (int jj = nd - 1; jj >= 0; jj--) {
+          int dn = dnum[d0 + jj]; const int* dp = dpack + dadr[d0 + jj];
+          float s0 = x[32 * jj], s1 = 0.f; int k = 0;
+          for (; k + 2 <= dn; k += 2) {
+            int p0 = dp[k], p1 = dp[k + 1];
+            s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * ((p1 & 0xffff) - d0)], s1);
+          }
+          if (k < dn) { int p0 = dp[k]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
+          x[32 * jj] = s0 + s1;
         }
-        for (int i = 0; i < nd; i++) x[32 * i] *= p_invD()[d0 + i];
         for (int i = 0; i < nd; i++) {
-          float s = x[32 * i]; int a = madr[d0 + i], dn = ddepth[d0 + i];
-#pragma unroll 4
-          for (int m = 1; m <= dn; m++) { int cc = mcol[a + m] - d0; s -= p_LD()[a + m] * x[32 * cc]; }
-          x[32 * i] = s;
+          int a = madr[d0 + i], dn = ddepth[d0 + i];
+          float s0 = x[32 * i] * p_invD()[d0 + i], s1 = 0.f; int m = 1;
+          for (; m + 1 <= dn; m += 2) {
+            s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0); s1 = fmaf(-LDp[a + m + 1], x[32 * (mcol[a + m + 1] - d0)], s1);
+          }
+          if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0);
+          x[32 * i] = s0 + s1;
         }
         // lower triangle: A[i][j] = J_i . x for i >= j
         for (int i = j0; i < n; i++) {
@@ -890,61 +906,29 @@ struct Engine {
     team_sync();
   }
 
-  // ---- qfrc_constraint = J' f ; qacc = qacc_smooth + M^-1 qfrc_constraint
-  __device__ void finish_constraint() {
+  // ---- qfrc_constraint = J' f, also copied into qacc as the right-hand side of the pass-1 solve
+  __device__ void qfrc_constraint() {
     const int* disl = I(DI_dof_island); const int* iadr = I(DI_island_dofadr);
     int nv = dim(DD_nv);
+#pragma unroll 1
     for (int d = lane; d < nv; d += 32) {
-      int k = disl[d]; int n = p_isl_n()[k]; float s = 0.f;
-      if (n) {
-        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = d - iadr[k]; const float* J = p_arena() + p_isl_J()[k];
-        for (int i = 0; i < n; i++) s = fmaf(J[i * ldj + c], p_row_f()[e0 + i], s);
+      int k = disl[d]; int n = p_isl_n()[k]; float s0 = 0.f, s1 = 0.f;
+      if (n && p_misc()[MISC_NEFC] > 0) {
+        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = d - iadr[k]; const float* J = p_arena() + p_isl_J()[k]; const float* f = p_row_f() + e0;
+        int i = 0;
+        for (; i + 2 <= n; i += 2) { s0 = fmaf(J[i * ldj + c], f[i], s0); s1 = fmaf(J[(i + 1) * ldj + c], f[i + 1], s1); }
+        if (i < n) s0 = fmaf(J[i * ldj + c], f[i], s0);
       }
-      p_qfc()[d] = s; p_qacc()[d] = s;
+      p_qfc()[d] = s0 + s1; p_qacc()[d] = s0 + s1;
     }
-    sync();
-    solve(p_qacc());
-    for (int d = lane; d < nv; d += 32) p_qacc()[d] += p_qas()[d];
     sync();
   }
 
-  // ---- mj_forward
 #ifdef B2_PHASE_TIMING
 #define B2_TICK(k) do { long long t_ = clock64(); if (tl == 0 && B.phase_cycles) atomicAdd(&B.phase_cycles[k], (unsigned long long)(t_ - tphase)); tphase = t_; } while (0)
 #else
 #define B2_TICK(k) do { } while (0)
 #endif
-  // ---- mj_forward.  Warp 0 runs the dynamics chain (velocities, CRB, M, L'DL, qacc_smooth) while warp 1 % W runs the
-  // contact chain (narrow phase, row compaction); the J fill, A build and PGS sweeps use the whole team.
-  __device__ __forceinline__ void forward(unsigned long long* counters) {
-    int nv = dim(DD_nv);
-#ifdef B2_PHASE_TIMING
-    long long tphase = clock64();
-#endif
-    if (wl == 0) { kinematics(); com_pos(); }
-    team_sync(); B2_TICK(0);
-    if (wl == 0) {
-      vel_pass(); backward_pass(); mass_and_smooth();
-      factor(0.f);
-      for (int d = lane; d < nv; d += 32) p_qas()[d] = p_qfs()[d];
-      sync();
-      solve(p_qas());
-    }
-    if (wl == (1 % W)) { collision(counters); make_rows(counters); }
-    team_sync(); B2_TICK(1);
-    if (p_misc()[MISC_NEFC] > 0) {
-      fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11);
-      if (wl == 0) finish_constraint();
-      team_sync(); B2_TICK(12);
-    } else {
-      if (wl == 0) {
-        for (int d = lane; d < nv; d += 32) { p_qacc()[d] = p_qas()[d]; p_qfc()[d] = 0.f; }
-        if (lane == 0) p_misc()[MISC_ITERS] = 0;
-      }
-      team_sync();
-    }
-  }
-
   __device__ void reset_data() {   // warp-level (called by warp 0)
     const float* q0 = F(DF_qpos0);
     int nq = dim(DD_nq), nv = dim(DD_nv), nu = dim(DD_nu);
@@ -959,41 +943,67 @@ struct Engine {
     return __any_sync(B2_FULL, bad);
   }
 
-  // ---- mj_step with the Euler integrator (implicit joint damping) -- SURVEY B.0 / B.7.
-  // integrate == false stops after mj_forward.  The kernel calls this from exactly one site and the NaN retry is a
-  // loop, so the whole pipeline is inlined once (kernel parameters stay constant-bank operands, code stays small).
+  // ---- mj_step with the Euler integrator (implicit joint damping) -- SURVEY B.0 / B.7 (integrate == false: mj_forward).
+  // The step is a loop over three passes that share ONE call site of factor() and solve():
+  //   pass 0  velocities, CRB, M, bias | contacts, rows     -> factor(M)        -> qacc_smooth = M^-1 qfrc_smooth
+  //   pass 1  J, A, PGS (whole team), qfrc_constraint       ->                    qacc = qacc_smooth + M^-1 qfrc_constraint
+  //   pass 2  (mj_Euler)                                    -> factor(M + h D)  -> qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint)
+  // Warp 0 runs the dynamics chain while warp 1 % W runs the contact chain; the NaN retry of mj_step is the outer loop.
   __device__ __forceinline__ void step_euler(unsigned long long* counters, bool integrate) {
     float* time = p_time();
     const int* jtype = I(DI_jnt_type); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
     int nq = dim(DD_nq), nv = dim(DD_nv), njnt = dim(DD_njnt); float h = P.opt[DO_timestep];
+#ifdef B2_PHASE_TIMING
+    long long tphase = clock64();
+#endif
     if (integrate && wl == 0) {
       if (bad_state(p_qpos(), nq) | bad_state(p_qvel(), nv)) {
         reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); }
       }
     }
+#pragma unroll 1
     for (int attempt = 0; attempt < 2; attempt++) {
-      forward(counters);
-      if (!integrate || attempt == 1) break;
-      if (wl == 0) {
-        bool bad = bad_state(p_qacc(), nv);
-        if (bad) { reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); } }
-        if (lane == 0) p_misc()[MISC_FLAG] = bad ? 1 : 0;
+      if (wl == 0) { kinematics(); com_pos(); }
+      team_sync(); B2_TICK(0);
+      bool restart = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; pass++) {
+        if (pass == 0) {
+          if (wl == 0) { vel_pass(); backward_pass(); mass_and_smooth(); }
+          if (wl == (1 % W)) { collision(counters); make_rows(counters); }
+        } else if (pass == 1) {
+          if (p_misc()[MISC_NEFC] > 0) { fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11); }
+          else if (tl == 0) p_misc()[MISC_ITERS] = 0;
+          if (wl == 0) qfrc_constraint();
+        } else {
+          if (!integrate) break;
+          if (attempt == 0) {      // mj_checkAcc
+            if (wl == 0) { bool bad = bad_state(p_qacc(), nv); if (lane == 0) p_misc()[MISC_FLAG] = bad ? 1 : 0; }
+            team_sync();
+            if (p_misc()[MISC_FLAG]) {
+              if (wl == 0) { reset_data(); if (lane == 0) { *time = 0.f; if (counters) atomicAdd(&counters[CTR_NAN_RESET], 1ull); } }
+              team_sync(); restart = true; break;
+            }
+          }
+          if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
+        }
+        if (wl == 0) {
+          if (pass != 1) factor(pass == 0 ? 0.f : h);
+          float* x = b2_smem + wb + (pass == 0 ? B.off.qas : pass == 1 ? B.off.qacc : B.off.tmp);
+          if (pass == 0) { for (int d = lane; d < nv; d += 32) x[d] = p_qfs()[d]; sync(); }
+          solve(x);
+          if (pass == 1) { for (int d = lane; d < nv; d += 32) x[d] += p_qas()[d]; sync(); }
+        }
+        team_sync(); B2_TICK(1 + pass);
       }
-      team_sync();
-      if (!p_misc()[MISC_FLAG]) break;
+      if (!restart) break;
     }
     if (!integrate) return;
-#ifdef B2_PHASE_TIMING
-    long long tphase = clock64();
-#endif
     if (wl == 0) {
-      // (M + h*diag(damping)) qacc' = qfrc_smooth + qfrc_constraint
-      factor(h);
-      for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d];
-      sync();
-      solve(p_tmp());
+#pragma unroll 1
       for (int d = lane; d < nv; d += 32) { p_qvel()[d] += h * p_tmp()[d]; p_warm()[d] = p_qacc()[d]; }
       sync();
+#pragma unroll 1
       for (int j = lane; j < njnt; j += 32) {
         int qa = jq[j], da = jd[j];
         if (jtype[j] == 0) {

@@ -23,7 +23,7 @@ B2DEV_MAGIC = 0x42324456  # "B2DV"
 
 DIMS = ["nq", "nv", "nu", "nbody", "njnt", "ntree", "nroot", "ncg", "npair", "nM", "nlim", "nisland", "maxdepth",
         "maxdofdepth", "iterations", "integrator", "solver", "nprm", "nmaskw", "ndesc", "maxraw", "nsite",
-        "ls_iterations", "maxspan", "npairtab"]
+        "ls_iterations", "maxspan", "npairtab", "nfacstep"]
 OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "impratio", "meaninertia", "pgs_scale", "ls_tolerance"]
 
 INT_FIELDS = [
@@ -34,6 +34,7 @@ INT_FIELDS = [
     "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid",
     "dof_bodyid", "dof_Madr", "dof_depth", "dof_isrot", "dof_island", "dof_tree", "dof_actadr", "dof_actnum",
     "dof_jnt", "dofact", "Mcol", "dlevel_adr", "dlevel_dof", "dof_descadr", "dof_descnum", "desc_pack", "pair_mn",
+    "bw_pack", "fw_pack", "fac_step", "fac_ops",
     "tree_dofadr", "tree_dofnum", "island_dofadr", "island_dofnum",
     "act_dofid", "act_ctrllimited", "act_forcelimited",
     "lim_jnt",
@@ -132,6 +133,28 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
         for mm in range(1, n + 1):
             pair_mn.append(mm | (n << 8))
     T["pair_mn"] = i32(pair_mn if pair_mn else [0])
+    # level-ordered packed per-dof records for the L'DL solves (same order as dlevel_dof):
+    #   bw_pack = dof | n_desc << 8 | desc_adr << 16      fw_pack = dof | Madr << 8
+    assert nv < 256 and len(desc_dof) < 65536 and max(desc_num, default=0) < 256
+    T["bw_pack"] = i32([(d | (int(desc_num[d]) << 8) | (int(desc_adr[d]) << 16)) for d in dl] if dl else [0])
+    T["fw_pack"] = i32([(d | (int(A["dof_Madr"][d]) << 8)) for d in dl] if dl else [0])
+    # flat program of the L'DL factorisation: one step per eliminated dof k (leaves first) with depth > 0,
+    #   fac_step = diag_adr | n_ops << 10 | op_adr << 16 ; fac_ops = tgt | a << 10 | b << 20  (LD[tgt] -= LD[a]*LD[b]/LD[diag])
+    assert nM < 1024
+    fac_step, fac_ops = [], []
+    for k in range(nv - 1, -1, -1):
+        ak = int(A["dof_Madr"][k]); dk = int(D["dof_depth"][k])
+        if dk == 0:
+            continue
+        start = len(fac_ops)
+        for n in range(1, dk + 1):
+            for mm in range(1, n + 1):
+                aa = int(A["dof_Madr"][Mcol[ak + mm]])
+                fac_ops.append((aa + (n - mm)) | ((ak + mm) << 10) | ((ak + n) << 20))
+        cnt = len(fac_ops) - start
+        assert cnt < 64 and start < 65536
+        fac_step.append(ak | (cnt << 10) | (start << 16))
+    T["fac_step"] = i32(fac_step if fac_step else [0]); T["fac_ops"] = i32(fac_ops if fac_ops else [0])
     ndesc = len(desc_dof)
     T["tree_dofadr"] = i32(D["tree_dofadr"]); T["tree_dofnum"] = i32(D["tree_dofnum"])
     nisland = int(island_of_tree.max()) + 1 if ntree else 0
@@ -222,7 +245,7 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
     T["dims"] = i32([int(A["nq"]), nv, nu, nbody, njnt, ntree, nroot, ncg, npair, nM, nlim, nisland,
                      int(D["dims"][14]), maxdd, int(A["iterations"]), int(A["integrator"]), int(A["solver"]), nprm,
                      nmaskw, ndesc, maxraw, int(A["nsite"]), int(A["ls_iterations"]), int(isl_num.max()) if nisland else 0,
-                     len(pair_mn)])
+                     len(pair_mn), len(fac_step)])
     return T
 
 

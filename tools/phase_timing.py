@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 16)()
 L = capi.lib(); L.b2_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 L.b2_phase_cycles(env.batch.handle, out)
-names = ["kinematics+com_pos", "dynamics chain || contact chain", "-", "-", "-", "-", "-", "-", "-",
+names = ["kinematics+com_pos", "pass0: dynamics||contacts + factor + solve", "pass1: (J,A,PGS below) + qfc + solve", "pass2: factor(M+hD) + solve", "-", "-", "-", "-", "-",
          "fill_rows", "build_A", "pgs", "finish", "euler(factor+solve+integrate)"]
 tot = sum(out[:14]) or 1
 st = env.episode_stats()
