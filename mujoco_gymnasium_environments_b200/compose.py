@@ -10,7 +10,10 @@ where the reference package is not installed.
 """
 from __future__ import annotations
 
+import importlib
 import os
+import sys
+import types
 import xml.etree.ElementTree as ET
 
 
@@ -57,6 +60,97 @@ def quadruped_parkour_mjcf(assets_root: str) -> str:
     return ET.tostring(base, encoding="unicode")
 
 
+# ---------------------------------------------------------------------------------------------- inline generators
+# Five reference envs build their MJCF in Python (dancing ``dancing_env.py:156-678``, soccer ``soccer_env.py:120-220``,
+# martial arts ``martial_arts_env.py:150-381``, construction ``construction_env.py:177-494``, rescue
+# ``rescue_env.py:121-277``).  Neither ``mujoco`` nor ``gymnasium`` is installed, so stand-in modules are registered whose
+# ``MjModel.from_xml_string`` captures its argument; the *unmodified* reference module is imported from ``assets_root``
+# and its constructor runs up to that call.  Only the compiled numeric tables are committed.
+class _Captured(Exception):
+    def __init__(self, xml):
+        self.xml = xml
+
+
+def _install_stubs():
+    mj = types.ModuleType("mujoco")
+
+    class MjModel:
+        @staticmethod
+        def from_xml_string(s, *a, **k):
+            raise _Captured(s)
+
+        @staticmethod
+        def from_xml_path(p, *a, **k):
+            with open(p) as f:
+                raise _Captured(f.read())
+
+    mj.MjModel = MjModel
+    mj.MjData = object
+    mj.viewer = types.ModuleType("mujoco.viewer")
+    sys.modules["mujoco"] = mj
+    sys.modules["mujoco.viewer"] = mj.viewer
+
+    gym = types.ModuleType("gymnasium")
+
+    class Env:
+        pass
+
+    gym.Env = Env
+    gym.register = lambda *a, **k: None
+    spaces = types.ModuleType("gymnasium.spaces")
+    spaces.Box = lambda *a, **k: None
+    spaces.Discrete = lambda *a, **k: None
+    spaces.Dict = lambda *a, **k: None
+    utils = types.ModuleType("gymnasium.utils")
+    seeding = types.ModuleType("gymnasium.utils.seeding")
+    import numpy as np
+    seeding.np_random = lambda seed=None: (np.random.default_rng(seed), seed)
+    utils.seeding = seeding
+    gym.spaces = spaces
+    gym.utils = utils
+    envs = types.ModuleType("gymnasium.envs")
+    reg = types.ModuleType("gymnasium.envs.registration")
+    reg.register = lambda *a, **k: None
+    envs.registration = reg
+    gym.envs = envs
+    for n, m in (("gymnasium", gym), ("gymnasium.spaces", spaces), ("gymnasium.utils", utils),
+                 ("gymnasium.utils.seeding", seeding), ("gymnasium.envs", envs), ("gymnasium.envs.registration", reg)):
+        sys.modules[n] = m
+
+
+TARGETS = {
+    "dancing": ("humanoid_dancing_env", "dancing_env", "HumanoidDancingEnv"),
+    "soccer": ("humanoid_soccer_env", "soccer_env", "HumanoidSoccerEnv"),
+    "martial_arts": ("humanoid_martial_arts_env", "martial_arts_env", "HumanoidMartialArtsEnv"),
+    "construction": ("humanoid_construction_env", "construction_env", "HumanoidConstructionEnv"),
+    "rescue": ("bipedal_rescue_env", "rescue_env", "BipedalRescueEnv"),
+    "arm": ("robotic_arm_assembly_env", "assembly_env", "RoboticArmAssemblyEnv"),
+}
+
+
+def inline_mjcf(task: str, root: str) -> str:
+    pkg, mod, cls = TARGETS[task]
+    _install_stubs()
+    sys.path.insert(0, os.path.join(root, pkg))
+    cwd = os.getcwd()
+    os.chdir("/tmp")          # martial arts rewrites an asset file relative to its module; keep our tree clean
+    try:
+        m = importlib.import_module(mod)
+        try:
+            getattr(m, cls)()
+        except _Captured as c:
+            return c.xml
+        except OSError as e:   # read-only reference tree: martial arts writes its scene file before loading it
+            raise RuntimeError(f"{task}: constructor failed before the model was built: {e}")
+    finally:
+        os.chdir(cwd)
+        sys.path.pop(0)
+    raise RuntimeError(f"{task}: constructor finished without building a model")
+
+
+
 COMPOSERS = {
     "quadruped_parkour": quadruped_parkour_mjcf,
+    "humanoid_dancing": lambda root: inline_mjcf("dancing", root),
 }
+

@@ -28,7 +28,7 @@ struct B2Batch {
   float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
   float *d_act, *d_obs, *d_rew, *d_inject; uint8_t *d_term, *d_trunc;
   cudaStream_t own_stream;
-  int obs_dim, act_dim, nti, ntf;
+  int obs_dim, act_dim, nti, ntf, ninj;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -59,10 +59,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     for (int i = tl; i < nv; i += TEAM) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
     for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
     if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; }
-    if (Task::NTI > 0) {
-      if (tl < Task::NTI) s_ti[tl] = B.ti[(size_t)env * B.nti + tl];
-      if (tl < Task::NTF) s_tf[tl] = B.tf[(size_t)env * B.ntf + tl];
-    }
+    for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
+    for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
   }
   E.team_sync();
 
@@ -71,18 +69,18 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   if (mode == MODE_PHYS) nsub = B.nsub;
   else if (mode == MODE_FORWARD) nsub = 1;
   else if (mode == MODE_RESET) {
-    if (w0) Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + 4 * env : nullptr);
+    if (w0) Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + (size_t)Task::NINJ * env : nullptr);
     E.team_sync(); nsub = Task::SETTLE; stage = 1;
   } else {
-    if (w0) Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act);
+    if (w0) { Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act); Task::pre_physics(E, tp, s_ti, s_tf); }
     E.team_sync(); nsub = Task::FRAME_SKIP;
   }
   while (true) {
-    if (nsub > 0) { E.step_euler(ctr, mode != MODE_FORWARD); nsub--; continue; }
+    if (nsub > 0) { E.step(ctr, mode != MODE_FORWARD); nsub--; continue; }
     if (mode == MODE_PHYS || mode == MODE_FORWARD) break;
     if (stage == 0) {   // end of the control step
       if (w0) {
-        Task::post_physics(E, tp, s_ti);
+        Task::post_physics(E, tp, s_ti, s_tf);
         Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
         E.sync();
         if (lane == 0) {
@@ -106,9 +104,9 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
       }
       E.team_sync();
       nsub = Task::SETTLE; stage = 1;
-      if (nsub == 0) { if (w0) Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); break; }
+      if (nsub == 0) { if (w0) { Task::after_settle(E, tp, s_ti, s_tf); Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); } break; }
     } else {            // end of the settle steps of a reset
-      if (w0) Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim);
+      if (w0) { Task::after_settle(E, tp, s_ti, s_tf); Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); }
       break;
     }
   }
@@ -143,23 +141,23 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     for (int i = tl; i < nv; i += TEAM) { gv[i] = E.p_qvel()[i]; gw[i] = E.p_warm()[i]; ga[i] = E.p_qapp()[i]; }
     for (int i = tl; i < nu; i += TEAM) gc[i] = E.p_ctrl()[i];
     if (tl == 0) B.time[env] = *E.p_time();
-    if (Task::NTI > 0) {
-      if (tl < Task::NTI) B.ti[(size_t)env * B.nti + tl] = s_ti[tl];
-      if (tl < Task::NTF) B.tf[(size_t)env * B.ntf + tl] = s_tf[tl];
-    }
+    for (int i = tl; i < Task::NTI; i += TEAM) B.ti[(size_t)env * B.nti + i] = s_ti[i];
+    for (int i = tl; i < Task::NTF; i += TEAM) B.tf[(size_t)env * B.ntf + i] = s_tf[i];
   }
 }
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
+  template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void reset_state(EN& E, const TaskParams&, const BatchView&, int, int*, float*, const float*) {
     E.reset_data(); if (E.lane == 0) *E.p_time() = 0.f; E.sync();
   }
   template <class EN> __device__ static void observe(EN&, const TaskParams&, float*) {}
   template <class EN> __device__ static float reward_and_done(EN&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
-  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*) {}
+  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*, float*) {}
 };
 
 __global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
@@ -203,6 +201,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   switch (b->tp.task) {
     case TASK_NONE: return launch_task<NoTask>(b, mode, inject, s);
     case TASK_QUADRUPED_PARKOUR: return launch_task<QuadrupedTask>(b, mode, inject, s);
+    case TASK_HUMANOID_DANCING: return launch_task<DancingTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -236,7 +235,7 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
   for (int k = 0; k < DD_COUNT; k++) dm.dim[k] = dims[k];
   const double* opt = flts + dm.foff[DF_opt];
   for (int k = 0; k < DO_COUNT; k++) dm.opt[k] = (float)opt[k];
-  if (dm.dim[DD_integrator] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the Euler integrator is built in this round"); }
+  if (dm.dim[DD_integrator] != 0 && dm.dim[DD_integrator] != 1) { delete m; return fail(B2_ERR_UNSUPPORTED, "integrator must be Euler or RK4"); }
   if (dm.dim[DD_solver] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the PGS solver is built in this round"); }
   if (dm.dim[DD_nisland] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "too many islands"); }
   std::vector<float> f32(n_flts);
@@ -257,17 +256,20 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
+  int keep_frames = 0; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-    case TASK_QUADRUPED_PARKOUR: b->obs_dim = QuadrupedTask::OBS; b->act_dim = QuadrupedTask::ACT; b->nti = QuadrupedTask::NTI; b->ntf = QuadrupedTask::NTF; break;
+#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES
+    case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
+    case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
-  v.seed = seed; v.env_offset = env_offset;
+  v.seed = seed; v.env_offset = env_offset; v.keep_frames = keep_frames; v.inject_stride = b->ninj;
   // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped); rows: 4 per contact + limits
   int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
   int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
@@ -278,13 +280,13 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
-  int raw_need = r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
-  int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim)) ? 0 : 32 * dim[DD_nv];
+  int raw_need = 2 * r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
+  int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim, keep_frames)) ? 0 : 32 * dim[DD_nv];
   (void)maxspan;
   int arena = (o_arena > 0 ? o_arena : 4608) + scratch;
   if (arena < raw_need) arena = raw_need;
   v.arena_floats = r4(arena);
-  v.ws_floats = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, &v.off);
+  v.ws_floats = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, b->nti, b->ntf, &v.off);
   v.model_floats = model_smem_floats(m->dm.n_ints, m->dm.n_flts);
   const int smem_max = 227 * 1024;
   int epb = (smem_max - v.model_floats * 4 - 16) / (v.ws_floats * 4);
@@ -315,7 +317,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMallocHost(&b->h_act, N * ad * 4)); CK(cudaMallocHost(&b->h_obs, N * od * 4)); CK(cudaMallocHost(&b->h_rew, N * 4));
   CK(cudaMallocHost(&b->h_term, N)); CK(cudaMallocHost(&b->h_trunc, N));
   CK(cudaMalloc(&b->d_act, N * ad * 4)); CK(cudaMalloc(&b->d_obs, N * od * 4)); CK(cudaMalloc(&b->d_rew, N * 4));
-  CK(cudaMalloc(&b->d_term, N)); CK(cudaMalloc(&b->d_trunc, N)); CK(cudaMalloc(&b->d_inject, N * 4 * 4));
+  CK(cudaMalloc(&b->d_term, N)); CK(cudaMalloc(&b->d_trunc, N)); CK(cudaMalloc(&b->d_inject, N * (size_t)b->ninj * 4));
   CK(cudaStreamCreate(&b->own_stream));
   *out = b;
   return B2_OK;

@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include "../../include/b2_device_layout.h"
 #include "b2_math.cuh"
+#include "b2_collide.cuh"
 
 namespace b2 {
 
@@ -52,7 +53,7 @@ extern __shared__ __align__(128) float b2_smem[];
 
 #define B2_WS_FLOAT_FIELDS(X) X(qpos) X(qvel) X(warm) X(ctrl) X(qapp) X(xpos) X(xmat) X(cdof) X(rootcom) \
   X(xquat) X(xipos) X(cvel) X(cacc) X(cinert) X(M) X(LD) X(invD) X(qfs) X(qas) X(qfc) X(qacc) X(tmp) X(con) \
-  X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act)
+  X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc)
 #define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
 
 struct WsOff {
@@ -67,7 +68,7 @@ __host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline int model_smem_floats(int n_ints, int n_flts) { return (r4(n_ints) + r4(n_flts) + 31) & ~31; }
 
 // per-warp carve-up in floats; returns the slice size (multiple of 32 floats)
-__host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int arena_floats, WsOff* o) {
+__host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int arena_floats, int nti, int ntf, WsOff* o) {
   int off = 0;
   auto take = [&](int n_words) { int r = off; off += r4(n_words); return r; };
   int nq = dim[DD_nq], nv = dim[DD_nv], nu = dim[DD_nu], nb = dim[DD_nbody], nM = dim[DD_nM];
@@ -75,16 +76,21 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   WsOff t;
   t.qpos = take(nq); t.qvel = take(nv); t.warm = take(nv); t.ctrl = take(nu > 0 ? nu : 1); t.qapp = take(nv);
   t.xpos = take(3 * nb);
-  // contiguous block [xmat .. cinert]: dead once the J rows are filled, reused as scratch by the A build
-  t.xmat = take(9 * nb); t.cdof = take(6 * nv); t.rootcom = take(3 * (nroot > 0 ? nroot : 1));
-  t.xquat = take(4 * nb); t.xipos = take(3 * nb); t.cvel = take(6 * nb); t.cacc = take(6 * nb); t.cinert = take(10 * nb);
+  // contiguous block [xmat .. rootcom]: dead once the J rows are filled, reused as scratch by the A build; xquat and
+  // rootcom sit at its end so a task that reads them after the step (keep_frames) only shortens the reusable part
+  t.xmat = take(9 * nb); t.cdof = take(6 * nv); t.xipos = take(3 * nb); t.cvel = take(6 * nb); t.cacc = take(6 * nb);
+  t.cinert = take(10 * nb); t.xquat = take(4 * nb); t.rootcom = take(3 * (nroot > 0 ? nroot : 1));
   t.M = take(nM); t.LD = take(nM); t.invD = take(nv); t.qfs = take(nv); t.qas = take(nv); t.qfc = take(nv);
   t.qacc = take(nv); t.tmp = take(nv);
   t.con = take(con_cap * B2_CON_STRIDE); t.lim_row = take(2 * (nlim > 0 ? nlim : 1)); t.con_row = take(con_cap);
   t.row_info = take(row_cap); t.row_R = take(row_cap); t.row_b = take(row_cap); t.row_f = take(row_cap); t.row_res = take(row_cap);
   t.isl_n = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
   t.isl_A = take(B2_MAX_ISLANDS); t.isl_ldj = take(B2_MAX_ISLANDS);
-  t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(16); t.tf = take(8); t.act = take(40);
+  t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(nti > 0 ? nti : 1); t.tf = take(ntf > 0 ? ntf : 1);
+  t.act = take(40);
+  bool rk4 = dim[DD_integrator] == 1;
+  t.rk_q0 = take(rk4 ? nq : 0); t.rk_v0 = take(rk4 ? nv : 0); t.rk_sv = take(rk4 ? nv : 0); t.rk_sa = take(rk4 ? nv : 0);
+  t.xfrc = take(0);
   t.arena = take(arena_floats);
   if (o) *o = t;
   return (off + 31) & ~31;
@@ -107,15 +113,20 @@ struct BatchView {
   int nsub;                                          // physics sub-steps for MODE_PHYS
   int env_offset;                                    // global index of env 0 (multi-GPU sharding keeps RNG streams fixed)
   int envs_per_block; int ws_floats; int model_floats;   // shared-memory slices, in floats
+  int keep_frames;                                   // the task reads xquat / subtree com of the last forward pass
+  int inject_stride;                                 // floats per env of the injected reset draws
+  float* xfrc_applied;                               // [N][6*nbody] Cartesian applied forces, or null
   WsOff off;
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PHYS = 2, MODE_FORWARD = 3 };
 
-// floats in the contiguous dead block [xmat .. cinert]
-__host__ __device__ inline int dead_block_floats(const int* dim) {
+// floats of the contiguous dead block [xmat .. rootcom] the A build may overwrite
+__host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames) {
   int nb = dim[DD_nbody], nv = dim[DD_nv], nroot = dim[DD_nroot];
-  return r4(9 * nb) + r4(6 * nv) + r4(3 * (nroot > 0 ? nroot : 1)) + r4(4 * nb) + r4(3 * nb) + r4(6 * nb) + r4(6 * nb) + r4(10 * nb);
+  int n = r4(9 * nb) + r4(6 * nv) + r4(3 * nb) + r4(6 * nb) + r4(6 * nb) + r4(10 * nb);
+  if (!keep_frames) n += r4(4 * nb) + r4(3 * (nroot > 0 ? nroot : 1));
+  return n;
 }
 
 // -------------------------------------------------------------------------------------------- engine (one warp)
@@ -453,80 +464,56 @@ struct Engine {
 #pragma unroll
       for (int c = 0; c < 3; c++) mat[3 * r + c] = xm[3 * r] * lm[c] + xm[3 * r + 1] * lm[3 + c] + xm[3 * r + 2] * lm[6 + c];
   }
-  __device__ __forceinline__ static void put_raw(float* dst, float dist, V3 pos, V3 n, V3 t) {
-    dst[0] = dist; st3(dst + 1, pos); st3(dst + 4, n); st3(dst + 7, t);
-  }
-  // writes up to maxn raw contacts (10 floats each) to dst, returns the count
-  __device__ int collide(int t1, int t2, V3 p1, const float* m1, V3 p2, const float* m2, const float* s2, float margin,
-                         float* dst, int maxn) const {
-    if (t1 != 0) return 0;   // only plane-vs-primitive pairs are built this round
-    V3 n = matcol(m1, 2);
-    if (t2 == 2) {
-      float cd = dot(p2 - p1, n);
-      if (cd > margin + s2[0]) return 0;
-      float dist = cd - s2[0];
-      put_raw(dst, dist, p2 + n * (-dist * 0.5f - s2[0]), n, v3(0, 0, 0));
-      return 1;
-    }
-    if (t2 == 3) {
-      V3 ax = matcol(m2, 2); int cnt = 0;
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        V3 pe = s ? p2 - ax * s2[1] : p2 + ax * s2[1];
-        float cd = dot(pe - p1, n);
-        if (cd > margin + s2[0]) continue;
-        float dist = cd - s2[0];
-        put_raw(dst + 10 * cnt, dist, pe + n * (-dist * 0.5f - s2[0]), n, ax);
-        cnt++;
-      }
-      return cnt;
-    }
-    if (t2 == 6) {
-      float dist = dot(p2 - p1, n); int cnt = 0;
-      for (int i = 0; i < 8; i++) {
-        V3 v = v3((i & 1) ? s2[0] : -s2[0], (i & 2) ? s2[1] : -s2[1], (i & 4) ? s2[2] : -s2[2]);
-        V3 cn = mulmat(m2, v);
-        float ld = dot(n, cn);
-        if (dist + ld > margin || ld > 0.f) continue;
-        float d = dist + ld;
-        put_raw(dst + 10 * cnt, d, cn + p2 - n * (d * 0.5f), n, v3(0, 0, 0));
-        if (++cnt >= 4 || cnt >= maxn) return cnt;
-      }
-      return cnt;
-    }
-    return 0;
-  }
+  // candidate pairs are culled first (bounding spheres / plane distance) and the survivors compacted, in pair order,
+  // into an active list, so the narrow phase runs one *surviving* pair per lane
   __device__ void collision(unsigned long long* counters) {
     const int* pc1 = I(DI_pair_cg1); const int* pc2 = I(DI_pair_cg2); const int* pprm = I(DI_pair_prm);
     const int* praw = I(DI_pair_rawadr); const int* pmax = I(DI_pair_maxcon); const int* cgtype = I(DI_cg_type);
+    const int* cgbody = I(DI_cg_body); const float* cgpos = F(DF_cg_pos); const float* cgmat = F(DF_cg_mat);
     const float* cgsize = F(DF_cg_size); const float* cgrb = F(DF_cg_rbound); const float* prm = F(DF_prm);
     int npair = dim(DD_npair);
-    // raw slots: [count(int) per pair | 10 floats per raw contact] in the arena
-    int* rcount = (int*)p_arena(); float* rdata = p_arena() + r4(npair);
-    for (int p = lane; p < npair; p += 32) {
-      int g1 = pc1[p], g2 = pc2[p]; float margin = prm[B2DEV_PRM_STRIDE * pprm[p]];
-      V3 p1, p2; float m1[9], m2[9];
-      geom_pose(g1, p1, m1); geom_pose(g2, p2, m2);
-      int n = 0;
-      bool cull;
-      if (cgtype[g1] == 0) cull = dot(p2 - p1, matcol(m1, 2)) > cgrb[g2] + margin;
-      else { V3 d = p2 - p1; float bd = cgrb[g1] + cgrb[g2] + margin; cull = dot(d, d) > bd * bd; }
-      if (!cull) n = collide(cgtype[g1], cgtype[g2], p1, m1, p2, m2, cgsize + 3 * g2, margin, rdata + 10 * praw[p], pmax[p]);
-      rcount[p] = n;
+    // arena: [count per active pair | active pair ids | 10 floats per raw contact slot]
+    int* rcount = (int*)p_arena(); int* alist = rcount + r4(npair); float* rdata = p_arena() + 2 * r4(npair);
+    const unsigned lt = (1u << lane) - 1u;
+    int nact = 0;
+    for (int p0 = 0; p0 < npair; p0 += 32) {
+      int p = p0 + lane; bool keep = false;
+      if (p < npair) {
+        int g1 = pc1[p], g2 = pc2[p]; float margin = prm[B2DEV_PRM_STRIDE * pprm[p]];
+        int b1 = cgbody[g1], b2 = cgbody[g2];
+        V3 q1 = ld3(p_xpos() + 3 * b1) + mulmat(p_xmat() + 9 * b1, ld3(cgpos + 3 * g1));
+        V3 q2 = ld3(p_xpos() + 3 * b2) + mulmat(p_xmat() + 9 * b2, ld3(cgpos + 3 * g2));
+        V3 d = q2 - q1;
+        if (cgtype[g1] == 0) {
+          V3 n = mulmat(p_xmat() + 9 * b1, matcol(cgmat + 9 * g1, 2));
+          keep = !(dot(d, n) > cgrb[g2] + margin);
+        } else { float bd = cgrb[g1] + cgrb[g2] + margin; keep = !(dot(d, d) > bd * bd); }
+      }
+      unsigned m = __ballot_sync(B2_FULL, keep);
+      if (keep) alist[nact + __popc(m & lt)] = p;
+      nact += __popc(m);
     }
     sync();
-    // ordered compaction (pair order == MuJoCo contact order)
+    for (int k = lane; k < nact; k += 32) {
+      int p = alist[k], g1 = pc1[p], g2 = pc2[p]; float margin = prm[B2DEV_PRM_STRIDE * pprm[p]];
+      V3 p1, p2; float m1[9], m2[9];
+      geom_pose(g1, p1, m1); geom_pose(g2, p2, m2);
+      rcount[k] = collide_pair(cgtype[g1], cgtype[g2], p1, m1, cgsize + 3 * g1, p2, m2, cgsize + 3 * g2, margin,
+                               rdata + B2_RAW * praw[p], pmax[p]);
+    }
+    sync();
+    // ordered compaction (active list is in pair order == MuJoCo contact order)
     int base = 0, dropped = 0;
-    for (int p0 = 0; p0 < npair; p0 += 32) {
-      int p = p0 + lane; int n = (p < npair) ? rcount[p] : 0;
+    for (int k0 = 0; k0 < nact; k0 += 32) {
+      int k = k0 + lane; int n = (k < nact) ? rcount[k] : 0; int p = (k < nact) ? alist[k] : 0;
       int incl = n;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(B2_FULL, incl, o); if (lane >= o) incl += v; }
       int start = base + incl - n;
-      for (int k = 0; k < n; k++) {
-        int c = start + k;
+      for (int q = 0; q < n; q++) {
+        int c = start + q;
         if (c >= conCap()) { dropped++; continue; }
-        const float* src = rdata + 10 * (praw[p] + k);
+        const float* src = rdata + B2_RAW * (praw[p] + q);
         float* dst = p_con() + B2_CON_STRIDE * c;
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         // frame: normal, then orthogonalised tangent hint (mju_makeFrame)
@@ -630,7 +617,7 @@ struct Engine {
   __device__ __forceinline__ int max_span() const { return dim(DD_maxspan); }
   // A-build scratch: 32 floats per dof; in the dead block [xmat .. cinert] when it fits, else at the arena tail
   __device__ __forceinline__ int scratch_in_arena() const {
-    return (32 * dim(DD_nv) <= dead_block_floats(P.dim)) ? 0 : 32 * dim(DD_nv);
+    return (32 * dim(DD_nv) <= dead_block_floats(P.dim, B.keep_frames)) ? 0 : 32 * dim(DD_nv);
   }
   __device__ __forceinline__ float* scratch_base() const {
     int sc = scratch_in_arena();
@@ -943,16 +930,38 @@ struct Engine {
     return __any_sync(B2_FULL, bad);
   }
 
-  // ---- mj_step with the Euler integrator (implicit joint damping) -- SURVEY B.0 / B.7 (integrate == false: mj_forward).
-  // The step is a loop over three passes that share ONE call site of factor() and solve():
+  // ---- q_to = q_from (+) h * vel  (mj_integratePos: free-joint quaternions by the exponential map)
+  __device__ __forceinline__ void integrate_pos(float* q_to, const float* q_from, const float* vel, float h) {
+    const int* jtype = I(DI_jnt_type); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
+    int njnt = dim(DD_njnt);
+#pragma unroll 1
+    for (int j = lane; j < njnt; j += 32) {
+      int qa = jq[j], da = jd[j];
+      if (jtype[j] == 0) {
+        for (int k = 0; k < 3; k++) q_to[qa + k] = q_from[qa + k] + h * vel[da + k];
+        V3 om = ld3(vel + da + 3); float n = norm(om);
+        Q4 q = ldq(q_from + qa + 3);
+        if (n >= B2_MINVAL) q = qnormalize(qmul(q, axisangle(om * (1.f / n), h * n)));
+        stq(q_to + qa + 3, q);
+      } else q_to[qa] = q_from[qa] + h * vel[da];
+    }
+  }
+
+  // ---- mj_step -- SURVEY B.0 / B.7 (integrate == false: mj_forward).
+  // One forward evaluation is a loop over passes that share ONE call site of factor() and solve():
   //   pass 0  velocities, CRB, M, bias | contacts, rows     -> factor(M)        -> qacc_smooth = M^-1 qfrc_smooth
   //   pass 1  J, A, PGS (whole team), qfrc_constraint       ->                    qacc = qacc_smooth + M^-1 qfrc_constraint
-  //   pass 2  (mj_Euler)                                    -> factor(M + h D)  -> qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint)
-  // Warp 0 runs the dynamics chain while warp 1 % W runs the contact chain; the NaN retry of mj_step is the outer loop.
-  __device__ __forceinline__ void step_euler(unsigned long long* counters, bool integrate) {
+  //   pass 2  (mj_Euler only)                               -> factor(M + h D)  -> qacc' = (M + h D)^-1 (qfrc_smooth + qfrc_constraint)
+  // Warp 0 runs the dynamics chain while warp 1 % W runs the contact chain; the NaN retry of mj_step (mj_checkAcc) is the
+  // attempt loop.  Euler (implicit joint damping) is one evaluation; RK4 (mj_RungeKutta, N = 4) is four evaluations
+  // around the same loop body: the classical tableau is diagonal, so only q0, v0 and the two running weighted sums of
+  // stage velocities / accelerations are kept.  qacc_warmstart is refreshed once per mj_step, from the last stage.
+  __device__ __forceinline__ void step(unsigned long long* counters, bool integrate) {
     float* time = p_time();
-    const int* jtype = I(DI_jnt_type); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
-    int nq = dim(DD_nq), nv = dim(DD_nv), njnt = dim(DD_njnt); float h = P.opt[DO_timestep];
+    int nq = dim(DD_nq), nv = dim(DD_nv); float h = P.opt[DO_timestep];
+    const bool rk4 = dim(DD_integrator) == 1;
+    const int nstage = (integrate && rk4) ? 4 : 1;
+    const int npass = (integrate && !rk4) ? 3 : 2;
 #ifdef B2_PHASE_TIMING
     long long tphase = clock64();
 #endif
@@ -962,22 +971,33 @@ struct Engine {
       }
     }
 #pragma unroll 1
-    for (int attempt = 0; attempt < 2; attempt++) {
-      if (wl == 0) { kinematics(); com_pos(); }
-      team_sync(); B2_TICK(0);
-      bool restart = false;
+    for (int stage = 0; stage < nstage; stage++) {
 #pragma unroll 1
-      for (int pass = 0; pass < 3; pass++) {
-        if (pass == 0) {
-          if (wl == 0) { vel_pass(); backward_pass(); mass_and_smooth(); }
-          if (wl == (1 % W)) { collision(counters); make_rows(counters); }
-        } else if (pass == 1) {
-          if (p_misc()[MISC_NEFC] > 0) { fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11); }
-          else if (tl == 0) p_misc()[MISC_ITERS] = 0;
-          if (wl == 0) qfrc_constraint();
-        } else {
-          if (!integrate) break;
-          if (attempt == 0) {      // mj_checkAcc
+      for (int attempt = 0; attempt < 2; attempt++) {
+        if (wl == 0) { kinematics(); com_pos(); }
+        team_sync(); B2_TICK(0);
+        bool restart = false;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; pass++) {
+          if (pass == 0) {
+            if (wl == 0) { vel_pass(); backward_pass(); mass_and_smooth(); }
+            if (wl == (1 % W)) { collision(counters); make_rows(counters); }
+          } else if (pass == 1) {
+            if (p_misc()[MISC_NEFC] > 0) { fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11); }
+            else if (tl == 0) p_misc()[MISC_ITERS] = 0;
+            if (wl == 0) qfrc_constraint();
+          } else {
+            if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
+          }
+          if (wl == 0) {
+            if (pass != 1) factor(pass == 0 ? 0.f : h);
+            float* x = b2_smem + wb + (pass == 0 ? B.off.qas : pass == 1 ? B.off.qacc : B.off.tmp);
+            if (pass == 0) { for (int d = lane; d < nv; d += 32) x[d] = p_qfs()[d]; sync(); }
+            solve(x);
+            if (pass == 1) { for (int d = lane; d < nv; d += 32) x[d] += p_qas()[d]; sync(); }
+          }
+          team_sync(); B2_TICK(1 + pass);
+          if (pass == 1 && integrate && stage == 0 && attempt == 0) {      // mj_checkAcc
             if (wl == 0) { bool bad = bad_state(p_qacc(), nv); if (lane == 0) p_misc()[MISC_FLAG] = bad ? 1 : 0; }
             team_sync();
             if (p_misc()[MISC_FLAG]) {
@@ -985,36 +1005,46 @@ struct Engine {
               team_sync(); restart = true; break;
             }
           }
-          if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
         }
-        if (wl == 0) {
-          if (pass != 1) factor(pass == 0 ? 0.f : h);
-          float* x = b2_smem + wb + (pass == 0 ? B.off.qas : pass == 1 ? B.off.qacc : B.off.tmp);
-          if (pass == 0) { for (int d = lane; d < nv; d += 32) x[d] = p_qfs()[d]; sync(); }
-          solve(x);
-          if (pass == 1) { for (int d = lane; d < nv; d += 32) x[d] += p_qas()[d]; sync(); }
-        }
-        team_sync(); B2_TICK(1 + pass);
+        if (!restart) break;
       }
-      if (!restart) break;
+      if (nstage == 4) {
+        if (wl == 0) {
+          const float bw = (stage == 0 || stage == 3) ? (1.0f / 6.0f) : (1.0f / 3.0f);
+          const float cs = stage == 2 ? 1.0f : 0.5f;
+          if (stage == 0) {
+#pragma unroll 1
+            for (int i = lane; i < nq; i += 32) p_rk_q0()[i] = p_qpos()[i];
+          }
+#pragma unroll 1
+          for (int d = lane; d < nv; d += 32) {
+            float v = p_qvel()[d], a = p_qacc()[d];
+            if (stage == 0) { p_rk_v0()[d] = v; p_rk_sv()[d] = bw * v; p_rk_sa()[d] = bw * a; }
+            else { p_rk_sv()[d] = fmaf(bw, v, p_rk_sv()[d]); p_rk_sa()[d] = fmaf(bw, a, p_rk_sa()[d]); }
+          }
+          sync();
+          if (stage < 3) {
+            integrate_pos(p_qpos(), p_rk_q0(), p_qvel(), h * cs);     // uses this stage's velocity
+            sync();
+#pragma unroll 1
+            for (int d = lane; d < nv; d += 32) p_qvel()[d] = fmaf(h * cs, p_qacc()[d], p_rk_v0()[d]);
+          } else {
+            integrate_pos(p_qpos(), p_rk_q0(), p_rk_sv(), h);
+#pragma unroll 1
+            for (int d = lane; d < nv; d += 32) { p_qvel()[d] = fmaf(h, p_rk_sa()[d], p_rk_v0()[d]); p_warm()[d] = p_qacc()[d]; }
+            if (lane == 0) { *time += h; if (counters) atomicAdd(&counters[CTR_SUBSTEPS], 1ull); }
+          }
+          sync();
+        }
+        team_sync();
+      }
     }
-    if (!integrate) return;
+    if (!integrate || rk4) { B2_TICK(13); return; }
     if (wl == 0) {
 #pragma unroll 1
       for (int d = lane; d < nv; d += 32) { p_qvel()[d] += h * p_tmp()[d]; p_warm()[d] = p_qacc()[d]; }
       sync();
-#pragma unroll 1
-      for (int j = lane; j < njnt; j += 32) {
-        int qa = jq[j], da = jd[j];
-        if (jtype[j] == 0) {
-          for (int k = 0; k < 3; k++) p_qpos()[qa + k] += h * p_qvel()[da + k];
-          V3 om = ld3(p_qvel() + da + 3); float n = norm(om);
-          if (n >= B2_MINVAL) {
-            Q4 q = qnormalize(qmul(ldq(p_qpos() + qa + 3), axisangle(om * (1.f / n), h * n)));
-            stq(p_qpos() + qa + 3, q);
-          }
-        } else p_qpos()[qa] += h * p_qvel()[da];
-      }
+      integrate_pos(p_qpos(), p_qpos(), p_qvel(), h);
       if (lane == 0) { *time += h; if (counters) atomicAdd(&counters[CTR_SUBSTEPS], 1ull); }
     }
     team_sync();

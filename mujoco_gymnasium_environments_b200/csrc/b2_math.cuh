@@ -1,7 +1,9 @@
 // b2_math.cuh -- small fp32 vector / quaternion / spatial-algebra helpers for the step kernel.
 // Spatial vectors are [angular(3); linear(3)] expressed at the tree's com origin.
 #pragma once
+#ifndef B2_HOST_BUILD
 #include <cuda_runtime.h>
+#endif
 
 namespace b2 {
 
@@ -102,11 +104,13 @@ __device__ __forceinline__ S6 mul_inert(const float* i, S6 v) {
   return r;
 }
 
+#ifndef B2_HOST_BUILD
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+#endif
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 }  // namespace b2

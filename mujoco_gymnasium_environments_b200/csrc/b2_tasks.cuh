@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -31,7 +31,7 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -142,7 +142,9 @@ struct QuadrupedTask {
     return reward;
   }
 
-  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, const int* ti) {
+  template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, const int* ti, float*) {
     // _update_dynamic_obstacles: uses the pre-increment step counter; takes effect on the next step
     if (E.lane == 0) {
       float t = (float)ti[0] * 0.01f;
@@ -150,6 +152,188 @@ struct QuadrupedTask {
       E.p_ctrl()[tp.ids[8]] = 100.0f * sinf(0.3f * t);
     }
     E.sync();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ humanoid dancing
+// humanoid_dancing_env/dancing_env.py: step :833-894, reset :763-831, _generate_dance_sequence :896-905,
+// _set_initial_pose :907-922, _update_rhythm :924-937, _update_visual_effects :939-955, _check_move_transition :957-973,
+// _update_crowd_excitement :975-1002, _update_episode_stats :1004-1026, _get_observation :1028-1120,
+// _calculate_reward :1122-1207, _check_termination :1209-1234.
+// The scalar clocks the reference keeps in Python floats (time_since_last_beat, combo_multiplier, move_start_time) are
+// fp64 here as well: their threshold tests (beat phase 0.1/0.9, int(combo), 0.8 * duration) decide reward branches.
+// ti: [0] current_step [1] beat_count [2] current_measure [3] current_move_idx [4] episode id [5] fall_start_step + 1
+//     (0 = attribute absent; survives reset) [6] longest_combo [7] len(move_history) [8] last three history
+//     entries, 4 bits each [9..11] the 20 moves of dance_sequence, 4 bits each
+// tf: [0] performance_score [1] crowd_excitement [2,3] time_since_last_beat (f64) [4,5] combo_multiplier (f64)
+//     [6,7] move_start_time (f64) [8..10] spotlight_position (survives reset) [11] energy_used [12] time_on_beat
+//     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
+// ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
+struct DancingTask {
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1;
+  static constexpr int NJ = 29, NSEQ = 20;
+  static constexpr double DT = 0.01667, BEAT = 0.5;
+
+  __device__ static __forceinline__ double& D(float* tf, int k) { return *reinterpret_cast<double*>(tf + k); }
+  __device__ static __forceinline__ int seq_move(const int* ti, int k) { return (ti[9 + (k >> 3)] >> (4 * (k & 7))) & 15; }
+  __device__ static __forceinline__ float difficulty(int move) {
+    const float dif[10] = {1.f, 2.f, 2.f, 3.f, 2.f, 1.f, 2.f, 3.f, 2.f, 4.f};   // dance_moves in key order (:57-68)
+    return dif[move];
+  }
+  template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
+    const float* q = E.p_xquat() + 4 * torso;
+    return q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3] > 0.7f;      // element (2,2) of mju_quat2Mat
+  }
+
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
+      act_clipped[i] = a; E.p_ctrl()[i] = a;
+    }
+    E.sync();
+  }
+  // _update_rhythm + _update_visual_effects: run before mj_step, the spotlight chases the torso position of the
+  // previous step's last forward pass
+  template <class EN> __device__ static void pre_physics(EN& E, const TaskParams&, int* ti, float* tf) {
+    if (E.lane == 0) {
+      double t = D(tf, 2) + DT;
+      if (t >= BEAT) { t -= BEAT; ti[1] += 1; if ((ti[1] & 3) == 0) ti[2] += 1; }
+      D(tf, 2) = t;
+      tf[8] += 0.1f * (tf[13] - tf[8]); tf[9] += 0.1f * (tf[14] - tf[9]); tf[10] += 0.1f * (5.0f - tf[10]);
+    }
+    E.sync();
+  }
+
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+                                     const float* inject) {
+    E.reset_data();
+    if (E.lane == 0) {
+      float* q = E.p_qpos();
+      q[2] = 1.8f; q[3] = 1.0f;      // "root height" / "quaternion w" land on abdomen_z and neck_x
+      unsigned ep = (unsigned)ti[4];
+      if (ep == 0) { tf[8] = 0.f; tf[9] = 0.f; tf[10] = 5.f; ti[5] = 0; }    // constructor state (:99)
+      int packed[3] = {0, 0, 0};
+      for (int k = 0; k < NSEQ; k++) {
+        int mv; float dur;
+        if (inject) { mv = (int)inject[2 * k]; dur = inject[2 * k + 1]; }
+        else {
+          mv = min(9, (int)(10.0f * rng_uniform(B.seed, (unsigned)(B.env_offset + env), ep, 2 * k)));
+          dur = 1.0f + 2.0f * rng_uniform(B.seed, (unsigned)(B.env_offset + env), ep, 2 * k + 1);
+        }
+        packed[k >> 3] |= (mv & 15) << (4 * (k & 7));
+        tf[16 + k] = dur;
+      }
+      ti[0] = 0; ti[1] = 0; ti[2] = 0; ti[3] = 0; ti[4] = (int)(ep + 1); ti[6] = 0; ti[7] = 0; ti[8] = 0;
+      ti[9] = packed[0]; ti[10] = packed[1]; ti[11] = packed[2];
+      tf[0] = 0.f; tf[1] = 0.5f; D(tf, 2) = 0.0; D(tf, 4) = 1.0; D(tf, 6) = 0.0; tf[11] = 0.f; tf[12] = 0.f;
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  // end of reset(): prev_joint_vel <- qvel[6:], move_history <- [] (:822-826)
+  template <class EN> __device__ static void after_settle(EN& E, const TaskParams& tp, int* ti, float* tf) {
+    for (int i = E.lane; i < 23; i += 32) tf[36 + i] = E.p_qvel()[6 + i];
+    if (E.lane < 3) tf[13 + E.lane] = E.p_xpos()[3 * tp.ids[0] + E.lane];
+    if (E.lane == 0) { ti[7] = 0; ti[8] = 0; }
+    E.sync();
+  }
+
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
+    int torso = tp.ids[0];
+    const int* ti = E.p_ti(); float* tf = E.p_tf();
+    const float* jr = E.F(DF_jnt_range);
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 29) {                       // qpos[7+i] normalised by the range of joint i (:1034-1049)
+        if (i < 22) { float lo = jr[2 * i], hi = jr[2 * i + 1]; if (lo < hi) v = clampf(2.f * (E.p_qpos()[7 + i] - lo) / (hi - lo) - 1.f, -1.f, 1.f); }
+      } else if (i < 58) { int k = i - 29; if (k < 23) v = clampf(E.p_qvel()[6 + k] / 10.0f, -1.f, 1.f); }
+      else if (i < 62) v = E.p_xquat()[4 * torso + i - 58];
+      else if (i < 65) v = clampf(E.p_qvel()[i - 62] / 5.0f, -1.f, 1.f);
+      else if (i < 68) v = clampf(E.p_qvel()[i - 62] / 10.0f, -1.f, 1.f);
+      else if (i < 71) v = clampf(E.p_rootcom()[3 * E.I(DI_body_rootidx)[torso] + i - 68] / 10.0f, -1.f, 1.f);
+      else if (i < 73) {
+        int foot = tp.ids[1 + i - 71], ncon = E.p_misc()[MISC_NCON];
+        const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+        for (int c = 0; c < ncon; c++) {
+          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+          if ((g1 == foot && (g2 == tp.ids[3] || g2 == tp.ids[4])) || (g2 == foot && (g1 == tp.ids[3] || g1 == tp.ids[4]))) v = 1.f;
+        }
+      } else if (i < 76) v = 0.f;
+      else if (i == 76) v = (float)(D(tf, 2) / BEAT);
+      else if (i == 77) v = (float)((BEAT - D(tf, 2)) / BEAT);
+      else if (i < 88) { if (ti[3] < NSEQ && seq_move(ti, ti[3]) == i - 78) v = 1.f; }
+      else if (i == 88) v = clampf((float)(D(tf, 4) / 10.0), 0.f, 1.f);
+      else if (i == 89) v = tf[1];
+      else if (i < 93) v = clampf((tf[8 + i - 90] - E.p_xpos()[3 * torso + i - 90]) / 10.0f, -1.f, 1.f);
+      else v = 1.0f - fminf(tf[11] / 1000.0f, 1.0f);
+      obs[i] = v;
+    }
+  }
+
+  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*, float*) {}
+
+  // lane 0: current_step += 1 -> reward -> terminated -> truncated -> stats -> crowd -> move transition -> prev state
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    int torso = tp.ids[0];
+    ti[0] += 1;
+    const float* qv = E.p_qvel() + 6; const float* prev = tf + 36;
+    double tslb = D(tf, 2), combo = D(tf, 4);
+    double phase = tslb / BEAT;
+    float mv2 = 0.f, dv2 = 0.f;
+    for (int i = 0; i < 23; i++) { float v = qv[i], dvi = v - prev[i]; mv2 = fmaf(v, v, mv2); dv2 = fmaf(dvi, dvi, dv2); }
+    float mv = sqrtf(mv2), jerk = sqrtf(dv2);
+    bool up = upright(E, torso);
+    float reward = 0.f;
+    if (phase < 0.1 || phase > 0.9) {
+      if (mv > 1.0f) { reward += 100.0f; combo = fmin(combo + 0.1, 10.0); }
+      else combo = fmax(combo - 0.05, 1.0);
+    }
+    if (up) { reward += 30.0f; if (jerk > 0.5f) reward += 15.0f; }
+    reward += 20.0f * expf(-0.1f * jerk);
+    if (ti[7] > 2) { int h = ti[8], a = h & 15, b = (h >> 4) & 15, c = (h >> 8) & 15; if (a != b && b != c && a != c) reward += 50.0f; }
+    double now = (double)ti[0] * DT, elapsed = now - D(tf, 6);
+    int idx = ti[3];
+    if (idx < NSEQ && elapsed > (double)tf[16 + idx] * 0.8) reward += 200.0f * difficulty(seq_move(ti, idx));
+    {
+      const float* jr = E.F(DF_jnt_range); float used = 0.f;
+      for (int i = 0; i < 22; i++) { float lo = jr[2 * i], hi = jr[2 * i + 1]; if (lo < hi) used += fabsf(E.p_qpos()[7 + i] - 0.5f * (lo + hi)) / (hi - lo); }
+      if (used > 5.0f) reward += 10.0f;
+    }
+    float a2 = 0.f, a1 = 0.f;
+    for (int i = 0; i < ACT; i++) { a2 = fmaf(act[i], act[i], a2); a1 += fabsf(act[i]); }
+    reward += -0.05f * a2;
+    if (!up) { reward += -500.0f; combo = 1.0; }
+    if (phase > 0.2 && phase < 0.8 && mv > 3.0f) reward += -5.0f;
+    if (reward > 0.f) reward *= (float)combo;
+    tf[0] += reward;
+    // _check_termination
+    int term = 0;
+    if (!up) { if (ti[5] == 0) ti[5] = ti[0] + 1; else if (ti[0] - (ti[5] - 1) > 120) term = 1; }
+    else ti[5] = 0;
+    const float* xp = E.p_xpos() + 3 * torso;
+    if (sqrtf(xp[0] * xp[0] + xp[1] * xp[1]) > 15.0f || xp[2] < 0.f || xp[2] > 5.0f) term = 1;
+    *terminated = term; *truncated = ti[0] >= MAX_STEPS;
+    // _update_episode_stats
+    tf[11] += a1 * (float)DT;
+    if (phase < 0.1 || phase > 0.9) tf[12] += (float)DT;
+    ti[6] = max(ti[6], (int)combo);
+    // _update_crowd_excitement
+    {
+      float onbeat = (tslb < 0.1 || tslb > BEAT - 0.1) ? 0.1f : 0.f;
+      float cf = fminf((float)(combo / 10.0), 1.0f) * 0.2f;
+      float df = idx < NSEQ ? difficulty(seq_move(ti, idx)) / 4.0f * 0.1f : 0.f;
+      tf[1] = clampf(tf[1] + (onbeat + cf + df) * 0.01f, 0.f, 1.f) * 0.999f;
+    }
+    // _check_move_transition
+    if (idx < NSEQ && elapsed >= (double)tf[16 + idx]) {
+      idx += 1; ti[3] = idx; D(tf, 6) = now;
+      if (idx < NSEQ) { ti[8] = ((ti[8] << 4) | seq_move(ti, idx)) & 0xfff; ti[7] += 1; }
+    }
+    D(tf, 4) = combo;
+    for (int i = 0; i < 23; i++) tf[36 + i] = qv[i];
+    tf[13] = xp[0]; tf[14] = xp[1]; tf[15] = xp[2];
+    return reward;
   }
 };
 

@@ -1,1 +1,2 @@
 from .quadruped_parkour import QuadrupedParkourEnv  # noqa: F401
+from .humanoid_dancing import HumanoidDancingEnv  # noqa: F401

@@ -73,6 +73,20 @@ def _quad_obs_space(t: ModelTables) -> Box:
     return Box(lo, hi, dtype=np.float32)
 
 
+# ---------------------------------------------------------------------------------------------- humanoid dancing
+def _dance_desc(t: ModelTables) -> capi.B2TaskDesc:
+    # dancing_env.py:680-720: torso body, foot / floor / stage geoms; joint_indices are 0..28 in joint_names order
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_HUMANOID_DANCING
+    ids = [t.name2id("body", "torso"), t.name2id("geom", "right_foot"), t.name2id("geom", "left_foot"),
+           t.name2id("geom", "dance_floor"), t.name2id("geom", "stage")]
+    for k, v in enumerate(ids):
+        d.ids[k] = v
+    for k in range(29):
+        d.act_lo[k] = -200.0; d.act_hi[k] = 200.0
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -81,4 +95,11 @@ TASKS: Dict[str, TaskSpec] = {
         observation_space=_quad_obs_space,
         info_keys=["step_count", "episode_reward", "max_forward_progress", "checkpoints_reached", "fall_count",
                    "course_completion"]),
+    "humanoid_dancing": TaskSpec(
+        name="humanoid_dancing", task_id=capi.TASK_HUMANOID_DANCING, obs_dim=94, act_dim=29, max_episode_steps=3600,
+        frame_skip=1, render_fps=60, bytes_per_env_step=1954, describe=_dance_desc,
+        action_space=lambda t: Box(np.full(29, -200.0, np.float32), np.full(29, 200.0, np.float32), dtype=np.float32),
+        observation_space=lambda t: Box(np.full(94, -np.inf, np.float32), np.full(94, np.inf, np.float32), dtype=np.float32),
+        info_keys=["episode_stats", "current_move", "beat_phase", "combo_multiplier", "crowd_excitement",
+                   "performance_score"]),
 }

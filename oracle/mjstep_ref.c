@@ -529,6 +529,269 @@ static int sphere_box(RawCon *c, const real *pos1, real r1, const real *pos2, co
   return 1;
 }
 
+/* ---- pairs beyond MuJoCo's closed-form primitives.  MuJoCo resolves cylinder-vs-{capsule,box} with its convex
+ * (libccd/MPR) path and box-vs-{capsule,box} with engine_collision_box.c; neither source is available here, so the
+ * functions below restate the *geometry* those routines solve (closest features, one contact for convex pairs, two for
+ * a capsule lying on a face, up to eight for box faces) with deterministic tie-breaking.  Contact ordering inside a
+ * pair and multi-contact selection in edge-on configurations are [EXT-unverified]; see DESIGN.md section 2. */
+
+/* signed distance of point p (cylinder frame) to the solid cylinder (radius r, half height h); closest surface point
+ * cp and outward direction n at it */
+static real point_cylinder(const real *p, real r, real h, real *cp, real *n) {
+  real rho = sqrt(p[0]*p[0] + p[1]*p[1]), az = fabs(p[2]), sz = p[2] < 0 ? -1.0 : 1.0;
+  real ux = 1, uy = 0;
+  if (rho > MINVAL) { ux = p[0] / rho; uy = p[1] / rho; }
+  if (az <= h && rho <= r) {                       /* inside: leave through the nearer of cap and side */
+    if (h - az <= r - rho) { cp[0] = p[0]; cp[1] = p[1]; cp[2] = sz*h; n[0] = n[1] = 0; n[2] = sz; return -(h - az); }
+    cp[0] = ux*r; cp[1] = uy*r; cp[2] = p[2]; n[0] = ux; n[1] = uy; n[2] = 0; return -(r - rho);
+  }
+  if (rho <= r) { cp[0] = p[0]; cp[1] = p[1]; cp[2] = sz*h; n[0] = n[1] = 0; n[2] = sz; return az - h; }   /* cap */
+  if (az <= h) { cp[0] = ux*r; cp[1] = uy*r; cp[2] = p[2]; n[0] = ux; n[1] = uy; n[2] = 0; return rho - r; } /* side */
+  cp[0] = ux*r; cp[1] = uy*r; cp[2] = sz*h;                                                                /* rim */
+  real v[3] = {p[0]-cp[0], p[1]-cp[1], p[2]-cp[2]}, dd = norm3(v);
+  n[0] = v[0]/dd; n[1] = v[1]/dd; n[2] = v[2]/dd;
+  return dd;
+}
+static void to_local(real *r, const real *mat, const real *v) {   /* mat' v */
+  r[0] = mat[0]*v[0] + mat[3]*v[1] + mat[6]*v[2];
+  r[1] = mat[1]*v[0] + mat[4]*v[1] + mat[7]*v[2];
+  r[2] = mat[2]*v[0] + mat[5]*v[1] + mat[8]*v[2];
+}
+/* sphere (geom1) vs cylinder (geom2): normal points from the sphere to the cylinder */
+static int sphere_cylinder(RawCon *c, const real *pos1, real r1, const real *pos2, const real *mat2, const real *size2, real margin) {
+  real dif[3] = {pos1[0]-pos2[0], pos1[1]-pos2[1], pos1[2]-pos2[2]}, pl[3], cp[3], n[3];
+  to_local(pl, mat2, dif);
+  real dist = point_cylinder(pl, size2[0], size2[1], cp, n) - r1;
+  if (dist > margin) return 0;
+  real posl[3] = {cp[0] + n[0]*dist*0.5, cp[1] + n[1]*dist*0.5, cp[2] + n[2]*dist*0.5}, nl[3] = {-n[0], -n[1], -n[2]};
+  c->dist = dist;
+  mulmatvec3(c->frame, mat2, nl); mulmatvec3(c->pos, mat2, posl);
+  for (int k = 0; k < 3; k++) { c->pos[k] += pos2[k]; c->frame[3+k] = 0; }
+  return 1;
+}
+/* capsule (geom1) vs cylinder (geom2): one contact, the deeper of the two end spheres (first end on ties) */
+static int capsule_cylinder(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
+                            const real *mat2, const real *size2, real margin) {
+  real ax[3] = {mat1[2], mat1[5], mat1[8]}; RawCon t[2]; int have = 0;
+  for (int s = 0; s < 2; s++) {
+    real sg = s ? -size1[1] : size1[1], p[3] = {pos1[0] + ax[0]*sg, pos1[1] + ax[1]*sg, pos1[2] + ax[2]*sg};
+    if (sphere_cylinder(&t[s], p, size1[0], pos2, mat2, size2, margin)) have |= 1 << s;
+  }
+  if (!have) return 0;
+  int pick = (have == 3) ? (t[1].dist < t[0].dist ? 1 : 0) : (have == 1 ? 0 : 1);
+  *c = t[pick];
+  return 1;
+}
+/* cylinder (geom1) vs box (geom2): one contact at the box vertex deepest in the cylinder (first vertex on ties) */
+static int cylinder_box(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
+                        const real *mat2, const real *size2, real margin) {
+  real best = 1e300, bcp[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
+  for (int i = 0; i < 8; i++) {
+    real v[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])}, w[3], pl[3], cp[3], n[3];
+    mulmatvec3(w, mat2, v);
+    for (int k = 0; k < 3; k++) w[k] += pos2[k] - pos1[k];
+    to_local(pl, mat1, w);
+    real dd = point_cylinder(pl, size1[0], size1[1], cp, n);
+    if (dd < best) { best = dd; memcpy(bcp, cp, sizeof(cp)); memcpy(bn, n, sizeof(n)); }
+  }
+  if (best > margin) return 0;
+  real posl[3] = {bcp[0] + bn[0]*best*0.5, bcp[1] + bn[1]*best*0.5, bcp[2] + bn[2]*best*0.5};
+  c->dist = best;
+  mulmatvec3(c->frame, mat1, bn); mulmatvec3(c->pos, mat1, posl);
+  for (int k = 0; k < 3; k++) { c->pos[k] += pos1[k]; c->frame[3+k] = 0; }
+  return 1;
+}
+
+/* squared distance from the point c + a t (box frame) to the box with half sizes s */
+static real seg_box_d2(const real *c, const real *a, const real *s, real t) {
+  real f = 0;
+  for (int k = 0; k < 3; k++) { real p = fabs(c[k] + a[k]*t) - s[k]; if (p > 0) f += p*p; }
+  return f;
+}
+/* capsule (geom1) vs box (geom2).  t* = segment parameter closest to the box (exact minimisation of the piecewise
+ * quadratic distance, smallest t on ties); contact 1 = sphere-box at t*.  If that contact is on a face (exactly one
+ * coordinate outside the box), a second sphere-box test is made at the far end of the part of the segment that lies
+ * over the same face; the two contacts are emitted in ascending t. */
+static int capsule_box(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
+                       const real *mat2, const real *size2, real margin) {
+  real ax[3] = {mat1[2], mat1[5], mat1[8]}, dif[3] = {pos1[0]-pos2[0], pos1[1]-pos2[1], pos1[2]-pos2[2]}, cl[3], al[3];
+  to_local(cl, mat2, dif); to_local(al, mat2, ax);
+  real l = size1[1], r = size1[0];
+  {                                                  /* axis passes through the box: one contact at the chord point nearest the capsule centre */
+    real te = -l, tx = l; int hit = 1;
+    for (int k = 0; k < 3; k++) {
+      if (fabs(al[k]) <= 1e-9) { if (fabs(cl[k]) > size2[k]) hit = 0; continue; }
+      real u = (-size2[k] - cl[k]) / al[k], v = (size2[k] - cl[k]) / al[k];
+      if (u > v) { real w = u; u = v; v = w; }
+      if (u > te) te = u; if (v < tx) tx = v;
+    }
+    if (hit && te <= tx) {
+      real tm = te > 0 ? te : (tx < 0 ? tx : 0), pm[3] = {pos1[0] + ax[0]*tm, pos1[1] + ax[1]*tm, pos1[2] + ax[2]*tm};
+      return sphere_box(c, pm, r, pos2, mat2, size2, margin);
+    }
+  }
+  real cand[24]; int nc = 0;
+  cand[nc++] = -l; cand[nc++] = l;
+  for (int k = 0; k < 3; k++) if (fabs(al[k]) > 1e-9) for (int sg = -1; sg <= 1; sg += 2) {
+    real t = (sg*size2[k] - cl[k]) / al[k];
+    if (t > -l && t < l) cand[nc++] = t;
+  }
+  for (int i = 1; i < nc; i++) { real v = cand[i]; int j = i - 1; while (j >= 0 && cand[j] > v) { cand[j+1] = cand[j]; j--; } cand[j+1] = v; }
+  int nb = nc;
+  for (int i = 0; i + 1 < nb; i++) {                 /* stationary point of the quadratic on each interval */
+    real ta = cand[i], tb = cand[i+1], tm = 0.5*(ta + tb), num = 0, den = 0;
+    for (int k = 0; k < 3; k++) {
+      real p = cl[k] + al[k]*tm;
+      if (p > size2[k]) { num += al[k]*(cl[k] - size2[k]); den += al[k]*al[k]; }
+      else if (p < -size2[k]) { num += al[k]*(cl[k] + size2[k]); den += al[k]*al[k]; }
+    }
+    if (den > 1e-12) { real t = -num / den; if (t > ta && t < tb) cand[nc++] = t; }
+  }
+  real tbest = cand[0], fbest = seg_box_d2(cl, al, size2, cand[0]);
+  for (int i = 1; i < nc; i++) {
+    real f = seg_box_d2(cl, al, size2, cand[i]);
+    if (f < fbest || (f == fbest && cand[i] < tbest)) { fbest = f; tbest = cand[i]; }
+  }
+  real p1[3] = {pos1[0] + ax[0]*tbest, pos1[1] + ax[1]*tbest, pos1[2] + ax[2]*tbest};
+  RawCon first; int n1 = sphere_box(&first, p1, r, pos2, mat2, size2, margin);
+  if (!n1) return 0;
+  /* face contact? */
+  int nout = 0, kf = -1;
+  for (int k = 0; k < 3; k++) if (fabs(cl[k] + al[k]*tbest) > size2[k] + 1e-6 + 1e-5*size2[k]) { nout++; kf = k; }
+  int n = 0; real t2 = tbest; int have2 = 0; RawCon second;
+  if (nout == 1) {
+    real ta = -l, tb = l; int ok = 1;
+    for (int k = 0; k < 3; k++) if (k != kf) {
+      if (fabs(al[k]) <= 1e-9) { if (fabs(cl[k]) > size2[k]) ok = 0; continue; }
+      real u = (-size2[k] - cl[k]) / al[k], v = (size2[k] - cl[k]) / al[k];
+      if (u > v) { real w = u; u = v; v = w; }
+      if (u > ta) ta = u; if (v < tb) tb = v;
+    }
+    if (ok && tb >= ta) {
+      t2 = (tbest - ta > tb - tbest) ? ta : tb;
+      if (fabs(t2 - tbest) > 1e-3*l) {
+        real p2[3] = {pos1[0] + ax[0]*t2, pos1[1] + ax[1]*t2, pos1[2] + ax[2]*t2};
+        have2 = sphere_box(&second, p2, r, pos2, mat2, size2, margin);
+      }
+    }
+  }
+  if (have2 && t2 < tbest) { c[n++] = second; c[n++] = first; }
+  else { c[n++] = first; if (have2) c[n++] = second; }
+  return n;
+}
+
+/* box (geom1) vs box (geom2): separating-axis test over the 15 axes; a face axis wins unless an edge axis is
+ * better by a clear margin.  Face case: the incident face is clipped against the side planes of the reference face
+ * (Sutherland-Hodgman, <= 8 points), points farther than `margin` from the reference face are dropped.  Edge case: one
+ * contact between the closest points of the two edges.  The frame normal points from box 1 to box 2. */
+static int box_box(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
+                   const real *mat2, const real *size2, real margin) {
+  real A[3][3], B[3][3], p[3] = {pos2[0]-pos1[0], pos2[1]-pos1[1], pos2[2]-pos1[2]};
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = mat1[3*k+i]; B[i][k] = mat2[3*k+i]; }   /* axes as rows */
+  real R[3][3], Q[3][3], pa[3], pb[3];
+  for (int i = 0; i < 3; i++) { pa[i] = dot3(p, A[i]); pb[i] = dot3(p, B[i]); for (int j = 0; j < 3; j++) { R[i][j] = dot3(A[i], B[j]); Q[i][j] = fabs(R[i][j]); } }
+  real best = -1e300; int code = -1; real bsign = 1;
+  for (int i = 0; i < 3; i++) {                    /* faces of box 1 */
+    real s = fabs(pa[i]) - (size1[i] + size2[0]*Q[i][0] + size2[1]*Q[i][1] + size2[2]*Q[i][2]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = i; bsign = pa[i] < 0 ? -1 : 1; }
+  }
+  for (int j = 0; j < 3; j++) {                    /* faces of box 2 */
+    real s = fabs(pb[j]) - (size2[j] + size1[0]*Q[0][j] + size1[1]*Q[1][j] + size1[2]*Q[2][j]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = 3 + j; bsign = pb[j] < 0 ? -1 : 1; }
+  }
+  real ebest = -1e300; int ecode = -1; real en[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    real L[3]; cross3(L, A[i], B[j]);
+    real len = norm3(L);
+    if (len < 1e-6) continue;
+    for (int k = 0; k < 3; k++) L[k] /= len;
+    real ra = 0, rb = 0;
+    for (int k = 0; k < 3; k++) { ra += size1[k]*fabs(dot3(A[k], L)); rb += size2[k]*fabs(dot3(B[k], L)); }
+    real pl = dot3(p, L), s = fabs(pl) - (ra + rb);
+    if (s > margin) return 0;
+    if (s > ebest) { ebest = s; ecode = 3*i + j; real sg = pl < 0 ? -1 : 1; en[0] = L[0]*sg; en[1] = L[1]*sg; en[2] = L[2]*sg; }
+  }
+  if (ecode >= 0 && ebest > best + 1e-4 + 0.02*fabs(best)) {
+    /* edge-edge: edge of box 1 along A[i], of box 2 along B[j], both through the corner facing the other box */
+    int i = ecode / 3, j = ecode % 3; real ea[3], eb[3];
+    for (int k = 0; k < 3; k++) { ea[k] = pos1[k]; eb[k] = pos2[k]; }
+    for (int a = 0; a < 3; a++) if (a != i) { real sg = dot3(en, A[a]) > 0 ? 1 : -1; for (int k = 0; k < 3; k++) ea[k] += sg*size1[a]*A[a][k]; }
+    for (int b = 0; b < 3; b++) if (b != j) { real sg = dot3(en, B[b]) > 0 ? -1 : 1; for (int k = 0; k < 3; k++) eb[k] += sg*size2[b]*B[b][k]; }
+    real w[3] = {eb[0]-ea[0], eb[1]-ea[1], eb[2]-ea[2]}, uaub = dot3(A[i], B[j]), q1 = dot3(A[i], w), q2 = -dot3(B[j], w);
+    real dd = 1 - uaub*uaub, alpha = 0, beta = 0;
+    if (dd > 1e-12) { alpha = (q1 + uaub*q2) / dd; beta = (uaub*q1 + q2) / dd; }
+    if (alpha > size1[i]) alpha = size1[i]; if (alpha < -size1[i]) alpha = -size1[i];
+    if (beta > size2[j]) beta = size2[j]; if (beta < -size2[j]) beta = -size2[j];
+    for (int k = 0; k < 3; k++) {
+      real x1 = ea[k] + alpha*A[i][k], x2 = eb[k] + beta*B[j][k];
+      c->pos[k] = 0.5*(x1 + x2); c->frame[k] = en[k]; c->frame[3+k] = 0;
+    }
+    c->dist = ebest;
+    return 1;
+  }
+  /* face case */
+  const real (*Rf)[3], (*If)[3]; const real *rs, *is, *rp, *ip; int fi; real nout[3];
+  if (code < 3) { Rf = A; If = B; rs = size1; is = size2; rp = pos1; ip = pos2; fi = code; for (int k = 0; k < 3; k++) nout[k] = bsign*A[fi][k]; }
+  else { Rf = B; If = A; rs = size2; is = size1; rp = pos2; ip = pos1; fi = code - 3; for (int k = 0; k < 3; k++) nout[k] = -bsign*B[fi][k]; }
+  /* incident face: the face of the other box most anti-parallel to nout */
+  int ii = 0; real mn = 1e300, isg = 1;
+  for (int k = 0; k < 3; k++) { real dn = dot3(If[k], nout); if (-fabs(dn) < mn) { mn = -fabs(dn); ii = k; isg = dn > 0 ? -1 : 1; } }
+  int i1 = (ii + 1) % 3, i2 = (ii + 2) % 3, r1 = (fi + 1) % 3, r2 = (fi + 2) % 3;
+  real poly[16][3], tmp[16][3]; int np = 4;
+  static const int sx[4] = {1, -1, -1, 1}, sy[4] = {1, 1, -1, -1};
+  for (int v = 0; v < 4; v++) for (int k = 0; k < 3; k++)
+    poly[v][k] = ip[k] + isg*is[ii]*If[ii][k] + sx[v]*is[i1]*If[i1][k] + sy[v]*is[i2]*If[i2][k] - rp[k];
+  /* clip against the four side planes  +-Rf[r1] . x <= rs[r1],  +-Rf[r2] . x <= rs[r2]  (x relative to the reference centre) */
+  for (int pl = 0; pl < 4 && np > 0; pl++) {
+    const real *axv = Rf[pl < 2 ? r1 : r2]; real sg = (pl & 1) ? -1 : 1, lim = rs[pl < 2 ? r1 : r2]; int nn = 0;
+    for (int v = 0; v < np; v++) {
+      const real *a = poly[v], *b = poly[(v + 1) % np];
+      real da = sg*dot3(axv, a) - lim, db = sg*dot3(axv, b) - lim;
+      if (da <= 0) { memcpy(tmp[nn++], a, sizeof(real)*3); }
+      if ((da < 0 && db > 0) || (da > 0 && db < 0)) { real t = da / (da - db); for (int k = 0; k < 3; k++) tmp[nn][k] = a[k] + t*(b[k] - a[k]); nn++; }
+    }
+    np = nn > 8 ? 8 : nn;
+    memcpy(poly, tmp, sizeof(real)*3*np);
+  }
+  int cnt = 0; real fsign = (code < 3) ? 1.0 : -1.0;   /* nout is the outward normal of the reference face */
+  for (int v = 0; v < np && cnt < 8; v++) {
+    real depth = dot3(poly[v], nout) - rs[fi];
+    if (depth > margin) continue;
+    c[cnt].dist = depth;
+    for (int k = 0; k < 3; k++) { c[cnt].pos[k] = poly[v][k] + rp[k] - nout[k]*depth*0.5; c[cnt].frame[k] = fsign*nout[k]; c[cnt].frame[3+k] = 0; }
+    cnt++;
+  }
+  return cnt;
+}
+
+/* direct access to the narrow phase for differential tests: types/poses/sizes in, up to 8 contacts of
+ * [dist, pos(3), normal(3), tangent hint(3)] out; returns the count (-1: pair type outside the subset) */
+int ref_collide_raw(int t1, int t2, const double *p1, const double *m1, const double *s1, const double *p2,
+                    const double *m2, const double *s2, double margin, double *out80) {
+  RawCon raw[8]; int n = -1;
+  memset(raw, 0, sizeof(raw));
+  if (t1 == B2_GEOM_PLANE) {
+    if (t2 == B2_GEOM_SPHERE) n = plane_sphere(raw, p1, m1, p2, s2[0], margin);
+    else if (t2 == B2_GEOM_CAPSULE) n = plane_capsule(raw, p1, m1, p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_BOX) n = plane_box(raw, p1, m1, p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_CYLINDER) n = plane_cylinder(raw, p1, m1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_SPHERE) {
+    if (t2 == B2_GEOM_SPHERE) n = sphere_sphere_raw(raw, p1, s1[0], p2, s2[0], margin);
+    else if (t2 == B2_GEOM_CAPSULE) n = sphere_capsule(raw, p1, s1[0], p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_BOX) n = sphere_box(raw, p1, s1[0], p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_CYLINDER) n = sphere_cylinder(raw, p1, s1[0], p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_CAPSULE) {
+    if (t2 == B2_GEOM_CAPSULE) n = capsule_capsule(raw, p1, m1, s1, p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_CYLINDER) n = capsule_cylinder(raw, p1, m1, s1, p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_BOX) n = capsule_box(raw, p1, m1, s1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) n = cylinder_box(raw, p1, m1, s1, p2, m2, s2, margin);
+  else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) n = box_box(raw, p1, m1, s1, p2, m2, s2, margin);
+  for (int k = 0; k < n && k < 8; k++) { out80[10*k] = raw[k].dist; memcpy(out80 + 10*k + 1, raw[k].pos, 3*sizeof(real)); memcpy(out80 + 10*k + 4, raw[k].frame, 6*sizeof(real)); }
+  return n;
+}
+
 static int collide_pair(const RefModel *m, const RefData *d, int g1, int g2, real margin, RawCon *out) {
   int t1 = MI(geom_type)[g1], t2 = MI(geom_type)[g2];
   const real *p1 = d->geom_xpos + 3*g1, *p2 = d->geom_xpos + 3*g2, *m1 = d->geom_xmat + 9*g1, *m2 = d->geom_xmat + 9*g2;
@@ -545,9 +808,18 @@ static int collide_pair(const RefModel *m, const RefData *d, int g1, int g2, rea
       case B2_GEOM_SPHERE: return sphere_sphere_raw(out, p1, s1[0], p2, s2[0], margin);
       case B2_GEOM_CAPSULE: return sphere_capsule(out, p1, s1[0], p2, m2, s2, margin);
       case B2_GEOM_BOX: return sphere_box(out, p1, s1[0], p2, m2, s2, margin);
+      case B2_GEOM_CYLINDER: return sphere_cylinder(out, p1, s1[0], p2, m2, s2, margin);
     }
-  } else if (t1 == B2_GEOM_CAPSULE && t2 == B2_GEOM_CAPSULE) {
-    return capsule_capsule(out, p1, m1, s1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_CAPSULE) {
+    switch (t2) {
+      case B2_GEOM_CAPSULE: return capsule_capsule(out, p1, m1, s1, p2, m2, s2, margin);
+      case B2_GEOM_CYLINDER: return capsule_cylinder(out, p1, m1, s1, p2, m2, s2, margin);
+      case B2_GEOM_BOX: return capsule_box(out, p1, m1, s1, p2, m2, s2, margin);
+    }
+  } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) {
+    return cylinder_box(out, p1, m1, s1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) {
+    return box_box(out, p1, m1, s1, p2, m2, s2, margin);
   }
   return -1; /* pair type outside the restated subset */
 }

@@ -180,4 +180,243 @@ class QuadrupedParkourRef:
                     stuck_counter=self.stuck_counter)
 
 
-TASKS = {"quadruped_parkour": QuadrupedParkourRef}
+class HumanoidDancingRef:
+    """humanoid_dancing_env/dancing_env.py restated: __init__ :36-154, _get_model_indices :680-720, reset :763-831,
+    step :833-894, _generate_dance_sequence :896-905, _set_initial_pose :907-922, _update_rhythm :924-937,
+    _update_visual_effects :939-955, _check_move_transition :957-973, _update_crowd_excitement :975-1002,
+    _update_episode_stats :1004-1026, _get_observation :1028-1120, _calculate_reward :1122-1207,
+    _check_termination :1209-1234, helpers :1237-1282.  Index aliasing (qpos[7+i] paired with joint i's range, qpos[2]/[3]
+    written as "root height / quaternion w") and the state that leaks across reset (fall_start_step, spotlight) are kept."""
+
+    MOVES = ["basic_step", "spin", "jump", "moonwalk", "robot_wave", "freeze", "hip_hop_bounce", "breakdance_toprock",
+             "salsa_basic", "ballet_pirouette"]
+    DIFFICULTY = dict(zip(MOVES, [1, 2, 2, 3, 2, 1, 2, 3, 2, 4]))
+    JOINT_NAMES = ["abdomen_x", "abdomen_y", "abdomen_z", "neck_x", "neck_y", "right_shoulder1", "right_shoulder2",
+                   "right_elbow", "right_wrist_x", "right_wrist_y", "right_wrist_z", "left_shoulder1", "left_shoulder2",
+                   "left_elbow", "left_wrist_x", "left_wrist_y", "left_wrist_z", "right_hip_x", "right_hip_y",
+                   "right_hip_z", "right_knee", "right_ankle_x", "right_ankle_y", "left_hip_x", "left_hip_y",
+                   "left_hip_z", "left_knee", "left_ankle_x", "left_ankle_y"]
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("humanoid_dancing")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.dt = 0.01667; self.max_episode_steps = 3600; self.current_step = 0
+        self.floor_radius = 10.0
+        self.beat_interval = 60.0 / 120
+        self.time_since_last_beat = 0.0; self.beat_count = 0; self.current_measure = 0
+        self.dance_sequence = []; self.current_move_idx = 0; self.move_start_time = 0.0
+        self.robot_height = 1.8
+        self.performance_score = 0.0; self.combo_multiplier = 1.0
+        self.spotlight_position = np.array([0.0, 0.0, 5.0])
+        self.crowd_excitement = 0.5
+        self.num_joints = int(t.nu)
+        self.joint_indices = [t.name2id("joint", n) for n in self.JOINT_NAMES]
+        self.torso_id = t.name2id("body", "torso")
+        self.right_foot_id = t.name2id("geom", "right_foot"); self.left_foot_id = t.name2id("geom", "left_foot")
+        self.floor_id = t.name2id("geom", "dance_floor"); self.stage_id = t.name2id("geom", "stage")
+        self.jnt_range = np.asarray(t.jnt_range)
+        self.action_low = np.full(self.num_joints, -200.0); self.action_high = np.full(self.num_joints, 200.0)
+        self.episode_stats = dict(total_score=0, longest_combo=0, energy_used=0.0, time_on_beat=0.0, crowd_rating=0.0)
+        self.prev_joint_vel = None
+        self.move_history = []
+        self.np_random = np.random.default_rng(seed)
+
+    # -- reset :763-831; `sequence` lets tests inject the 20 (move index, duration) draws
+    def reset(self, seed=None, sequence=None):
+        if seed is not None:
+            self.np_random = np.random.default_rng(seed)
+        d = self.data
+        ref.mj_resetData(self.model, d)
+        self.current_step = 0; self.beat_count = 0; self.current_measure = 0; self.time_since_last_beat = 0.0
+        self.performance_score = 0.0; self.combo_multiplier = 1.0
+        self.crowd_excitement = 0.5
+        if sequence is None:
+            sequence = []
+            for _ in range(20):
+                move = int(self.np_random.integers(0, 10)); duration = self.np_random.uniform(1.0, 3.0)
+                sequence.append((move, duration))
+        self.dance_sequence = [dict(move=self.MOVES[int(mv)], duration=float(du)) for mv, du in sequence]
+        self.current_move_idx = 0; self.move_start_time = 0.0
+        self.episode_stats = dict(total_score=0, longest_combo=0, energy_used=0.0, time_on_beat=0.0, crowd_rating=0.0)
+        # _set_initial_pose :907-922
+        d.qpos[0] = 0.0; d.qpos[1] = 0.0; d.qpos[2] = self.robot_height
+        d.qpos[3:7] = [1.0, 0.0, 0.0, 0.0]
+        for i, joint_idx in enumerate(self.joint_indices):
+            qpos_idx = 7 + i
+            if qpos_idx < len(d.qpos) and joint_idx < len(self.jnt_range):
+                d.qpos[qpos_idx] = 0.0
+        ref.mj_step(self.model, d, 10)
+        obs = self._get_observation()
+        self.prev_joint_vel = d.qvel[6:].copy()
+        self.move_history = []
+        return obs, dict(episode_stats=dict(self.episode_stats), beat_phase=0.0, combo_multiplier=self.combo_multiplier)
+
+    def step(self, action):
+        d = self.data
+        action = np.clip(np.asarray(action, np.float64), self.action_low, self.action_high)
+        d.ctrl[:] = action
+        # _update_rhythm :924-937
+        self.time_since_last_beat += self.dt
+        if self.time_since_last_beat >= self.beat_interval:
+            self.time_since_last_beat -= self.beat_interval
+            self.beat_count += 1
+            if self.beat_count % 4 == 0:
+                self.current_measure += 1
+        # _update_visual_effects :939-955 (torso position of the previous forward pass)
+        robot_pos = d.xpos[self.torso_id].copy()
+        target = np.array([robot_pos[0], robot_pos[1], 5.0])
+        self.spotlight_position = self.spotlight_position + 0.1 * (target - self.spotlight_position)
+        ref.mj_step(self.model, d)
+        self.current_step += 1
+        obs = self._get_observation()
+        reward = self._calculate_reward(action)
+        terminated = self._check_termination()
+        truncated = self.current_step >= self.max_episode_steps
+        self._update_episode_stats()
+        self._update_crowd_excitement()
+        self._check_move_transition()
+        info = dict(episode_stats=dict(self.episode_stats), beat_phase=self.time_since_last_beat / self.beat_interval,
+                    combo_multiplier=self.combo_multiplier, crowd_excitement=self.crowd_excitement,
+                    performance_score=self.performance_score)
+        self.prev_joint_vel = d.qvel[6:].copy()
+        return obs, reward, terminated, truncated, info
+
+    def _check_move_transition(self):
+        current_time = self.current_step * self.dt
+        move_elapsed = current_time - self.move_start_time
+        if self.current_move_idx < len(self.dance_sequence):
+            if move_elapsed >= self.dance_sequence[self.current_move_idx]["duration"]:
+                self.current_move_idx += 1
+                self.move_start_time = current_time
+                if self.current_move_idx < len(self.dance_sequence):
+                    self.move_history.append(self.dance_sequence[self.current_move_idx]["move"])
+
+    def _update_crowd_excitement(self):
+        on_beat = 0.1 if (self.time_since_last_beat < 0.1 or self.time_since_last_beat > self.beat_interval - 0.1) else 0.0
+        combo_factor = min(self.combo_multiplier / 10.0, 1.0) * 0.2
+        if self.current_move_idx < len(self.dance_sequence):
+            difficulty_factor = self.DIFFICULTY[self.dance_sequence[self.current_move_idx]["move"]] / 4.0 * 0.1
+        else:
+            difficulty_factor = 0.0
+        change = (on_beat + combo_factor + difficulty_factor) * 0.01
+        self.crowd_excitement = float(np.clip(self.crowd_excitement + change, 0.0, 1.0))
+        self.crowd_excitement *= 0.999
+
+    def _update_episode_stats(self):
+        self.episode_stats["energy_used"] += float(np.sum(np.abs(self.data.ctrl))) * self.dt
+        beat_phase = self.time_since_last_beat / self.beat_interval
+        if beat_phase < 0.1 or beat_phase > 0.9:
+            self.episode_stats["time_on_beat"] += self.dt
+        self.episode_stats["longest_combo"] = max(self.episode_stats["longest_combo"], int(self.combo_multiplier))
+        self.episode_stats["crowd_rating"] = self.crowd_excitement
+        self.episode_stats["total_score"] = self.performance_score
+
+    def _foot_contacts(self):
+        c = np.zeros(2)
+        ground = (self.floor_id, self.stage_id)
+        for con in self.data.contact:
+            if (con.geom1 == self.right_foot_id and con.geom2 in ground) or (con.geom2 == self.right_foot_id and con.geom1 in ground):
+                c[0] = 1.0
+            if (con.geom1 == self.left_foot_id and con.geom2 in ground) or (con.geom2 == self.left_foot_id and con.geom1 in ground):
+                c[1] = 1.0
+        return c
+
+    def _is_robot_upright(self):
+        w, x, y, z = self.data.xquat[self.torso_id]
+        return (w*w - x*x - y*y + z*z) > 0.7          # rot_mat[2, 2] of mju_quat2Mat
+
+    def _get_observation(self):
+        d = self.data
+        obs = []
+        for i in range(self.num_joints):
+            qpos_idx = 7 + i
+            if i < len(self.joint_indices) and qpos_idx < len(d.qpos):
+                lo, hi = self.jnt_range[self.joint_indices[i]]
+                if lo < hi:
+                    obs.append(np.clip(2 * (d.qpos[qpos_idx] - lo) / (hi - lo) - 1, -1.0, 1.0))
+                else:
+                    obs.append(0.0)
+            else:
+                obs.append(0.0)
+        for i in range(self.num_joints):
+            obs.append(np.clip(d.qvel[6 + i] / 10.0, -1.0, 1.0) if i < len(d.qvel) - 6 else 0.0)
+        obs.extend(d.xquat[self.torso_id])
+        obs.extend(np.clip(d.qvel[:3] / 5.0, -1.0, 1.0))
+        obs.extend(np.clip(d.qvel[3:6] / 10.0, -1.0, 1.0))
+        obs.extend(np.clip(d.subtree_com[self.torso_id] / 10.0, -1.0, 1.0))
+        obs.extend(self._foot_contacts())
+        obs.extend(np.zeros(3))
+        obs.append(self.time_since_last_beat / self.beat_interval)
+        obs.append((self.beat_interval - self.time_since_last_beat) / self.beat_interval)
+        enc = np.zeros(len(self.MOVES))
+        if self.current_move_idx < len(self.dance_sequence):
+            enc[self.MOVES.index(self.dance_sequence[self.current_move_idx]["move"])] = 1.0
+        obs.extend(enc)
+        obs.append(np.clip(self.combo_multiplier / 10.0, 0.0, 1.0))
+        obs.append(self.crowd_excitement)
+        obs.extend(np.clip((self.spotlight_position - d.xpos[self.torso_id]) / 10.0, -1.0, 1.0))
+        obs.append(1.0 - min(self.episode_stats["energy_used"] / 1000.0, 1.0))
+        return np.array(obs, dtype=np.float32)
+
+    def _calculate_reward(self, action):
+        d = self.data
+        reward = 0.0
+        beat_phase = self.time_since_last_beat / self.beat_interval
+        if beat_phase < 0.1 or beat_phase > 0.9:
+            if np.linalg.norm(d.qvel[6:]) > 1.0:
+                reward += 100.0
+                self.combo_multiplier = min(self.combo_multiplier + 0.1, 10.0)
+            else:
+                self.combo_multiplier = max(self.combo_multiplier - 0.05, 1.0)
+        if self._is_robot_upright():
+            reward += 30.0
+            if self.prev_joint_vel is not None and np.linalg.norm(d.qvel[6:] - self.prev_joint_vel) > 0.5:
+                reward += 15.0
+        if self.prev_joint_vel is not None:
+            reward += 20.0 * np.exp(-0.1 * np.linalg.norm(d.qvel[6:] - self.prev_joint_vel))
+        if len(self.move_history) > 2 and len(set(self.move_history[-3:])) == 3:
+            reward += 50.0
+        move_elapsed = self.current_step * self.dt - self.move_start_time
+        if self.current_move_idx < len(self.dance_sequence):
+            mv = self.dance_sequence[self.current_move_idx]
+            if move_elapsed > mv["duration"] * 0.8:
+                reward += 200.0 * self.DIFFICULTY[mv["move"]]
+        used = 0.0
+        for i, joint_idx in enumerate(self.joint_indices):
+            qpos_idx = 7 + i
+            if qpos_idx < len(d.qpos) and joint_idx < len(self.jnt_range):
+                lo, hi = self.jnt_range[joint_idx]
+                if lo < hi:
+                    used += abs(d.qpos[qpos_idx] - (lo + hi) / 2) / (hi - lo)
+        if used > 5.0:
+            reward += 10.0
+        reward += -0.05 * float(np.sum(np.square(action)))
+        if not self._is_robot_upright():
+            reward += -500.0
+            self.combo_multiplier = 1.0
+        if 0.2 < beat_phase < 0.8 and np.linalg.norm(d.qvel[6:]) > 3.0:
+            reward += -5.0
+        if reward > 0:
+            reward *= self.combo_multiplier
+        self.performance_score += reward
+        return float(reward)
+
+    def _check_termination(self):
+        if not self._is_robot_upright():
+            if not hasattr(self, "fall_start_step"):
+                self.fall_start_step = self.current_step
+            elif self.current_step - self.fall_start_step > 120:
+                return True
+        elif hasattr(self, "fall_start_step"):
+            delattr(self, "fall_start_step")
+        pos = self.data.xpos[self.torso_id]
+        if np.linalg.norm(pos[:2]) > self.floor_radius * 1.5:
+            return True
+        if pos[2] < 0.0 or pos[2] > 5.0:
+            return True
+        return False
+
+
+TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef}
