@@ -1,9 +1,10 @@
 """bench.py -- env-steps/s of the batched env.step hot path (BASELINE.json metric) on N B200s of one node.
 
 python bench.py --gpus N --steps K --warmup W           this repo's CUDA path (quadruped_parkour, 4096 envs/GPU)
+python bench.py --task humanoid_dancing ...              BASELINE.json configs[2] (8192 envs/GPU, RK4, self contacts)
 python bench.py --impl reference ...                     the CPU arm: the reference's algorithm restated (oracle port),
                                                          one process per env on all host cores
-One "step" = one env.step over the whole batch (clip, 10 x mj_step, obs, reward, termination, same-step auto-reset).
+One "step" = one env.step over the whole batch (clip, frame_skip x mj_step, obs, reward, termination, same-step auto-reset).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -19,9 +20,17 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec (step+reward+obs)"
 UNIT = "env-steps/s"
+# --task selects the workload; the default is BASELINE.json configs[1] (the config the metric is quoted on at N=1)
+WORKLOADS = {
+    "quadruped_parkour": (4096, 6000, "quadruped_parkour_env: {n} envs/GPU lockstep, frame_skip 10 (dt 1 ms), Euler, PGS-50, 48 plane "
+                          "contact pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
+    "humanoid_dancing": (8192, 1500, "humanoid_dancing_env: {n} envs/GPU lockstep, 1 RK4 step (dt 16.67 ms, 4 forward passes), PGS-50, "
+                         "106 self-contact candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
+    "humanoid_soccer": (4096, 1500, "humanoid_soccer_env: {n} envs/GPU lockstep, 1 Euler step (dt 20 ms), PGS-50, free ball + box field, "
+                        "251 candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
+}
 TASK = "quadruped_parkour"
-WORKLOAD = ("quadruped_parkour_env: {n} envs/GPU lockstep, frame_skip 10 (dt 1 ms), 48 plane contact pairs, "
-            "uniform random actions over action_space x {s}, same-step auto-reset")
+WORKLOAD = WORKLOADS[TASK][2]
 
 
 def cpu_arm(n_steps, action_scale):
@@ -84,11 +93,15 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--task", default="quadruped_parkour", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = the task's BASELINE.json size")
     ap.add_argument("--action-scale", type=float, default=1.0)
     ap.add_argument("--cpu-steps", type=int, default=0, help="control steps per CPU process (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    global TASK, WORKLOAD
+    TASK = a.task; WORKLOAD = WORKLOADS[TASK][2]
+    a.envs_per_gpu = a.envs_per_gpu or WORKLOADS[TASK][0]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(a.warmup, 3)
 
@@ -115,7 +128,7 @@ def main():
     # ---- CPU baseline first (spawned processes; before CUDA is initialised in this one)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_arm(a.cpu_steps or 6000, a.action_scale)
+        cpu = cpu_arm(a.cpu_steps or WORKLOADS[TASK][1], a.action_scale)
 
     import numpy as np
     import torch

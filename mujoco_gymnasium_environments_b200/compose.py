@@ -152,5 +152,6 @@ def inline_mjcf(task: str, root: str) -> str:
 COMPOSERS = {
     "quadruped_parkour": quadruped_parkour_mjcf,
     "humanoid_dancing": lambda root: inline_mjcf("dancing", root),
+    "humanoid_soccer": lambda root: inline_mjcf("soccer", root),
 }
 

@@ -58,6 +58,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     for (int i = tl; i < nq; i += TEAM) E.p_qpos()[i] = gq[i];
     for (int i = tl; i < nv; i += TEAM) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
     for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
+    if (tl < 8) E.p_xfrc()[tl] = 0.f;
     if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; }
     for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
     for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
@@ -148,7 +149,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -157,7 +158,7 @@ struct NoTask {
   }
   template <class EN> __device__ static void observe(EN&, const TaskParams&, float*) {}
   template <class EN> __device__ static float reward_and_done(EN&, const TaskParams&, const float*, int*, float*, int* a, int* b) { *a = 0; *b = 0; return 0.f; }
-  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*, float*) {}
+  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, int*, float*) {}
 };
 
 __global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
@@ -202,6 +203,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
     case TASK_NONE: return launch_task<NoTask>(b, mode, inject, s);
     case TASK_QUADRUPED_PARKOUR: return launch_task<QuadrupedTask>(b, mode, inject, s);
     case TASK_HUMANOID_DANCING: return launch_task<DancingTask>(b, mode, inject, s);
+    case TASK_HUMANOID_SOCCER: return launch_task<SoccerTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -256,20 +258,21 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int keep_frames = 0; b->ninj = 1;
+  int keep_frames = 0, xfrc_body = -1; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES
+#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
+    case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
-  v.seed = seed; v.env_offset = env_offset; v.keep_frames = keep_frames; v.inject_stride = b->ninj;
+  v.seed = seed; v.env_offset = env_offset; v.keep_frames = keep_frames; v.inject_stride = b->ninj; v.xfrc_body = xfrc_body;
   // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped); rows: 4 per contact + limits
   int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
   int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
@@ -294,6 +297,12 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   if (o_epb > 0 && o_epb < epb) epb = o_epb;
   if (epb < 1) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
   v.envs_per_block = epb;
+  if (o_arena <= 0) {
+    // the CTA's shared memory is allocated anyway: hand what is left over to the arenas (more rows before truncation)
+    int spare = ((smem_max - v.model_floats * 4 - 16) / epb - v.ws_floats * 4) / 4;
+    spare = (spare / 32) * 32;
+    if (spare > 0) { v.arena_floats += spare; v.ws_floats = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, b->nti, b->ntf, &v.off); }
+  }
   b->smem = ((size_t)v.model_floats + (size_t)epb * v.ws_floats) * 4 + 16;
   size_t N = n_envs;
   CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));

@@ -54,7 +54,7 @@ extern __shared__ __align__(128) float b2_smem[];
 #define B2_WS_FLOAT_FIELDS(X) X(qpos) X(qvel) X(warm) X(ctrl) X(qapp) X(xpos) X(xmat) X(cdof) X(rootcom) \
   X(xquat) X(xipos) X(cvel) X(cacc) X(cinert) X(M) X(LD) X(invD) X(qfs) X(qas) X(qfc) X(qacc) X(tmp) X(con) \
   X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc)
-#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
+#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
 
 struct WsOff {
 #define X(n) int n;
@@ -84,13 +84,13 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   t.qacc = take(nv); t.tmp = take(nv);
   t.con = take(con_cap * B2_CON_STRIDE); t.lim_row = take(2 * (nlim > 0 ? nlim : 1)); t.con_row = take(con_cap);
   t.row_info = take(row_cap); t.row_R = take(row_cap); t.row_b = take(row_cap); t.row_f = take(row_cap); t.row_res = take(row_cap);
-  t.isl_n = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
+  t.isl_n = take(B2_MAX_ISLANDS); t.isl_nl = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
   t.isl_A = take(B2_MAX_ISLANDS); t.isl_ldj = take(B2_MAX_ISLANDS);
   t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(nti > 0 ? nti : 1); t.tf = take(ntf > 0 ? ntf : 1);
   t.act = take(40);
   bool rk4 = dim[DD_integrator] == 1;
   t.rk_q0 = take(rk4 ? nq : 0); t.rk_v0 = take(rk4 ? nv : 0); t.rk_sv = take(rk4 ? nv : 0); t.rk_sa = take(rk4 ? nv : 0);
-  t.xfrc = take(0);
+  t.xfrc = take(8);
   t.arena = take(arena_floats);
   if (o) *o = t;
   return (off + 31) & ~31;
@@ -115,7 +115,7 @@ struct BatchView {
   int envs_per_block; int ws_floats; int model_floats;   // shared-memory slices, in floats
   int keep_frames;                                   // the task reads xquat / subtree com of the last forward pass
   int inject_stride;                                 // floats per env of the injected reset draws
-  float* xfrc_applied;                               // [N][6*nbody] Cartesian applied forces, or null
+  int xfrc_body;                                     // body whose xfrc_applied the task drives (-1: none); value in ws.xfrc[0..5]
   WsOff off;
 };
 
@@ -124,6 +124,7 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_PHYS = 2, MODE_FORWARD = 3 };
 // floats of the contiguous dead block [xmat .. rootcom] the A build may overwrite
 __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames) {
   int nb = dim[DD_nbody], nv = dim[DD_nv], nroot = dim[DD_nroot];
+  if (keep_frames >= 2) return 0;      // the task reads xipos/xmat too: nothing of the block may be overwritten
   int n = r4(9 * nb) + r4(6 * nv) + r4(3 * nb) + r4(6 * nb) + r4(6 * nb) + r4(10 * nb);
   if (!keep_frames) n += r4(4 * nb) + r4(3 * (nroot > 0 ? nroot : 1));
   return n;
@@ -367,6 +368,14 @@ struct Engine {
         if (flimited[ac]) af = clampf(af, frange[2 * ac], frange[2 * ac + 1]);
         f += g * af;
       }
+      if (B.xfrc_body > 0) {        // mj_xfrcAccumulate for the one body the task pushes: [force(3), torque(3)] at its com
+        int xb = B.xfrc_body;
+        if ((I(DI_body_chainmask)[xb * dim(DD_nmaskw) + (i >> 5)] >> (i & 31)) & 1) {
+          V3 fr = ld3(p_xfrc()), tq = ld3(p_xfrc() + 3);
+          V3 off = ld3(p_xipos() + 3 * xb) - ld3(p_rootcom() + 3 * I(DI_body_rootidx)[xb]);
+          f += dot(cd.a, tq + cross(off, fr)) + dot(cd.l, fr);
+        }
+      }
       p_qfs()[i] = f;
     }
     sync();
@@ -391,7 +400,7 @@ struct Engine {
     }
 #pragma unroll 1
     for (int st = 0; st < nstep; st++) {
-      int w = fstep[st], cnt = (w >> 10) & 63, oa = w >> 16;
+      int w = fstep[st], cnt = (w >> 10) & 255, oa = w >> 18;
       float inv = 1.0f / LD[w & 1023];
 #pragma unroll 1
       for (int p = lane; p < cnt; p += 32) {
@@ -574,6 +583,8 @@ struct Engine {
       }
       sync();
     }
+    if (lane < B2_MAX_ISLANDS) p_isl_nl()[lane] = p_isl_n()[lane];      // limit rows come first in every island
+    sync();
     for (int c0 = 0; c0 < ncon; c0 += 32) {
       int c = c0 + lane; bool valid = c < ncon;
       int isl = valid ? contact_island(c) : -1 - lane;
@@ -590,23 +601,33 @@ struct Engine {
     }
     // island bases and arena carve-up: J (n x ldj) then packed A (n(n+1)/2); one island may spill its A to HBM
     if (lane == 0) {
-      int adr = 0, used = 0, ovf = 0;
+      int adr = 0, used = 0, ovf = 0, cut = 0;
       const int* inum = I(DI_island_dofnum);
       int scratch = scratch_in_arena();
       for (int k = 0; k < nisl; k++) {
         int n = min(p_isl_n()[k], maxrows);
         int ldj = inum[k] | 1;
+        // rows that do not fit (row buffer, or J + packed A in what is left of the arena) are cut from the island's tail:
+        // the last contacts go first, the joint limits last; every cut is counted
+        int avail = arenaFloats() - scratch - used - 8;
+        if (adr + n > rowCap()) { n = max(rowCap() - adr, 0); ovf++; }
+        if (r4(n * ldj) + r4(n * (n + 1) / 2) > avail) {
+          float hb = (float)ldj + 0.5f;
+          int nf = avail > 0 ? (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) : 0;
+          while (nf > 0 && r4(nf * ldj) + r4(nf * (nf + 1) / 2) > avail) nf--;
+          n = min(n, nf); ovf++;
+        }
+        { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
+        cut += min(p_isl_n()[k], maxrows) - n;
         int needJ = r4(n * ldj), needA = r4(n * (n + 1) / 2);
-        int aoff = -2;
-        if (adr + n > rowCap() || used + needJ > arenaFloats() - scratch) { if (n) ovf++; n = 0; needJ = 0; needA = 0; }
-        else if (used + needJ + needA <= arenaFloats() - scratch) aoff = used + needJ;
-        else { n = 0; needJ = 0; needA = 0; ovf++; }
+        int aoff = used + needJ;
         p_isl_n()[k] = n; p_isl_adr()[k] = adr; p_isl_ldj()[k] = ldj; p_isl_J()[k] = used; p_isl_A()[k] = aoff;
         adr += n; used += needJ + (aoff >= 0 ? needA : 0);
       }
       p_isl_adr()[nisl] = adr; p_misc()[MISC_NEFC] = adr; p_misc()[MISC_ARENA_USED] = used;
       if (counters) {
         if (ovf) atomicAdd(&counters[CTR_ARENA_OVERFLOW], (unsigned long long)ovf);
+        if (cut) atomicAdd(&counters[CTR_ROW_DROPPED], (unsigned long long)cut);
       }
     }
     dropped = (int)warp_sum((float)dropped);

@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -31,7 +31,7 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -144,7 +144,7 @@ struct QuadrupedTask {
 
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
-  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, const int* ti, float*) {
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, int* ti, float*) {
     // _update_dynamic_obstacles: uses the pre-increment step counter; takes effect on the next step
     if (E.lane == 0) {
       float t = (float)ti[0] * 0.01f;
@@ -170,7 +170,7 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1;
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -270,7 +270,7 @@ struct DancingTask {
     }
   }
 
-  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, const int*, float*) {}
+  template <class EN> __device__ static void post_physics(EN&, const TaskParams&, int*, float*) {}
 
   // lane 0: current_step += 1 -> reward -> terminated -> truncated -> stats -> crowd -> move transition -> prev state
   template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
@@ -333,6 +333,176 @@ struct DancingTask {
     D(tf, 4) = combo;
     for (int i = 0; i < 23; i++) tf[36 + i] = qv[i];
     tf[13] = xp[0]; tf[14] = xp[1]; tf[15] = xp[2];
+    return reward;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ humanoid soccer
+// humanoid_soccer_env/soccer_env.py: step :398-452, reset :347-396, _randomize_initial_state :454-496,
+// _update_environmental_factors :498-508, _update_goalkeeper :506-524, _apply_environmental_effects :526-537,
+// _get_observation :539-631, _calculate_reward :633-690, _check_termination :692-716, _update_episode_stats :718-730,
+// helpers :733-833.  Quirks kept: the robot pose is written through jnt_qposadr[0] (the goalkeeper /
+// ball coordinates, so the robot itself always starts at the origin), the ball quaternion is left un-normalised, the
+// goalkeeper force persists in qfrc_applied, the wind force accumulates in xfrc_applied[ball] until the next reset.
+// ti: [0] current_step [1] goal_scored [2] goals_scored [3] ball_contacts [4] episode id
+// tf: [0] return [1..3] prev_ball_pos [4..6] prev_robot_pos [7,8] wind force per airborne step [9,10] xfrc_applied[ball].xy
+//     [11] time_upright [12] distance_traveled [13] max_ball_speed
+// ids: [0] torso body [1] ball body [2] goalkeeper body [3] ball geom [4] right_foot geom [5] left_foot geom
+//      [6,7] bitmask of geoms whose name contains foot/shin/thigh/torso/head/hand/arm [8] first observed joint (abdomen_y)
+//      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
+// inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
+struct SoccerTask {
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1;
+  static constexpr int NJOINT = 29, NOBSJ = 25;
+
+  template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
+    const float* q = E.p_xquat() + 4 * torso;
+    return q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3] > 0.7f;
+  }
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
+      act_clipped[i] = a; E.p_ctrl()[i] = a;          // mj_step clamps the four root motors to their own ctrlrange
+    }
+    E.sync();
+  }
+  // _update_goalkeeper + _apply_environmental_effects: both read the ball position of the previous forward pass,
+  // which is exactly prev_ball_pos
+  template <class EN> __device__ static void pre_physics(EN& E, const TaskParams& tp, int* ti, float* tf) {
+    if (E.lane == 0) {
+      int gq = E.I(DI_jnt_qposadr)[tp.ids[9]];
+      if (tf[1] < -10.0f) {
+        float err = clampf(tf[2], -3.0f, 3.0f) - E.p_qpos()[gq];
+        E.p_qapp()[tp.ids[9]] = clampf(50.0f * err, -100.0f, 100.0f);      // joint id used as a dof index (:524)
+      }
+      if (tf[3] > 0.5f) { tf[9] += tf[7]; tf[10] += tf[8]; }
+      float* x = E.p_xfrc(); x[0] = tf[9]; x[1] = tf[10]; x[2] = x[3] = x[4] = x[5] = 0.f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+                                     const float* inject) {
+    E.reset_data();
+    const int* jq = E.I(DI_jnt_qposadr); const float* jr = E.F(DF_jnt_range);
+    unsigned ep = (unsigned)ti[4]; unsigned ge = (unsigned)(B.env_offset + env);
+    auto draw = [&](int k, float lo, float hi) { return inject ? inject[k] : lo + (hi - lo) * rng_uniform(B.seed, ge, ep, (unsigned)k); };
+    float* q = E.p_qpos();
+    if (E.lane == 0) {
+      float rx = draw(0, -15.f, -5.f), ry = draw(1, -10.f, 10.f), ang = draw(2, -0.5f, 0.5f);
+      int a0 = jq[0];
+      q[a0] = rx; q[a0 + 1] = ry; q[a0 + 2] = 1.4f;
+      float sn, cs; sincosf(0.5f * ang, &sn, &cs);
+      q[a0 + 3] = cs; q[a0 + 4] = 0.f; q[a0 + 5] = 0.f; q[a0 + 6] = sn;
+      int bq = jq[tp.ids[10]];
+      q[bq] = rx + 2.0f; q[bq + 1] = ry; q[bq + 2] = 0.15f;
+    }
+    E.sync();
+    for (int i = E.lane; i < NJOINT; i += 32) {
+      int j = tp.ids[8] + i; float lo = jr[2 * j], hi = jr[2 * j + 1];
+      float noise = draw(3 + i, -0.1f, 0.1f);
+      if (lo < hi) q[jq[j]] = clampf(0.5f * (lo + hi) + noise, lo, hi);
+    }
+    E.sync();
+    if (E.lane == 0) {
+      q[jq[tp.ids[9]]] = draw(32, -2.f, 2.f);
+      float ws = draw(33, 0.f, 2.f), wa = draw(34, 0.f, 6.283185307179586f);
+      float sn, cs; sincosf(wa, &sn, &cs);
+      tf[7] = ws * cs * 0.1f; tf[8] = ws * sn * 0.1f; tf[9] = 0.f; tf[10] = 0.f;
+      tf[0] = 0.f; tf[11] = 0.f; tf[12] = 0.f; tf[13] = 0.f;
+      ti[0] = 0; ti[1] = 0; ti[2] = 0; ti[3] = 0; ti[4] = (int)(ep + 1);
+      float* x = E.p_xfrc(); for (int k = 0; k < 6; k++) x[k] = 0.f;
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void after_settle(EN& E, const TaskParams& tp, int* ti, float* tf) {
+    if (E.lane < 3) { tf[1 + E.lane] = E.p_xpos()[3 * tp.ids[1] + E.lane]; tf[4 + E.lane] = E.p_xpos()[3 * tp.ids[0] + E.lane]; }
+    E.sync();
+  }
+  // current_step += 1 precedes the observation (:416-419), which reads it (time remaining)
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams&, int* ti, float*) { if (E.lane == 0) ti[0] += 1; E.sync(); }
+
+  template <class EN> __device__ static __forceinline__ bool robot_geom(const TaskParams& tp, int g) {
+    return g < 64 && ((g < 32 ? (unsigned)tp.ids[6] >> g : (unsigned)tp.ids[7] >> (g - 32)) & 1u);
+  }
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
+    const int torso = tp.ids[0], ball = tp.ids[1], gk = tp.ids[2];
+    const int* ti = E.p_ti();
+    const int* jq = E.I(DI_jnt_qposadr); const int* jd = E.I(DI_jnt_dofadr); const float* jr = E.F(DF_jnt_range);
+    const float* xp = E.p_xpos();
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 25) { int j = tp.ids[8] + i; float lo = jr[2 * j], hi = jr[2 * j + 1]; if (lo < hi) v = clampf(2.f * (E.p_qpos()[jq[j]] - lo) / (hi - lo) - 1.f, -1.f, 1.f); }
+      else if (i < 50) v = clampf(E.p_qvel()[jd[tp.ids[8] + i - 25]] / 10.0f, -1.f, 1.f);
+      else if (i < 54) v = E.p_xquat()[4 * torso + i - 50];
+      else if (i < 57) v = clampf(E.p_qvel()[i - 54] / 5.0f, -1.f, 1.f);
+      else if (i < 60) v = clampf(E.p_qvel()[i - 54] / 10.0f, -1.f, 1.f);
+      else if (i < 63) v = clampf((xp[3 * ball + i - 60] - xp[3 * torso + i - 60]) / 30.0f, -1.f, 1.f);
+      else if (i < 66) v = clampf(E.p_qvel()[jd[tp.ids[10]] + i - 63] / 20.0f, -1.f, 1.f);
+      else if (i < 69) { const float g[3] = {24.5f, 0.0f, 1.22f}; v = clampf((g[i - 66] - xp[3 * torso + i - 66]) / 30.0f, -1.f, 1.f); }
+      else if (i < 73) {
+        // (dist, |friction[:2]|) of the last contact between a foot geom and geom 0 (:765-785)
+        int foot = tp.ids[4 + ((i - 69) >> 1)], ncon = E.p_misc()[MISC_NCON];
+        const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+        const int* pprm = E.I(DI_pair_prm); const float* prm = E.F(DF_prm);
+        for (int c = 0; c < ncon; c++) {
+          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+          if ((g1 == foot && g2 == 0) || (g2 == foot && g1 == 0)) {
+            const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
+            v = ((i - 69) & 1) ? sqrtf(pr[2] * pr[2] + pr[3] * pr[3]) : E.p_con()[B2_CON_STRIDE * c];
+          }
+        }
+        v = clampf(v / 1000.0f, -1.f, 1.f);
+      } else if (i < 76) {
+        // subtree_com[torso]: mass-weighted com of the bodies below the torso (the `root` body is not part of it)
+        const float* mass = E.F(DF_body_mass); float s = 0.f, m = 0.f;
+        for (int b = tp.ids[11]; b < tp.ids[11] + tp.ids[12]; b++) { s = fmaf(mass[b], E.p_xipos()[3 * b + i - 73], s); m += mass[b]; }
+        v = clampf(s / m / 30.0f, -1.f, 1.f);
+      } else if (i == 76) v = 1.0f - (float)ti[0] / (float)MAX_STEPS;
+      else if (i == 77) {
+        float dx = xp[3 * ball] - xp[3 * torso], dy = xp[3 * ball + 1] - xp[3 * torso + 1], dz = xp[3 * ball + 2] - xp[3 * torso + 2];
+        v = clampf(sqrtf(dx * dx + dy * dy + dz * dz) / 50.0f, 0.f, 1.f);
+      } else v = clampf(xp[3 * gk + i - 78] / 15.0f, -1.f, 1.f);
+      obs[i] = v;
+    }
+  }
+
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    const int torso = tp.ids[0], ball = tp.ids[1];
+    V3 bp = ld3(E.p_xpos() + 3 * ball), rp = ld3(E.p_xpos() + 3 * torso);
+    V3 pb = ld3(tf + 1), pr = ld3(tf + 4);
+    float reward = 0.f;
+    if (bp.x > 24.0f && fabsf(bp.y) < 3.66f && bp.z < 2.44f) { reward += 10000.0f; ti[1] = 1; ti[2] += 1; }
+    {
+      int ncon = E.p_misc()[MISC_NCON]; bool touch = false;
+      const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+      for (int c = 0; c < ncon && !touch; c++) {
+        int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+        if (g1 == tp.ids[3] || g2 == tp.ids[3]) touch = robot_geom<EN>(tp, g1 == tp.ids[3] ? g2 : g1);
+      }
+      if (touch) { reward += 1000.0f; ti[3] += 1; }
+    }
+    float cur = norm(bp - rp), prev = norm(pb - pr);
+    if (cur < prev && cur > 2.0f) reward += 500.0f * (prev - cur);
+    bool up = upright(E, torso);
+    if (up) { reward += 200.0f; tf[11] += 0.02f; }
+    V3 goal = v3(24.5f, 0.f, 0.f);
+    float pg = norm(pr - goal), cg = norm(rp - goal);
+    if (cg < pg) reward += 100.0f * (pg - cg);
+    float a2 = 0.f;
+    for (int i = 0; i < ACT; i++) a2 = fmaf(act[i], act[i], a2);
+    reward += -0.1f * a2;
+    if (!up) reward += -1000.0f;
+    float pbg = norm(pb - goal), cbg = norm(bp - goal);
+    if (cbg < pbg) reward += 300.0f * (pbg - cbg);
+    tf[0] += reward;
+    *terminated = ti[1] || (!up && ti[0] > 100) || fabsf(bp.x) > 30.0f || fabsf(bp.y) > 20.0f || bp.z < -1.0f || bp.z > 10.0f ||
+                  fabsf(rp.x) > 30.0f || fabsf(rp.y) > 20.0f || rp.z < 0.0f || rp.z > 5.0f;
+    *truncated = ti[0] >= MAX_STEPS;
+    tf[12] += norm(rp - pr);
+    { const float* bv = E.p_qvel() + E.I(DI_jnt_dofadr)[tp.ids[10]]; tf[13] = fmaxf(tf[13], sqrtf(bv[0] * bv[0] + bv[1] * bv[1] + bv[2] * bv[2])); }
+    st3(tf + 1, bp); st3(tf + 4, rp);
     return reward;
   }
 };

@@ -139,7 +139,7 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
     T["bw_pack"] = i32([(d | (int(desc_num[d]) << 8) | (int(desc_adr[d]) << 16)) for d in dl] if dl else [0])
     T["fw_pack"] = i32([(d | (int(A["dof_Madr"][d]) << 8)) for d in dl] if dl else [0])
     # flat program of the L'DL factorisation: one step per eliminated dof k (leaves first) with depth > 0,
-    #   fac_step = diag_adr | n_ops << 10 | op_adr << 16 ; fac_ops = tgt | a << 10 | b << 20  (LD[tgt] -= LD[a]*LD[b]/LD[diag])
+    #   fac_step = diag_adr | n_ops << 10 | op_adr << 18 ; fac_ops = tgt | a << 10 | b << 20  (LD[tgt] -= LD[a]*LD[b]/LD[diag])
     assert nM < 1024
     fac_step, fac_ops = [], []
     for k in range(nv - 1, -1, -1):
@@ -152,8 +152,8 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
                 aa = int(A["dof_Madr"][Mcol[ak + mm]])
                 fac_ops.append((aa + (n - mm)) | ((ak + mm) << 10) | ((ak + n) << 20))
         cnt = len(fac_ops) - start
-        assert cnt < 64 and start < 65536
-        fac_step.append(ak | (cnt << 10) | (start << 16))
+        assert cnt < 256 and start < 8192
+        fac_step.append(ak | (cnt << 10) | (start << 18))
     T["fac_step"] = i32(fac_step if fac_step else [0]); T["fac_ops"] = i32(fac_ops if fac_ops else [0])
     ndesc = len(desc_dof)
     T["tree_dofadr"] = i32(D["tree_dofadr"]); T["tree_dofnum"] = i32(D["tree_dofnum"])
@@ -186,9 +186,8 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
         cg_type.append(A["geom_type"][g]); cg_body.append(A["geom_bodyid"][g]); cg_size.append(A["geom_size"][g])
         cg_pos.append(A["geom_pos"][g]); cg_mat.append(quat_to_mat(A["geom_quat"][g]).ravel())
         cg_rb.append(A["geom_rbound"][g])
-        if A["body_weldid"][A["geom_bodyid"][g]] == 0 and A["geom_bodyid"][g] != 0:
-            # static non-world body: fold the (constant) body pose into the geom and attach it to the world
-            raise NotImplementedError("static geoms on non-world bodies: fold pose at compile time")
+        # geoms of static non-world bodies (goal posts, ...) keep their body: the kinematics pass computes every
+        # body frame, static ones included; their island is -1 and their chain mask empty, so they only push back
     T["cg_type"] = i32(cg_type if ncg else [0]); T["cg_body"] = i32(cg_body if ncg else [0])
     T["cg_geomid"] = i32(used if ncg else [0])
     T["cg_size"] = f64(cg_size if ncg else [0] * 3); T["cg_pos"] = f64(cg_pos if ncg else [0] * 3)

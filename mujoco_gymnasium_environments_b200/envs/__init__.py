@@ -1,2 +1,3 @@
 from .quadruped_parkour import QuadrupedParkourEnv  # noqa: F401
 from .humanoid_dancing import HumanoidDancingEnv  # noqa: F401
+from .humanoid_soccer import HumanoidSoccerEnv  # noqa: F401

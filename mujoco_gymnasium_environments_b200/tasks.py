@@ -87,6 +87,49 @@ def _dance_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- humanoid soccer
+_SOCCER_PARTS = ("foot", "shin", "thigh", "torso", "head", "hand", "arm")          # soccer_env.py:797-798
+
+
+_SOCCER_JOINTS = ["abdomen_y", "abdomen_z", "abdomen_x", "neck_x", "neck_y",                # soccer_env.py:226-233
+                  "right_shoulder1", "right_shoulder2", "right_elbow", "right_wrist_y", "right_wrist_x", "right_wrist_z",
+                  "left_shoulder1", "left_shoulder2", "left_elbow", "left_wrist_y", "left_wrist_x", "left_wrist_z",
+                  "right_hip_x", "right_hip_z", "right_hip_y", "right_knee", "right_ankle_y", "right_ankle_x",
+                  "left_hip_x", "left_hip_z", "left_hip_y", "left_knee", "left_ankle_y", "left_ankle_x"]
+
+
+def _soccer_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_HUMANOID_SOCCER
+    mask = 0
+    for g, name in enumerate(t.names["geom"]):
+        if name and any(p in name for p in _SOCCER_PARTS):
+            assert g < 64
+            mask |= 1 << g
+    torso = t.name2id("body", "torso")
+    parent = t.body_parentid
+    def below(b):
+        while b > 0:
+            if b == torso:
+                return True
+            b = int(parent[b])
+        return False
+    sub = [b for b in range(int(t.nbody)) if below(b)]
+    assert sub == list(range(torso, torso + len(sub))), "torso subtree must be contiguous"
+    jids = [t.name2id("joint", n) for n in _SOCCER_JOINTS]
+    assert jids == list(range(jids[0], jids[0] + 29)), "observed joints must be contiguous"
+    lo32 = mask & 0xffffffff; hi32 = (mask >> 32) & 0xffffffff
+    as_i32 = lambda u: u - (1 << 32) if u >= (1 << 31) else u
+    ids = [torso, t.name2id("body", "ball"), t.name2id("body", "opponent_goalkeeper"), t.name2id("geom", "ball_geom"),
+           t.name2id("geom", "right_foot"), t.name2id("geom", "left_foot"), as_i32(lo32), as_i32(hi32), jids[0],
+           t.name2id("joint", "goalkeeper_y"), t.name2id("joint", "ball_joint"), sub[0], len(sub)]
+    for k, v in enumerate(ids):
+        d.ids[k] = v
+    for k in range(33):
+        d.act_lo[k] = -150.0; d.act_hi[k] = 150.0
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -102,4 +145,11 @@ TASKS: Dict[str, TaskSpec] = {
         observation_space=lambda t: Box(np.full(94, -np.inf, np.float32), np.full(94, np.inf, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "current_move", "beat_phase", "combo_multiplier", "crowd_excitement",
                    "performance_score"]),
+    "humanoid_soccer": TaskSpec(
+        name="humanoid_soccer", task_id=capi.TASK_HUMANOID_SOCCER, obs_dim=80, act_dim=33, max_episode_steps=5000,
+        frame_skip=1, render_fps=50, bytes_per_env_step=1626, describe=_soccer_desc,
+        action_space=lambda t: Box(np.full(33, -150.0, np.float32), np.full(33, 150.0, np.float32), dtype=np.float32),
+        observation_space=lambda t: Box(np.full(80, -1.0, np.float32), np.full(80, 1.0, np.float32), dtype=np.float32),
+        info_keys=["episode_stats", "ball_position", "robot_position", "goal_distance", "ball_contact", "robot_upright",
+                   "goal_scored"]),
 }

@@ -419,4 +419,198 @@ class HumanoidDancingRef:
         return False
 
 
-TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef}
+class HumanoidSoccerRef:
+    """humanoid_soccer_env/soccer_env.py restated: __init__ :32-118, _get_model_indices :222-263, reset :347-396,
+    step :398-452, _randomize_initial_state :454-496, _update_environmental_factors :498-508, _update_goalkeeper
+    :506-524, _apply_environmental_effects :526-537, _get_observation :539-631, _calculate_reward :633-690,
+    _check_termination :692-716, _update_episode_stats :718-730, helpers :733-833."""
+
+    JOINT_NAMES = ["abdomen_y", "abdomen_z", "abdomen_x", "neck_x", "neck_y",
+                   "right_shoulder1", "right_shoulder2", "right_elbow", "right_wrist_y", "right_wrist_x", "right_wrist_z",
+                   "left_shoulder1", "left_shoulder2", "left_elbow", "left_wrist_y", "left_wrist_x", "left_wrist_z",
+                   "right_hip_x", "right_hip_z", "right_hip_y", "right_knee", "right_ankle_y", "right_ankle_x",
+                   "left_hip_x", "left_hip_z", "left_hip_y", "left_knee", "left_ankle_y", "left_ankle_x"]
+    ROBOT_PARTS = ["foot", "shin", "thigh", "torso", "head", "hand", "arm"]
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("humanoid_soccer")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.dt = 0.02; self.max_episode_steps = 5000; self.current_step = 0
+        self.num_joints = int(t.nu)
+        self.joint_indices = [t.name2id("joint", n) for n in self.JOINT_NAMES]
+        self.torso_id = t.name2id("body", "torso"); self.ball_id = t.name2id("body", "ball")
+        self.goalkeeper_id = t.name2id("body", "opponent_goalkeeper")
+        self.ball_geom_id = t.name2id("geom", "ball_geom")
+        self.right_foot_id = t.name2id("geom", "right_foot"); self.left_foot_id = t.name2id("geom", "left_foot")
+        self.ball_joint = t.name2id("joint", "ball_joint"); self.goalkeeper_joint = t.name2id("joint", "goalkeeper_y")
+        self.jnt_range = np.asarray(t.jnt_range); self.jnt_qposadr = np.asarray(t.jnt_qposadr); self.jnt_dofadr = np.asarray(t.jnt_dofadr)
+        self.geom_names = t.names["geom"]
+        self.action_low = np.full(self.num_joints, -150.0); self.action_high = np.full(self.num_joints, 150.0)
+        self.wind_strength = 0.0; self.wind_direction = np.array([0.0, 0.0])
+        self.goal_scored = False
+        self.episode_stats = dict(goals_scored=0, ball_contacts=0, distance_traveled=0.0, time_upright=0.0, max_ball_speed=0.0)
+        self.prev_ball_pos = None; self.prev_robot_pos = None
+        self.np_random = np.random.default_rng(seed)
+
+    # -- reset :347-396; `draws` lets tests inject the 36 random draws in the reference's order
+    def reset(self, seed=None, draws=None):
+        if seed is not None:
+            self.np_random = np.random.default_rng(seed)
+        d = self.data
+        ref.mj_resetData(self.model, d)
+        self.current_step = 0; self.goal_scored = False
+        self.episode_stats = dict(goals_scored=0, ball_contacts=0, distance_traveled=0.0, time_upright=0.0, max_ball_speed=0.0)
+        it = iter(draws) if draws is not None else None
+        U = (lambda lo, hi: float(next(it))) if it is not None else (lambda lo, hi: self.np_random.uniform(lo, hi))
+        # _randomize_initial_state :454-496
+        robot_x = U(-15.0, -5.0); robot_y = U(-10.0, 10.0); robot_z = 1.4
+        a0 = self.jnt_qposadr[0]
+        d.qpos[a0:a0 + 3] = [robot_x, robot_y, robot_z]
+        angle = U(-0.5, 0.5)
+        d.qpos[a0 + 3:a0 + 7] = [np.cos(angle / 2), 0, 0, np.sin(angle / 2)]
+        bq = self.jnt_qposadr[self.ball_joint]
+        d.qpos[bq:bq + 3] = [robot_x + 2.0, robot_y, 0.15]
+        for joint_idx in self.joint_indices:
+            if joint_idx < len(d.qpos):
+                lo, hi = self.jnt_range[joint_idx]
+                if lo < hi:
+                    noise = U(-0.1, 0.1)
+                    d.qpos[self.jnt_qposadr[joint_idx]] = np.clip((lo + hi) / 2 + noise, lo, hi)
+        d.qpos[self.jnt_qposadr[self.goalkeeper_joint]] = U(-2.0, 2.0)
+        # _update_environmental_factors :498-508
+        self.wind_strength = U(0.0, 2.0)
+        wind_angle = U(0, 2 * np.pi)
+        self.wind_direction = np.array([np.cos(wind_angle), np.sin(wind_angle)])
+        self.field_friction_variation = U(0.05, 0.15)
+        ref.mj_step(self.model, d, 10)
+        obs = self._get_observation()
+        self.prev_ball_pos = d.xpos[self.ball_id].copy(); self.prev_robot_pos = d.xpos[self.torso_id].copy()
+        return obs, dict(episode_stats=dict(self.episode_stats))
+
+    def step(self, action):
+        d = self.data
+        action = np.clip(np.asarray(action, np.float64), self.action_low, self.action_high)
+        d.ctrl[:] = action
+        # _update_goalkeeper :506-524 (ball position of the previous forward pass)
+        ball_pos = d.xpos[self.ball_id]
+        if ball_pos[0] < -10.0:
+            error = np.clip(ball_pos[1], -3.0, 3.0) - d.qpos[self.jnt_qposadr[self.goalkeeper_joint]]
+            d.qfrc_applied[self.goalkeeper_joint] = np.clip(50.0 * error, -100.0, 100.0)
+        # _apply_environmental_effects :526-537
+        if ball_pos[2] > 0.5:
+            d.xfrc_applied[self.ball_id, :2] += self.wind_strength * self.wind_direction * 0.1
+        ref.mj_step(self.model, d)
+        self.current_step += 1
+        obs = self._get_observation()
+        reward = self._calculate_reward(action)
+        terminated = self._check_termination()
+        truncated = self.current_step >= self.max_episode_steps
+        robot_pos = d.xpos[self.torso_id]
+        self.episode_stats["distance_traveled"] += float(np.linalg.norm(robot_pos - self.prev_robot_pos))
+        bd = self.jnt_dofadr[self.ball_joint]
+        self.episode_stats["max_ball_speed"] = max(self.episode_stats["max_ball_speed"], float(np.linalg.norm(d.qvel[bd:bd + 3])))
+        info = dict(episode_stats=dict(self.episode_stats), ball_position=d.xpos[self.ball_id].copy(),
+                    robot_position=robot_pos.copy(), goal_scored=self.goal_scored)
+        self.prev_ball_pos = d.xpos[self.ball_id].copy(); self.prev_robot_pos = robot_pos.copy()
+        return obs, reward, terminated, truncated, info
+
+    def _is_robot_upright(self):
+        w, x, y, z = self.data.xquat[self.torso_id]
+        return (w*w - x*x - y*y + z*z) > 0.7
+
+    def _foot_contact_forces(self):
+        f = np.zeros(4)
+        for con in self.data.contact:
+            if (con.geom1 == self.right_foot_id and con.geom2 == 0) or (con.geom2 == self.right_foot_id and con.geom1 == 0):
+                f[0] = con.dist; f[1] = np.linalg.norm(con.friction[:2])
+            if (con.geom1 == self.left_foot_id and con.geom2 == 0) or (con.geom2 == self.left_foot_id and con.geom1 == 0):
+                f[2] = con.dist; f[3] = np.linalg.norm(con.friction[:2])
+        return f
+
+    def _check_ball_contact(self):
+        for con in self.data.contact:
+            if con.geom1 == self.ball_geom_id or con.geom2 == self.ball_geom_id:
+                other = con.geom2 if con.geom1 == self.ball_geom_id else con.geom1
+                name = self.geom_names[other]
+                if name and any(part in name for part in self.ROBOT_PARTS):
+                    return True
+        return False
+
+    def _get_observation(self):
+        d = self.data
+        obs = []
+        n = min(self.num_joints, 25)
+        for i in range(n):
+            if i < len(self.joint_indices) and self.joint_indices[i] < len(d.qpos):
+                j = self.joint_indices[i]
+                lo, hi = self.jnt_range[j]
+                obs.append(np.clip(2 * (d.qpos[self.jnt_qposadr[j]] - lo) / (hi - lo) - 1, -1.0, 1.0) if lo < hi else 0.0)
+            else:
+                obs.append(0.0)
+        for i in range(n):
+            if i < len(self.joint_indices) and self.joint_indices[i] < len(d.qvel):
+                obs.append(np.clip(d.qvel[self.jnt_dofadr[self.joint_indices[i]]] / 10.0, -1.0, 1.0))
+            else:
+                obs.append(0.0)
+        obs.extend(d.xquat[self.torso_id])
+        obs.extend(np.clip(d.qvel[:3] / 5.0, -1.0, 1.0))
+        obs.extend(np.clip(d.qvel[3:6] / 10.0, -1.0, 1.0))
+        robot_pos = d.xpos[self.torso_id]; ball_pos = d.xpos[self.ball_id]
+        rel = ball_pos - robot_pos
+        obs.extend(np.clip(rel / 30.0, -1.0, 1.0))
+        bd = self.jnt_dofadr[self.ball_joint]
+        obs.extend(np.clip(d.qvel[bd:bd + 3] / 20.0, -1.0, 1.0))
+        obs.extend(np.clip((np.array([24.5, 0.0, 1.22]) - robot_pos) / 30.0, -1.0, 1.0))
+        obs.extend(np.clip(self._foot_contact_forces() / 1000.0, -1.0, 1.0))
+        obs.extend(np.clip(d.subtree_com[self.torso_id] / 30.0, -1.0, 1.0))
+        obs.append(1.0 - self.current_step / self.max_episode_steps)
+        obs.append(np.clip(np.linalg.norm(rel) / 50.0, 0.0, 1.0))
+        obs.extend(np.clip(d.xpos[self.goalkeeper_id][:2] / 15.0, -1.0, 1.0))
+        return np.array(obs, dtype=np.float32)
+
+    def _calculate_reward(self, action):
+        d = self.data
+        reward = 0.0
+        ball_pos = d.xpos[self.ball_id].copy(); robot_pos = d.xpos[self.torso_id].copy()
+        if ball_pos[0] > 24.0 and abs(ball_pos[1]) < 3.66 and ball_pos[2] < 2.44:
+            reward += 10000.0; self.goal_scored = True; self.episode_stats["goals_scored"] += 1
+        if self._check_ball_contact():
+            reward += 1000.0; self.episode_stats["ball_contacts"] += 1
+        cur = np.linalg.norm(ball_pos - robot_pos)
+        if self.prev_ball_pos is not None and self.prev_robot_pos is not None:
+            prev = np.linalg.norm(self.prev_ball_pos - self.prev_robot_pos)
+            if cur < prev and cur > 2.0:
+                reward += 500.0 * (prev - cur)
+        if self._is_robot_upright():
+            reward += 200.0; self.episode_stats["time_upright"] += self.dt
+        goal = np.array([24.5, 0.0, 0.0])
+        if self.prev_robot_pos is not None:
+            pg = np.linalg.norm(self.prev_robot_pos - goal); cg = np.linalg.norm(robot_pos - goal)
+            if cg < pg:
+                reward += 100.0 * (pg - cg)
+        reward += -0.1 * float(np.sum(np.square(action)))
+        if not self._is_robot_upright():
+            reward += -1000.0
+        if self.prev_ball_pos is not None:
+            pbg = np.linalg.norm(self.prev_ball_pos - goal); cbg = np.linalg.norm(ball_pos - goal)
+            if cbg < pbg:
+                reward += 300.0 * (pbg - cbg)
+        return float(reward)
+
+    def _check_termination(self):
+        if self.goal_scored:
+            return True
+        if not self._is_robot_upright() and self.current_step > 100:
+            return True
+        b = self.data.xpos[self.ball_id]
+        if abs(b[0]) > 30.0 or abs(b[1]) > 20.0 or b[2] < -1.0 or b[2] > 10.0:
+            return True
+        r = self.data.xpos[self.torso_id]
+        if abs(r[0]) > 30.0 or abs(r[1]) > 20.0 or r[2] < 0.0 or r[2] > 5.0:
+            return True
+        return False
+
+
+TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef}

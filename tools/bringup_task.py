@@ -27,6 +27,12 @@ def make_inject(task, rng, n):
         inj = np.zeros((n, 40), np.float32)
         inj[:, 0::2] = rng.integers(0, 10, (n, 20)); inj[:, 1::2] = rng.uniform(1, 3, (n, 20))
         return inj
+    if task == "humanoid_soccer":
+        inj = np.zeros((n, 36), np.float32)
+        inj[:, 0] = rng.uniform(-15, -5, n); inj[:, 1] = rng.uniform(-10, 10, n); inj[:, 2] = rng.uniform(-.5, .5, n)
+        inj[:, 3:32] = rng.uniform(-.1, .1, (n, 29)); inj[:, 32] = rng.uniform(-2, 2, n); inj[:, 33] = rng.uniform(0, 2, n)
+        inj[:, 34] = rng.uniform(0, 2 * np.pi, n); inj[:, 35] = rng.uniform(.05, .15, n)
+        return inj
     raise KeyError(task)
 
 
@@ -35,6 +41,8 @@ def ref_reset(task, env, inj):
         return env.reset(randomize=(float(inj[0]), float(inj[1])))
     if task == "humanoid_dancing":
         return env.reset(sequence=[(int(inj[2 * k]), float(inj[2 * k + 1])) for k in range(20)])
+    if task == "humanoid_soccer":
+        return env.reset(draws=[float(x) for x in inj])
 
 
 def main():
