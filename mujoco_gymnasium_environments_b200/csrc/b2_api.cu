@@ -279,7 +279,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   b->W = (opts && opts->warps_per_env > 0) ? opts->warps_per_env : 3;
   if (b->W != 1 && b->W != 3) { delete b; return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3"); }
   v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < 32 ? dim[DD_maxraw] : 32); if (v.con_cap < 1) v.con_cap = 1;
-  v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > 32 * B2_PGS_S * 4) v.row_cap = 32 * B2_PGS_S * 4;
+  v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > B2_ISLAND_ROWS * 4) v.row_cap = B2_ISLAND_ROWS * 4;
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];

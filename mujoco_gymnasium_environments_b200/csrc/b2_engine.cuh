@@ -29,7 +29,7 @@ namespace b2 {
 #define B2_MAXIMP 0.9999f
 #define B2_MAX_ISLANDS 16
 #define B2_CON_STRIDE 16   // floats per contact record
-#define B2_PGS_S 3         // 32*S rows per island held in registers
+#define B2_ISLAND_ROWS 128  // rows per island: each lane of the sweeping warp owns 4 consecutive rows in registers
 #define B2_FULL 0xffffffffu
 
 struct DevModel {
@@ -54,7 +54,7 @@ extern __shared__ __align__(128) float b2_smem[];
 #define B2_WS_FLOAT_FIELDS(X) X(qpos) X(qvel) X(warm) X(ctrl) X(qapp) X(xpos) X(xmat) X(cdof) X(rootcom) \
   X(xquat) X(xipos) X(cvel) X(cacc) X(cinert) X(M) X(LD) X(invD) X(qfs) X(qas) X(qfc) X(qacc) X(tmp) X(con) \
   X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc)
-#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
+#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_warp) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
 
 struct WsOff {
 #define X(n) int n;
@@ -84,7 +84,7 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   t.qacc = take(nv); t.tmp = take(nv);
   t.con = take(con_cap * B2_CON_STRIDE); t.lim_row = take(2 * (nlim > 0 ? nlim : 1)); t.con_row = take(con_cap);
   t.row_info = take(row_cap); t.row_R = take(row_cap); t.row_b = take(row_cap); t.row_f = take(row_cap); t.row_res = take(row_cap);
-  t.isl_n = take(B2_MAX_ISLANDS); t.isl_nl = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
+  t.isl_n = take(B2_MAX_ISLANDS); t.isl_nl = take(B2_MAX_ISLANDS); t.isl_warp = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
   t.isl_A = take(B2_MAX_ISLANDS); t.isl_ldj = take(B2_MAX_ISLANDS);
   t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(nti > 0 ? nti : 1); t.tf = take(ntf > 0 ? ntf : 1);
   t.act = take(40);
@@ -558,7 +558,7 @@ struct Engine {
     int nlim = dim(DD_nlim), nisl = dim(DD_nisland), ncon = p_misc()[MISC_NCON];
     if (lane < B2_MAX_ISLANDS) p_isl_n()[lane] = 0;
     sync();
-    const int maxrows = 32 * B2_PGS_S;
+    const int maxrows = B2_ISLAND_ROWS;
     int dropped = 0;
     unsigned lt = (1u << lane) - 1u;
     for (int c0 = 0; c0 < nlim; c0 += 32) {
@@ -611,20 +611,33 @@ struct Engine {
         // the last contacts go first, the joint limits last; every cut is counted
         int avail = arenaFloats() - scratch - used - 8;
         if (adr + n > rowCap()) { n = max(rowCap() - adr, 0); ovf++; }
-        if (r4(n * ldj) + r4(n * (n + 1) / 2) > avail) {
-          float hb = (float)ldj + 0.5f;
-          int nf = avail > 0 ? (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) : 0;
-          while (nf > 0 && r4(nf * ldj) + r4(nf * (nf + 1) / 2) > avail) nf--;
+        if (r4(n * ldj) + a_floats(n) > avail) {
+          float hb = (float)ldj + 2.0f;
+          int nf = avail > 0 ? (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) + 4 : 0;
+          while (nf > 0 && r4(nf * ldj) + a_floats(nf) > avail) nf--;
           n = min(n, nf); ovf++;
         }
         { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
         cut += min(p_isl_n()[k], maxrows) - n;
-        int needJ = r4(n * ldj), needA = r4(n * (n + 1) / 2);
+        int needJ = r4(n * ldj), needA = a_floats(n);
         int aoff = used + needJ;
         p_isl_n()[k] = n; p_isl_adr()[k] = adr; p_isl_ldj()[k] = ldj; p_isl_J()[k] = used; p_isl_A()[k] = aoff;
         adr += n; used += needJ + (aoff >= 0 ? needA : 0);
       }
       p_isl_adr()[nisl] = adr; p_misc()[MISC_NEFC] = adr; p_misc()[MISC_ARENA_USED] = used;
+      // islands -> warps of the team, greedily by sweep length (4-row blocks), so the A build and the PGS sweeps of
+      // one env finish together
+      int load[W > 1 ? W : 1];
+#pragma unroll
+      for (int q = 0; q < W; q++) load[q] = 0;
+      for (int k = 0; k < nisl; k++) {
+        int best = 0;
+#pragma unroll
+        for (int q = 1; q < W; q++) if (load[q] < load[best]) best = q;
+        p_isl_warp()[k] = best;
+#pragma unroll
+        for (int q = 0; q < W; q++) if (q == best) load[q] += p_isl_n()[k] ? ((p_isl_n()[k] + 3) >> 2) + 2 : 0;
+      }
       if (counters) {
         if (ovf) atomicAdd(&counters[CTR_ARENA_OVERFLOW], (unsigned long long)ovf);
         if (cut) atomicAdd(&counters[CTR_ROW_DROPPED], (unsigned long long)cut);
@@ -765,8 +778,29 @@ struct Engine {
     team_sync();
   }
 
-  // packed symmetric index
-  __device__ __forceinline__ static int tri(int i) { return (i * (i + 1)) >> 1; }
+  // ---- layout of an island's A = J M^-1 J' + R: 4x4 tiles of the lower block triangle, tile (ti, tj <= ti) at
+  // 16 * (tri(ti) + tj) floats.  Row c of a tile (4 floats = one 128-bit load) sits at chunk slot c ^ ((tile >> 1) & 3), so
+  // eight consecutive lanes reading the same row of eight different tiles touch eight different 16-byte bank groups.
+  // Diagonal tiles are stored in full; rows / columns past n are zero (the sweep treats them as inert rows).
+  __device__ __host__ __forceinline__ static int tri(int i) { return (i * (i + 1)) >> 1; }
+  __device__ __host__ __forceinline__ static int a_floats(int n) { int nt = (n + 3) >> 2; return 16 * tri(nt); }
+  __device__ __forceinline__ static int a_index(int i, int j) {          // requires (i >> 2) >= (j >> 2)
+    int t = tri(i >> 2) + (j >> 2);
+    return 16 * t + 4 * ((i & 3) ^ ((t >> 1) & 3)) + (j & 3);
+  }
+  // C[k][j] = A(4M + k, 4b + j): one tile, four 128-bit shared loads, transposed on the fly when it lies above the diagonal
+  __device__ __forceinline__ static void tile_coeffs(const float* A, int M, int b, float (&C)[4][4]) {
+    const bool lower = M >= b; const int t = lower ? tri(M) + b : tri(b) + M; const int sw = (t >> 1) & 3;
+    const float4* q = reinterpret_cast<const float4*>(A + 16 * t);
+    float4 q0 = q[sw], q1 = q[1 ^ sw], q2 = q[2 ^ sw], q3 = q[3 ^ sw];
+    C[0][0] = q0.x; C[1][1] = q1.y; C[2][2] = q2.z; C[3][3] = q3.w;
+    C[0][1] = lower ? q0.y : q1.x; C[1][0] = lower ? q1.x : q0.y;
+    C[0][2] = lower ? q0.z : q2.x; C[2][0] = lower ? q2.x : q0.z;
+    C[0][3] = lower ? q0.w : q3.x; C[3][0] = lower ? q3.x : q0.w;
+    C[1][2] = lower ? q1.z : q2.y; C[2][1] = lower ? q2.y : q1.z;
+    C[1][3] = lower ? q1.w : q3.y; C[3][1] = lower ? q3.y : q1.w;
+    C[2][3] = lower ? q2.w : q3.z; C[3][2] = lower ? q3.z : q2.w;
+  }
 
   // ---- A = J M^-1 J' + R per island (mj_projectConstraint), 32 columns at a time, lane = column
   __device__ void build_A() {
@@ -775,12 +809,14 @@ struct Engine {
     const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
     const float* LDp = p_LD();
     int nisl = dim(DD_nisland);
-    // island k is built by warp k % W; its column scratch (32 floats per dof of the island) sits at 32 * dofadr
-    for (int k = wl; k < nisl; k += W) {
-      int n = p_isl_n()[k]; if (!n) continue;
+    // island k is built by the warp it was assigned to; its column scratch (32 floats per dof) sits at 32 * dofadr
+    for (int k = 0; k < nisl; k++) {
+      int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       int d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
       float* scratch = scratch_base() + 32 * d0;
       const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k);
+      { float4* Az = reinterpret_cast<float4*>(A); int nz = a_floats(n) >> 2; for (int i = lane; i < nz; i += 32) Az[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      sync();
       for (int j0 = 0; j0 < n; j0 += 32) {
         int j = j0 + lane; bool valid = j < n;
         float* x = scratch + lane;   // column, stride 32: lane-contiguous, conflict-free
@@ -789,12 +825,12 @@ struct Engine {
         // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent
         for (int jj = nd - 1; jj >= 0; jj--) {
           int dn = dnum[d0 + jj]; const int* dp = dpack + dadr[d0 + jj];
-          float s0 = x[32 * jj], s1 = 0.f; int k = 0;
-          for (; k + 2 <= dn; k += 2) {
-            int p0 = dp[k], p1 = dp[k + 1];
+          float s0 = x[32 * jj], s1 = 0.f; int q = 0;
+          for (; q + 2 <= dn; q += 2) {
+            int p0 = dp[q], p1 = dp[q + 1];
             s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * ((p1 & 0xffff) - d0)], s1);
           }
-          if (k < dn) { int p0 = dp[k]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
+          if (q < dn) { int p0 = dp[q]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
           x[32 * jj] = s0 + s1;
         }
         for (int i = 0; i < nd; i++) {
@@ -806,12 +842,28 @@ struct Engine {
           if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0);
           x[32 * i] = s0 + s1;
         }
-        // lower triangle: A[i][j] = J_i . x for i >= j
-        for (int i = j0; i < n; i++) {
-          const float* Ji = J + i * ldj; float s = 0.f;
-#pragma unroll 4
-          for (int c = 0; c < nd; c++) s = fmaf(Ji[c], x[32 * c], s);
-          if (valid && i >= j) A[tri(i) + j] = s + (i == j ? p_row_R()[e0 + i] : 0.f);
+        // lower triangle: A[i][j] = J_i . x for i >= j; four rows at a time share the loads of the column
+        for (int i = j0; i < n; i += 4) {
+          const float* J0 = J + i * ldj; const float* J1 = J + min(i + 1, n - 1) * ldj;
+          const float* J2 = J + min(i + 2, n - 1) * ldj; const float* J3 = J + min(i + 3, n - 1) * ldj;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 2
+          for (int c = 0; c < nd; c++) {
+            float xc = x[32 * c];
+            s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
+          }
+          if (valid) {
+            float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              int ii = i + u;
+              if (ii < n && ii >= j) {
+                float v = sv[u] + (ii == j ? p_row_R()[e0 + ii] : 0.f);
+                A[a_index(ii, j)] = v;
+                if ((ii >> 2) == (j >> 2) && ii != j) A[a_index(j, ii)] = v;      // diagonal tiles are stored in full
+              }
+            }
+          }
         }
         sync();
       }
@@ -821,39 +873,63 @@ struct Engine {
 
   // ---- PGS (mj_solPGS restated; row order = MuJoCo's within each island, islands are exactly decoupled so each
   // warp of the team sweeps its own islands; the stopping rule uses the improvement summed over all islands, exchanged
-  // through shared memory once per iteration).  Forces, residuals, 1/A_ii and the packed-A addresses of a sweep live in
-  // registers.  mj_solPGS's "restore if the cost went up by more than 1e-10" guard is dropped: for these scalar row
-  // updates the cost change is <= 0 in exact arithmetic, the guard only ever fires on round-off.
-  struct Chain { int n, e0; const float* A; float f[B2_PGS_S], r[B2_PGS_S], ainv[B2_PGS_S], ad[B2_PGS_S]; int adr[B2_PGS_S]; };
-  __device__ __forceinline__ void chain_load(Chain& c, int k, const float* res) {
-    c.n = p_isl_n()[k]; c.e0 = p_isl_adr()[k]; c.A = island_A(k);
+  // through shared memory once per iteration).  Lane L keeps rows 4L..4L+3 of the island (force, residual, 1/A_ii) in
+  // registers.  Rows are swept four at a time: the lane that owns block b updates its four rows in order from its
+  // diagonal tile -- a chain of one FFMA + one FMNMX per row -- the four force changes are broadcast with shuffles that
+  // overlap that chain, and every lane folds them into its residuals with the 4x4 tile (its rows x block b).  This is
+  // the same sequence of scalar row updates as mj_solPGS (same order, same clamps), at a quarter of the shuffles.
+  // mj_solPGS's "restore if the cost went up by more than 1e-10" guard is dropped: for these scalar row updates the cost
+  // change is <= 0 in exact arithmetic, the guard only ever fires on round-off.
+  struct Rows { float f[4], r[4], ainv[4], ad[4]; };
+  __device__ __forceinline__ void rows_load(Rows& w, int n, int e0, const float* A, const float* res) {
 #pragma unroll
-    for (int s = 0; s < B2_PGS_S; s++) {
-      int i = lane + 32 * s; bool v = i < c.n;
-      c.f[s] = v ? p_row_f()[c.e0 + i] : 0.f; c.r[s] = v ? res[c.e0 + i] : 0.f;
-      c.ad[s] = v ? c.A[tri(i) + i] : 1.f; c.ainv[s] = 1.f / c.ad[s];
-      c.adr[s] = tri(i);            // address of A(row 0, column i) in the packed lower triangle
+    for (int q = 0; q < 4; q++) {
+      int i = 4 * lane + q; bool v = i < n;
+      w.f[q] = v ? p_row_f()[e0 + i] : 0.f; w.r[q] = v ? res[e0 + i] : 0.f;
+      w.ad[q] = v ? A[a_index(i, i)] : 1.f; w.ainv[q] = v ? p_row_R()[e0 + i] : 1.f;      // row_R holds 1/A_ii during the solve
     }
   }
-  __device__ __forceinline__ void chain_store(const Chain& c, float* res) {
+  __device__ __forceinline__ void rows_store(const Rows& w, int n, int e0, float* res) {
 #pragma unroll
-    for (int s = 0; s < B2_PGS_S; s++) { int i = lane + 32 * s; if (i < c.n) { p_row_f()[c.e0 + i] = c.f[s]; res[c.e0 + i] = c.r[s]; } }
+    for (int q = 0; q < 4; q++) { int i = 4 * lane + q; if (i < n) { p_row_f()[e0 + i] = w.f[q]; res[e0 + i] = w.r[q]; } }
   }
-  template <int S>
-  __device__ __forceinline__ void sweep_slot(Chain& c, float& improvement) {
-    int nn = min(32, c.n - 32 * S);
-    for (int ii = 0; ii < nn; ii++) {
-      const int i = 32 * S + ii;
-      float dl = fmaxf(fmaf(-c.r[S], c.ainv[S], c.f[S]), 0.f) - c.f[S];
-      float dlb = __shfl_sync(B2_FULL, dl, ii);
-      if (lane == ii) { improvement -= dl * fmaf(0.5f * dl, c.ad[S], c.r[S]); c.f[S] += dl; }
+  // one 4-row block: C = tile (this lane's rows x block b), already loaded; Cn receives the next block's tile
+  __device__ __forceinline__ void sweep_block(Rows& w, const float* A, int M, int b, int bn, float (&C)[4][4], float (&Cn)[4][4],
+                                              float& improvement) {
+    tile_coeffs(A, M, bn, Cn);                                  // independent of the chain below
+    // block owner's row updates (every lane runs them on its own registers; only lane b's are used)
+    float g0 = fmaf(-w.r[0], w.ainv[0], w.f[0]), g1 = fmaf(-w.r[1], w.ainv[1], w.f[1]);
+    float g2 = fmaf(-w.r[2], w.ainv[2], w.f[2]), g3 = fmaf(-w.r[3], w.ainv[3], w.f[3]);
+    float c10 = C[1][0] * w.ainv[1], c20 = C[2][0] * w.ainv[2], c21 = C[2][1] * w.ainv[2];
+    float c30 = C[3][0] * w.ainv[3], c31 = C[3][1] * w.ainv[3], c32 = C[3][2] * w.ainv[3];
+    float h1 = fmaf(c10, w.f[0], g1), h2 = fmaf(c21, w.f[1], fmaf(c20, w.f[0], g2));
+    float h3 = fmaf(c32, w.f[2], fmaf(c31, w.f[1], fmaf(c30, w.f[0], g3)));
+    float n0 = fmaxf(g0, 0.f), e0 = n0 - w.f[0];
+    float d0 = __shfl_sync(B2_FULL, e0, b);
+    float p1 = fmaf(-c10, n0, h1), n1 = fmaxf(p1, 0.f), e1 = n1 - w.f[1];
+    float d1 = __shfl_sync(B2_FULL, e1, b);
+    float p2 = fmaf(-c21, n1, fmaf(-c20, n0, h2)), n2 = fmaxf(p2, 0.f), e2 = n2 - w.f[2];
+    float d2 = __shfl_sync(B2_FULL, e2, b);
+    float p3 = fmaf(-c32, n2, fmaf(-c31, n1, fmaf(-c30, n0, h3))), n3 = fmaxf(p3, 0.f), e3 = n3 - w.f[3];
+    float d3 = __shfl_sync(B2_FULL, e3, b);
+    // cost change of a row update: -dl (1/2 dl A_ii + residual at the time of the update), residual = (f - p) A_ii
+    float ch = e0 * w.ad[0] * fmaf(0.5f, e0, w.f[0] - g0) + e1 * w.ad[1] * fmaf(0.5f, e1, w.f[1] - p1) +
+               e2 * w.ad[2] * fmaf(0.5f, e2, w.f[2] - p2) + e3 * w.ad[3] * fmaf(0.5f, e3, w.f[3] - p3);
+    const bool own = lane == b;
+    improvement -= own ? ch : 0.f;
+    w.f[0] = own ? n0 : w.f[0]; w.f[1] = own ? n1 : w.f[1]; w.f[2] = own ? n2 : w.f[2]; w.f[3] = own ? n3 : w.f[3];
 #pragma unroll
-      for (int s2 = 0; s2 < B2_PGS_S; s2++) {
-        const int col = lane + 32 * s2;
-        if (col < c.n) c.r[s2] = fmaf(c.A[c.adr[s2]], dlb, c.r[s2]);
-        // A(i+1, col) - A(i, col) in the packed lower triangle: 1 right of the diagonal, i+1 left of it
-        c.adr[s2] += (s2 > S) ? 1 : (s2 < S) ? i + 1 : ((col > i) ? 1 : i + 1);
-      }
+    for (int q = 0; q < 4; q++)
+      w.r[q] = fmaf(C[q][3], d3, fmaf(C[q][2], d2, fmaf(C[q][1], d1, fmaf(C[q][0], d0, w.r[q]))));
+  }
+  __device__ __forceinline__ void sweep_island(Rows& w, int n, const float* A, float& improvement) {
+    const int nb = (n + 3) >> 2; const int M = min(lane, nb - 1);
+    float Ca[4][4], Cb[4][4];
+    tile_coeffs(A, M, 0, Ca);
+#pragma unroll 1
+    for (int b = 0; b < nb; b += 2) {
+      sweep_block(w, A, M, b, min(b + 1, nb - 1), Ca, Cb, improvement);
+      if (b + 1 < nb) sweep_block(w, A, M, b + 1, min(b + 2, nb - 1), Cb, Ca, improvement);
     }
   }
   __device__ void solve_pgs(unsigned long long* counters) {
@@ -862,17 +938,28 @@ struct Engine {
     float* res = p_row_res(); float* red = p_red();
     // residual r = A f + b, and warm-start acceptance: cost(f) = 1/2 f'A f + f'b > 0 -> cold start
     float cost = 0.f;
-    for (int k = wl; k < nisl; k += W) {
-      int n = p_isl_n()[k]; if (!n) continue;
+    for (int k = 0; k < nisl; k++) {
+      int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       int e0 = p_isl_adr()[k]; const float* A = island_A(k); const float* fr = p_row_f() + e0;
-      for (int i = lane; i < n; i += 32) {
-        float s0 = 0.f, s1 = 0.f; int ti = tri(i), j = 0;
-        for (; j + 2 <= i + 1; j += 2) { s0 = fmaf(A[ti + j], fr[j], s0); s1 = fmaf(A[ti + j + 1], fr[j + 1], s1); }
-        for (; j <= i; j++) s0 = fmaf(A[ti + j], fr[j], s0);
-        for (; j < n; j++) s0 = fmaf(A[tri(j) + i], fr[j], s0);
-        float s = s0 + s1, fi = fr[i], b = p_row_b()[e0 + i];
-        cost += fi * (0.5f * s + b);
-        res[e0 + i] = s + b;
+      const int nb = (n + 3) >> 2; const int M = min(lane, nb - 1);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int b = 0; b < nb; b++) {
+        float C[4][4]; tile_coeffs(A, M, b, C);
+        float fb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) fb[u] = (4 * b + u < n) ? fr[4 * b + u] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] = fmaf(C[q][3], fb[3], fmaf(C[q][2], fb[2], fmaf(C[q][1], fb[1], fmaf(C[q][0], fb[0], acc[q]))));
+      }
+      sync();
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        int i = 4 * lane + q;
+        if (i < n) {
+          float fi = fr[i], bi = p_row_b()[e0 + i]; cost += fi * (0.5f * acc[q] + bi); res[e0 + i] = acc[q] + bi;
+          p_row_R()[e0 + i] = 1.0f / A[a_index(i, i)];         // efc_R is folded into A by now: reuse its slot for 1/A_ii
+        }
       }
     }
     cost = warp_sum(cost);
@@ -882,8 +969,9 @@ struct Engine {
 #pragma unroll
     for (int q = 0; q < W; q++) total += red[q];
     if (total > 0.f) {
-      for (int k = wl; k < nisl; k += W) {
+      for (int k = 0; k < nisl; k++) {
         int n = p_isl_n()[k], e0 = p_isl_adr()[k];
+        if (p_isl_warp()[k] != wl) continue;
         for (int i = lane; i < n; i += 32) { p_row_f()[e0 + i] = 0.f; res[e0 + i] = p_row_b()[e0 + i]; }
       }
     }
@@ -891,13 +979,12 @@ struct Engine {
     int it = 0;
     for (; it < iters; it++) {
       float improvement = 0.f;
-      for (int k = wl; k < nisl; k += W) {
-        if (!p_isl_n()[k]) continue;
-        Chain c; chain_load(c, k, res);
-        sweep_slot<0>(c, improvement);
-        if (B2_PGS_S > 1) sweep_slot<(B2_PGS_S > 1 ? 1 : 0)>(c, improvement);
-        if (B2_PGS_S > 2) sweep_slot<(B2_PGS_S > 2 ? 2 : 0)>(c, improvement);
-        chain_store(c, res);
+      for (int k = 0; k < nisl; k++) {
+        int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+        int e0 = p_isl_adr()[k]; const float* A = island_A(k);
+        Rows w; rows_load(w, n, e0, A, res);
+        sweep_island(w, n, A, improvement);
+        rows_store(w, n, e0, res);
       }
       improvement = warp_sum(improvement);
       if (W > 1) {
