@@ -788,18 +788,25 @@ struct Engine {
     int t = tri(i >> 2) + (j >> 2);
     return 16 * t + 4 * ((i & 3) ^ ((t >> 1) & 3)) + (j & 3);
   }
-  // C[k][j] = A(4M + k, 4b + j): one tile, four 128-bit shared loads, transposed on the fly when it lies above the diagonal
+  // tile (this lane's rows x block b): four 128-bit shared loads; the 4x4 coefficients C[k][j] = A(4M + k, 4b + j) are
+  // picked out afterwards (transposed on the fly when the tile lies above the diagonal), so the loads can be issued a
+  // block ahead of their use
+  __device__ __forceinline__ static void tile_raw(const float* A, int M, int b, float4 (&q)[4], bool& lower) {
+    lower = M >= b; const int t = lower ? tri(M) + b : tri(b) + M; const int sw = (t >> 1) & 3;
+    const float4* p = reinterpret_cast<const float4*>(A + 16 * t);
+    q[0] = p[sw]; q[1] = p[1 ^ sw]; q[2] = p[2 ^ sw]; q[3] = p[3 ^ sw];
+  }
+  __device__ __forceinline__ static void tile_sel(const float4 (&q)[4], bool lower, float (&C)[4][4]) {
+    C[0][0] = q[0].x; C[1][1] = q[1].y; C[2][2] = q[2].z; C[3][3] = q[3].w;
+    C[0][1] = lower ? q[0].y : q[1].x; C[1][0] = lower ? q[1].x : q[0].y;
+    C[0][2] = lower ? q[0].z : q[2].x; C[2][0] = lower ? q[2].x : q[0].z;
+    C[0][3] = lower ? q[0].w : q[3].x; C[3][0] = lower ? q[3].x : q[0].w;
+    C[1][2] = lower ? q[1].z : q[2].y; C[2][1] = lower ? q[2].y : q[1].z;
+    C[1][3] = lower ? q[1].w : q[3].y; C[3][1] = lower ? q[3].y : q[1].w;
+    C[2][3] = lower ? q[2].w : q[3].z; C[3][2] = lower ? q[3].z : q[2].w;
+  }
   __device__ __forceinline__ static void tile_coeffs(const float* A, int M, int b, float (&C)[4][4]) {
-    const bool lower = M >= b; const int t = lower ? tri(M) + b : tri(b) + M; const int sw = (t >> 1) & 3;
-    const float4* q = reinterpret_cast<const float4*>(A + 16 * t);
-    float4 q0 = q[sw], q1 = q[1 ^ sw], q2 = q[2 ^ sw], q3 = q[3 ^ sw];
-    C[0][0] = q0.x; C[1][1] = q1.y; C[2][2] = q2.z; C[3][3] = q3.w;
-    C[0][1] = lower ? q0.y : q1.x; C[1][0] = lower ? q1.x : q0.y;
-    C[0][2] = lower ? q0.z : q2.x; C[2][0] = lower ? q2.x : q0.z;
-    C[0][3] = lower ? q0.w : q3.x; C[3][0] = lower ? q3.x : q0.w;
-    C[1][2] = lower ? q1.z : q2.y; C[2][1] = lower ? q2.y : q1.z;
-    C[1][3] = lower ? q1.w : q3.y; C[3][1] = lower ? q3.y : q1.w;
-    C[2][3] = lower ? q2.w : q3.z; C[3][2] = lower ? q3.z : q2.w;
+    float4 q[4]; bool lower; tile_raw(A, M, b, q, lower); tile_sel(q, lower, C);
   }
 
   // ---- A = J M^-1 J' + R per island (mj_projectConstraint), 32 columns at a time, lane = column
@@ -873,64 +880,73 @@ struct Engine {
 
   // ---- PGS (mj_solPGS restated; row order = MuJoCo's within each island, islands are exactly decoupled so each
   // warp of the team sweeps its own islands; the stopping rule uses the improvement summed over all islands, exchanged
-  // through shared memory once per iteration).  Lane L keeps rows 4L..4L+3 of the island (force, residual, 1/A_ii) in
-  // registers.  Rows are swept four at a time: the lane that owns block b updates its four rows in order from its
-  // diagonal tile -- a chain of one FFMA + one FMNMX per row -- the four force changes are broadcast with shuffles that
-  // overlap that chain, and every lane folds them into its residuals with the 4x4 tile (its rows x block b).  This is
-  // the same sequence of scalar row updates as mj_solPGS (same order, same clamps), at a quarter of the shuffles.
+  // through shared memory once per iteration).  Lane L keeps rows 4L..4L+3 of the island in registers.  Rows are swept
+  // four at a time: the lane that owns block b updates its four rows in order -- a chain of one FFMA + one FMNMX per row
+  // -- the four force changes are broadcast with shuffles that overlap that chain, and every lane folds them into its
+  // rows with the 4x4 tile (its rows x block b).  This is the same sequence of scalar row updates as mj_solPGS (same
+  // order, same clamps), at a quarter of the shuffles.  The per-row state is not the residual r_k but
+  //     H_k = f_k - r_k / A_kk + sum_{j<k, same block} (A_kj / A_kk) f_j ,
+  // the unclamped new force of row k before the earlier rows of its block have moved, so the owner's chain starts from
+  // registers: new f_0 = max(H_0, 0), new f_k = max(H_k - sum_{j<k} c_kj new f_j, 0).  A change d of block b moves
+  // H_k -= (1 / A_kk) sum_j A(k, 4b + j) d_j for every other row, and for the owner only through the strict upper
+  // triangle of its diagonal tile (the lower part and the diagonal are already inside H).  Raw tiles are loaded one block
+  // ahead into the other of two register buffers (sweep unrolled by two, no register rotation).
   // mj_solPGS's "restore if the cost went up by more than 1e-10" guard is dropped: for these scalar row updates the cost
   // change is <= 0 in exact arithmetic, the guard only ever fires on round-off.
-  struct Rows { float f[4], r[4], ainv[4], ad[4]; };
+  struct Rows { float f[4], H[4], ainv[4], ad[4], c[6]; };
+  // res[] holds H between sweeps (row_R holds 1/A_ii during the solve)
   __device__ __forceinline__ void rows_load(Rows& w, int n, int e0, const float* A, const float* res) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       int i = 4 * lane + q; bool v = i < n;
-      w.f[q] = v ? p_row_f()[e0 + i] : 0.f; w.r[q] = v ? res[e0 + i] : 0.f;
-      w.ad[q] = v ? A[a_index(i, i)] : 1.f; w.ainv[q] = v ? p_row_R()[e0 + i] : 1.f;      // row_R holds 1/A_ii during the solve
+      w.f[q] = v ? p_row_f()[e0 + i] : 0.f; w.H[q] = v ? res[e0 + i] : 0.f;
+      w.ad[q] = v ? A[a_index(i, i)] : 1.f; w.ainv[q] = v ? p_row_R()[e0 + i] : 1.f;
     }
+    const int i0 = 4 * min(lane, ((n + 3) >> 2) - 1);         // rows past n are zero in A: their c's vanish
+    w.c[0] = A[a_index(i0 + 1, i0)] * w.ainv[1]; w.c[1] = A[a_index(i0 + 2, i0)] * w.ainv[2]; w.c[2] = A[a_index(i0 + 2, i0 + 1)] * w.ainv[2];
+    w.c[3] = A[a_index(i0 + 3, i0)] * w.ainv[3]; w.c[4] = A[a_index(i0 + 3, i0 + 1)] * w.ainv[3]; w.c[5] = A[a_index(i0 + 3, i0 + 2)] * w.ainv[3];
   }
   __device__ __forceinline__ void rows_store(const Rows& w, int n, int e0, float* res) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) { int i = 4 * lane + q; if (i < n) { p_row_f()[e0 + i] = w.f[q]; res[e0 + i] = w.r[q]; } }
+    for (int q = 0; q < 4; q++) { int i = 4 * lane + q; if (i < n) { p_row_f()[e0 + i] = w.f[q]; res[e0 + i] = w.H[q]; } }
   }
-  // one 4-row block: C = tile (this lane's rows x block b), already loaded; Cn receives the next block's tile
-  __device__ __forceinline__ void sweep_block(Rows& w, const float* A, int M, int b, int bn, float (&C)[4][4], float (&Cn)[4][4],
-                                              float& improvement) {
-    tile_coeffs(A, M, bn, Cn);                                  // independent of the chain below
+  __device__ __forceinline__ void sweep_block(Rows& w, const float* A, int M, int b, int bn, const float4 (&qc)[4], bool loc,
+                                              float4 (&qn)[4], bool& lon, float& improvement) {
+    tile_raw(A, M, bn, qn, lon);                                // next block's tile: independent of the chain below
     // block owner's row updates (every lane runs them on its own registers; only lane b's are used)
-    float g0 = fmaf(-w.r[0], w.ainv[0], w.f[0]), g1 = fmaf(-w.r[1], w.ainv[1], w.f[1]);
-    float g2 = fmaf(-w.r[2], w.ainv[2], w.f[2]), g3 = fmaf(-w.r[3], w.ainv[3], w.f[3]);
-    float c10 = C[1][0] * w.ainv[1], c20 = C[2][0] * w.ainv[2], c21 = C[2][1] * w.ainv[2];
-    float c30 = C[3][0] * w.ainv[3], c31 = C[3][1] * w.ainv[3], c32 = C[3][2] * w.ainv[3];
-    float h1 = fmaf(c10, w.f[0], g1), h2 = fmaf(c21, w.f[1], fmaf(c20, w.f[0], g2));
-    float h3 = fmaf(c32, w.f[2], fmaf(c31, w.f[1], fmaf(c30, w.f[0], g3)));
-    float n0 = fmaxf(g0, 0.f), e0 = n0 - w.f[0];
+    float n0 = fmaxf(w.H[0], 0.f), e0 = n0 - w.f[0];
     float d0 = __shfl_sync(B2_FULL, e0, b);
-    float p1 = fmaf(-c10, n0, h1), n1 = fmaxf(p1, 0.f), e1 = n1 - w.f[1];
+    float p1 = fmaf(-w.c[0], n0, w.H[1]), n1 = fmaxf(p1, 0.f), e1 = n1 - w.f[1];
     float d1 = __shfl_sync(B2_FULL, e1, b);
-    float p2 = fmaf(-c21, n1, fmaf(-c20, n0, h2)), n2 = fmaxf(p2, 0.f), e2 = n2 - w.f[2];
+    float p2 = fmaf(-w.c[2], n1, fmaf(-w.c[1], n0, w.H[2])), n2 = fmaxf(p2, 0.f), e2 = n2 - w.f[2];
     float d2 = __shfl_sync(B2_FULL, e2, b);
-    float p3 = fmaf(-c32, n2, fmaf(-c31, n1, fmaf(-c30, n0, h3))), n3 = fmaxf(p3, 0.f), e3 = n3 - w.f[3];
+    float p3 = fmaf(-w.c[5], n2, fmaf(-w.c[4], n1, fmaf(-w.c[3], n0, w.H[3]))), n3 = fmaxf(p3, 0.f), e3 = n3 - w.f[3];
     float d3 = __shfl_sync(B2_FULL, e3, b);
-    // cost change of a row update: -dl (1/2 dl A_ii + residual at the time of the update), residual = (f - p) A_ii
-    float ch = e0 * w.ad[0] * fmaf(0.5f, e0, w.f[0] - g0) + e1 * w.ad[1] * fmaf(0.5f, e1, w.f[1] - p1) +
-               e2 * w.ad[2] * fmaf(0.5f, e2, w.f[2] - p2) + e3 * w.ad[3] * fmaf(0.5f, e3, w.f[3] - p3);
+    float C[4][4]; tile_sel(qc, loc, C);
     const bool own = lane == b;
+    // cost change of a row update: -dl (1/2 dl A_ii + residual at the time of the update), residual = (f - p) A_ii
+    float ch = e0 * w.ad[0] * fmaf(0.5f, e0, w.f[0] - w.H[0]) + e1 * w.ad[1] * fmaf(0.5f, e1, w.f[1] - p1) +
+               e2 * w.ad[2] * fmaf(0.5f, e2, w.f[2] - p2) + e3 * w.ad[3] * fmaf(0.5f, e3, w.f[3] - p3);
     improvement -= own ? ch : 0.f;
     w.f[0] = own ? n0 : w.f[0]; w.f[1] = own ? n1 : w.f[1]; w.f[2] = own ? n2 : w.f[2]; w.f[3] = own ? n3 : w.f[3];
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      w.r[q] = fmaf(C[q][3], d3, fmaf(C[q][2], d2, fmaf(C[q][1], d1, fmaf(C[q][0], d0, w.r[q]))));
+    float s0 = fmaf(C[0][3], d3, fmaf(C[0][2], d2, fmaf(C[0][1], d1, own ? 0.f : C[0][0] * d0)));
+    float s1 = fmaf(C[1][3], d3, fmaf(C[1][2], d2, own ? 0.f : fmaf(C[1][1], d1, C[1][0] * d0)));
+    float s2 = fmaf(C[2][3], d3, own ? 0.f : fmaf(C[2][2], d2, fmaf(C[2][1], d1, C[2][0] * d0)));
+    float s3 = own ? 0.f : fmaf(C[3][3], d3, fmaf(C[3][2], d2, fmaf(C[3][1], d1, C[3][0] * d0)));
+    w.H[0] = fmaf(-w.ainv[0], s0, w.H[0]); w.H[1] = fmaf(-w.ainv[1], s1, w.H[1]);
+    w.H[2] = fmaf(-w.ainv[2], s2, w.H[2]); w.H[3] = fmaf(-w.ainv[3], s3, w.H[3]);
   }
   __device__ __forceinline__ void sweep_island(Rows& w, int n, const float* A, float& improvement) {
     const int nb = (n + 3) >> 2; const int M = min(lane, nb - 1);
-    float Ca[4][4], Cb[4][4];
-    tile_coeffs(A, M, 0, Ca);
+    float4 qa[4], qb[4]; bool la, lb;
+    tile_raw(A, M, 0, qa, la);
+    const int nb2 = nb & ~1;
 #pragma unroll 1
-    for (int b = 0; b < nb; b += 2) {
-      sweep_block(w, A, M, b, min(b + 1, nb - 1), Ca, Cb, improvement);
-      if (b + 1 < nb) sweep_block(w, A, M, b + 1, min(b + 2, nb - 1), Cb, Ca, improvement);
+    for (int b = 0; b < nb2; b += 2) {
+      sweep_block(w, A, M, b, b + 1, qa, la, qb, lb, improvement);
+      sweep_block(w, A, M, b + 1, min(b + 2, nb - 1), qb, lb, qa, la, improvement);
     }
+    if (nb & 1) sweep_block(w, A, M, nb - 1, nb - 1, qa, la, qb, lb, improvement);
   }
   __device__ void solve_pgs(unsigned long long* counters) {
     int nisl = dim(DD_nisland), iters = dim(DD_iterations);
@@ -957,8 +973,13 @@ struct Engine {
       for (int q = 0; q < 4; q++) {
         int i = 4 * lane + q;
         if (i < n) {
-          float fi = fr[i], bi = p_row_b()[e0 + i]; cost += fi * (0.5f * acc[q] + bi); res[e0 + i] = acc[q] + bi;
-          p_row_R()[e0 + i] = 1.0f / A[a_index(i, i)];         // efc_R is folded into A by now: reuse its slot for 1/A_ii
+          float fi = fr[i], bi = p_row_b()[e0 + i]; cost += fi * (0.5f * acc[q] + bi);
+          float ainv = 1.0f / A[a_index(i, i)];
+          p_row_R()[e0 + i] = ainv;                             // efc_R is folded into A by now: reuse its slot for 1/A_ii
+          // H_k = f_k - r_k / A_kk + sum_{j<k in block} (A_kj / A_kk) f_j
+          float hk = fmaf(-(acc[q] + bi), ainv, fi);
+          for (int u = 0; u < q; u++) hk = fmaf(A[a_index(i, i - q + u)] * ainv, fr[i - q + u], hk);
+          res[e0 + i] = hk;
         }
       }
     }
@@ -972,7 +993,7 @@ struct Engine {
       for (int k = 0; k < nisl; k++) {
         int n = p_isl_n()[k], e0 = p_isl_adr()[k];
         if (p_isl_warp()[k] != wl) continue;
-        for (int i = lane; i < n; i += 32) { p_row_f()[e0 + i] = 0.f; res[e0 + i] = p_row_b()[e0 + i]; }
+        for (int i = lane; i < n; i += 32) { p_row_f()[e0 + i] = 0.f; res[e0 + i] = -p_row_b()[e0 + i] * p_row_R()[e0 + i]; }   // f = 0: H = -b / A_ii
       }
     }
     sync();
