@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libb2env.so")
+_SO = os.environ.get("B2_LIB_PATH", os.path.join(_HERE, "libb2env.so"))      # override: A/B builds in profiling runs
 _LIB = None
 
 SYMBOLS = ["b2_model_create", "b2_model_destroy", "b2_batch_create", "b2_batch_destroy", "b2_dims", "b2_reset",

@@ -44,7 +44,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN> E(P, B, B.model_floats + team * B.ws_floats, team);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -149,7 +149,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32;
+  static constexpr bool PGS_HOIST = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}

@@ -53,7 +53,7 @@ extern __shared__ __align__(128) float b2_smem[];
 
 #define B2_WS_FLOAT_FIELDS(X) X(qpos) X(qvel) X(warm) X(ctrl) X(qapp) X(xpos) X(xmat) X(cdof) X(rootcom) \
   X(xquat) X(xipos) X(cvel) X(cacc) X(cinert) X(M) X(LD) X(invD) X(qfs) X(qas) X(qfc) X(qacc) X(tmp) X(con) \
-  X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc)
+  X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc) X(LD2) X(invD2)
 #define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_warp) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
 
 struct WsOff {
@@ -91,6 +91,7 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   bool rk4 = dim[DD_integrator] == 1;
   t.rk_q0 = take(rk4 ? nq : 0); t.rk_v0 = take(rk4 ? nv : 0); t.rk_sv = take(rk4 ? nv : 0); t.rk_sa = take(rk4 ? nv : 0);
   t.xfrc = take(8);
+  t.LD2 = take(rk4 ? 0 : nM); t.invD2 = take(rk4 ? 0 : nv);      // factor of M + h D (Euler), built beside the factor of M
   t.arena = take(arena_floats);
   if (o) *o = t;
   return (off + 31) & ~31;
@@ -134,7 +135,9 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // One env is stepped by a team of W warps (W = 1: one warp per env).  Warp-synchronous phases (tree passes, row
 // compaction) run on one warp of the team; the parallel phases (J fill, A build, PGS sweeps) split islands / rows
 // over the team's warps; team_sync() is a named barrier private to the team.
-template <int W>
+// HOIST: a warp sweeping a single island keeps its PGS rows in registers across iterations; COOPMIN: islands with more
+// rows than this are built (A = J M^-1 J') by the whole team.  Both are per-task tuning knobs (A/B-measured on B200).
+template <int W, bool HOIST = true, int COOPMIN = 32>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -385,10 +388,10 @@ struct Engine {
   // one step per eliminated dof (leaves first); its rank-1 update is a list of independent (tgt, a, b) address
   // triples, one per lane; the division by D is deferred to one parallel pass, so a step costs one warp barrier and
   // three shared-memory round trips.
-  __device__ __forceinline__ void factor(float hdamp) {
+  __device__ __forceinline__ void factor(float hdamp, bool second) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth);
     const int* fstep = I(DI_fac_step); const int* fops = I(DI_fac_ops); const float* damp = F(DF_dof_damping);
-    float* LD = p_LD(); const float* M = p_M(); float* invD = p_invD();
+    float* LD = second ? p_LD2() : p_LD(); const float* M = p_M(); float* invD = second ? p_invD2() : p_invD();
     int nM = dim(DD_nM), nv = dim(DD_nv), nstep = dim(DD_nfacstep);
 #pragma unroll 1
     for (int k = lane; k < nM; k += 32) LD[k] = M[k];
@@ -424,10 +427,10 @@ struct Engine {
   // ---- x <- M^-1 x with the factor above; level-synchronous over dof depth (mj_solveLD).
   // backward (L^-T): every dof gathers from its descendants, deepest level first; forward (D^-1 then L^-1): a dof of
   // level l has exactly l ancestors, so the trip count is uniform across the level.
-  __device__ __forceinline__ void solve(float* x) {
+  __device__ __forceinline__ void solve(float* x, bool second) {
     const int* mcol = I(DI_Mcol); const int* dladr = I(DI_dlevel_adr);
     const int* bwp = I(DI_bw_pack); const int* fwp = I(DI_fw_pack); const int* dpack = I(DI_desc_pack);
-    const float* LD = p_LD(); const float* invD = p_invD();
+    const float* LD = second ? p_LD2() : p_LD(); const float* invD = second ? p_invD2() : p_invD();
     int maxd = dim(DD_maxdofdepth);
 #pragma unroll 1
     for (int l = maxd - 1; l >= 0; l--) {
@@ -809,71 +812,103 @@ struct Engine {
     float4 q[4]; bool lower; tile_raw(A, M, b, q, lower); tile_sel(q, lower, C);
   }
 
-  // ---- A = J M^-1 J' + R per island (mj_projectConstraint), 32 columns at a time, lane = column
-  __device__ void build_A() {
+  // ---- A = J M^-1 J' + R per island (mj_projectConstraint), 32 columns at a time, lane = column.
+  // Phase 1 of a column block: x_j = M^-1 J_j' for the 32 columns (per-lane sparse solves on a lane-contiguous scratch);
+  // phase 2: A(i, j) = J_i . x_j for all rows i >= j0, four rows at a time sharing the loads of the column.
+  // Islands with more than 32 rows are built by the whole team: one warp runs phase 1, all warps split the row groups of
+  // phase 2 (two team barriers per column block); small islands are built by the warp they are assigned to.
+  __device__ __forceinline__ void build_A_solve(int k, int j0, float* scratch) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum);
     const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
     const float* LDp = p_LD();
-    int nisl = dim(DD_nisland);
-    // island k is built by the warp it was assigned to; its column scratch (32 floats per dof) sits at 32 * dofadr
-    for (int k = 0; k < nisl; k++) {
-      int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
-      int d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
-      float* scratch = scratch_base() + 32 * d0;
-      const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k);
-      { float4* Az = reinterpret_cast<float4*>(A); int nz = a_floats(n) >> 2; for (int i = lane; i < nz; i += 32) Az[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      sync();
-      for (int j0 = 0; j0 < n; j0 += 32) {
-        int j = j0 + lane; bool valid = j < n;
-        float* x = scratch + lane;   // column, stride 32: lane-contiguous, conflict-free
-        for (int c = 0; c < nd; c++) x[32 * c] = valid ? J[j * ldj + c] : 0.f;
-        // x <- L^-T x (gather from descendants, highest dof first), then x <- L^-1 D^-1 x (gather from ancestors):
-        // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent
-        for (int jj = nd - 1; jj >= 0; jj--) {
-          int dn = dnum[d0 + jj]; const int* dp = dpack + dadr[d0 + jj];
-          float s0 = x[32 * jj], s1 = 0.f; int q = 0;
-          for (; q + 2 <= dn; q += 2) {
-            int p0 = dp[q], p1 = dp[q + 1];
-            s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * ((p1 & 0xffff) - d0)], s1);
-          }
-          if (q < dn) { int p0 = dp[q]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
-          x[32 * jj] = s0 + s1;
-        }
-        for (int i = 0; i < nd; i++) {
-          int a = madr[d0 + i], dn = ddepth[d0 + i];
-          float s0 = x[32 * i] * p_invD()[d0 + i], s1 = 0.f; int m = 1;
-          for (; m + 1 <= dn; m += 2) {
-            s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0); s1 = fmaf(-LDp[a + m + 1], x[32 * (mcol[a + m + 1] - d0)], s1);
-          }
-          if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0);
-          x[32 * i] = s0 + s1;
-        }
-        // lower triangle: A[i][j] = J_i . x for i >= j; four rows at a time share the loads of the column
-        for (int i = j0; i < n; i += 4) {
-          const float* J0 = J + i * ldj; const float* J1 = J + min(i + 1, n - 1) * ldj;
-          const float* J2 = J + min(i + 2, n - 1) * ldj; const float* J3 = J + min(i + 3, n - 1) * ldj;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 2
-          for (int c = 0; c < nd; c++) {
-            float xc = x[32 * c];
-            s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
-          }
-          if (valid) {
-            float sv[4] = {s0, s1, s2, s3};
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              int ii = i + u;
-              if (ii < n && ii >= j) {
-                float v = sv[u] + (ii == j ? p_row_R()[e0 + ii] : 0.f);
-                A[a_index(ii, j)] = v;
-                if ((ii >> 2) == (j >> 2) && ii != j) A[a_index(j, ii)] = v;      // diagonal tiles are stored in full
-              }
-            }
-          }
-        }
-        sync();
+    int n = p_isl_n()[k], d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k];
+    const float* J = p_arena() + p_isl_J()[k];
+    int j = j0 + lane; bool valid = j < n;
+    float* x = scratch + lane;   // column, stride 32: lane-contiguous, conflict-free
+    for (int c = 0; c < nd; c++) x[32 * c] = valid ? J[j * ldj + c] : 0.f;
+    // x <- L^-T x (gather from descendants, highest dof first), then x <- L^-1 D^-1 x (gather from ancestors):
+    // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent
+    for (int jj = nd - 1; jj >= 0; jj--) {
+      int dn = dnum[d0 + jj]; const int* dp = dpack + dadr[d0 + jj];
+      float s0 = x[32 * jj], s1 = 0.f; int q = 0;
+      for (; q + 2 <= dn; q += 2) {
+        int p0 = dp[q], p1 = dp[q + 1];
+        s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * ((p1 & 0xffff) - d0)], s1);
       }
+      if (q < dn) { int p0 = dp[q]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
+      x[32 * jj] = s0 + s1;
+    }
+    for (int i = 0; i < nd; i++) {
+      int a = madr[d0 + i], dn = ddepth[d0 + i];
+      float s0 = x[32 * i] * p_invD()[d0 + i], s1 = 0.f; int m = 1;
+      for (; m + 1 <= dn; m += 2) {
+        s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0); s1 = fmaf(-LDp[a + m + 1], x[32 * (mcol[a + m + 1] - d0)], s1);
+      }
+      if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0);
+      x[32 * i] = s0 + s1;
+    }
+  }
+  // rows i = j0 + 4 * (g0 + gs * t), t = 0, 1, ...
+  __device__ __forceinline__ void build_A_dots(int k, int j0, const float* scratch, int g0, int gs) {
+    const int* inum = I(DI_island_dofnum);
+    int n = p_isl_n()[k], nd = inum[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
+    const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k);
+    int j = j0 + lane; bool valid = j < n;
+    const float* x = scratch + lane;
+    for (int i = j0 + 4 * g0; i < n; i += 4 * gs) {
+      const float* J0 = J + i * ldj; const float* J1 = J + min(i + 1, n - 1) * ldj;
+      const float* J2 = J + min(i + 2, n - 1) * ldj; const float* J3 = J + min(i + 3, n - 1) * ldj;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 2
+      for (int c = 0; c < nd; c++) {
+        float xc = x[32 * c];
+        s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
+      }
+      if (valid) {
+        float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          int ii = i + u;
+          if (ii < n && ii >= j) {
+            float v = sv[u] + (ii == j ? p_row_R()[e0 + ii] : 0.f);
+            A[a_index(ii, j)] = v;
+            if ((ii >> 2) == (j >> 2) && ii != j) A[a_index(j, ii)] = v;      // diagonal tiles are stored in full
+          }
+        }
+      }
+    }
+  }
+  __device__ void build_A() {
+    const int* iadr = I(DI_island_dofadr);
+    int nisl = dim(DD_nisland);
+    // zero the tiles (rows / columns past n stay zero)
+    for (int k = 0; k < nisl; k++) {
+      int n = p_isl_n()[k]; if (!n) continue;
+      bool coop = W > 1 && n > COOPMIN;
+      if (!coop && p_isl_warp()[k] != wl) continue;
+      float4* Az = reinterpret_cast<float4*>(island_A(k)); int nz = a_floats(n) >> 2;
+      for (int i = coop ? tl : lane; i < nz; i += coop ? TEAM : 32) Az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    team_sync();
+    if (W > 1) {
+      for (int k = 0; k < nisl; k++) {
+        int n = p_isl_n()[k]; if (n <= COOPMIN) continue;
+        float* scratch = scratch_base() + 32 * iadr[k];
+        int turn = p_isl_warp()[k];
+        for (int j0 = 0; j0 < n; j0 += 32) {
+          if (wl == turn) build_A_solve(k, j0, scratch);
+          team_sync();
+          build_A_dots(k, j0, scratch, wl, W);
+          team_sync();
+          turn = (turn + 1 == W) ? 0 : turn + 1;
+        }
+      }
+    }
+    for (int k = 0; k < nisl; k++) {
+      int n = p_isl_n()[k]; if (!n || (W > 1 && n > COOPMIN) || p_isl_warp()[k] != wl) continue;
+      float* scratch = scratch_base() + 32 * iadr[k];
+      for (int j0 = 0; j0 < n; j0 += 32) { build_A_solve(k, j0, scratch); sync(); build_A_dots(k, j0, scratch, 0, 1); sync(); }
     }
     team_sync();
   }
@@ -997,15 +1032,24 @@ struct Engine {
       }
     }
     sync();
+    // a warp that sweeps exactly one island keeps its rows in registers across the iterations
+    int mine = 0, kone = -1;
+    for (int k = 0; k < nisl; k++) if (p_isl_n()[k] && p_isl_warp()[k] == wl) { mine++; kone = k; }
+    const bool single = HOIST && mine == 1;
+    Rows w1; int n1 = 0, e1 = 0; const float* A1 = nullptr;
+    if (single) { n1 = p_isl_n()[kone]; e1 = p_isl_adr()[kone]; A1 = island_A(kone); rows_load(w1, n1, e1, A1, res); }
     int it = 0;
     for (; it < iters; it++) {
       float improvement = 0.f;
-      for (int k = 0; k < nisl; k++) {
-        int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
-        int e0 = p_isl_adr()[k]; const float* A = island_A(k);
-        Rows w; rows_load(w, n, e0, A, res);
-        sweep_island(w, n, A, improvement);
-        rows_store(w, n, e0, res);
+      if (single) sweep_island(w1, n1, A1, improvement);
+      else {
+        for (int k = 0; k < nisl; k++) {
+          int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+          int e0 = p_isl_adr()[k]; const float* A = island_A(k);
+          Rows w; rows_load(w, n, e0, A, res);
+          sweep_island(w, n, A, improvement);
+          rows_store(w, n, e0, res);
+        }
       }
       improvement = warp_sum(improvement);
       if (W > 1) {
@@ -1018,6 +1062,7 @@ struct Engine {
       }
       if (improvement * scale < tol) { it++; break; }
     }
+    if (single) rows_store(w1, n1, e1, res);
     if (tl == 0) { p_misc()[MISC_ITERS] = it; if (counters) atomicAdd(&counters[CTR_SOLVER_ITERS], (unsigned long long)it); }
     team_sync();
   }
@@ -1111,6 +1156,12 @@ struct Engine {
           if (pass == 0) {
             if (wl == 0) { vel_pass(); backward_pass(); mass_and_smooth(); }
             if (wl == (1 % W)) { collision(counters); make_rows(counters); }
+            if (W == 3 && npass == 3) {
+              // mj_Euler's factor of M + h D does not depend on the constraint solve: the team's third warp builds it
+              // as soon as M exists (a two-warp named barrier hands M over), beside warp 0's factor of M
+              if (wl == 0 || wl == 2) asm volatile("bar.sync %0, 64;" ::"r"(barid + 6) : "memory");
+              if (wl == 2) factor(h, true);
+            }
           } else if (pass == 1) {
             if (p_misc()[MISC_NEFC] > 0) { fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11); }
             else if (tl == 0) p_misc()[MISC_ITERS] = 0;
@@ -1119,10 +1170,11 @@ struct Engine {
             if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
           }
           if (wl == 0) {
-            if (pass != 1) factor(pass == 0 ? 0.f : h);
+            if (pass == 0) factor(0.f, false);
+            else if (pass == 2 && W != 3) factor(h, true);
             float* x = b2_smem + wb + (pass == 0 ? B.off.qas : pass == 1 ? B.off.qacc : B.off.tmp);
             if (pass == 0) { for (int d = lane; d < nv; d += 32) x[d] = p_qfs()[d]; sync(); }
-            solve(x);
+            solve(x, pass == 2);
             if (pass == 1) { for (int d = lane; d < nv; d += 32) x[d] += p_qas()[d]; sync(); }
           }
           team_sync(); B2_TICK(1 + pass);
