@@ -23,6 +23,7 @@ struct B2Model {
 };
 struct B2Batch {
   B2Model* m; int n_envs, W; TaskParams tp; BatchView v; size_t smem;
+  DevModel dm;        // the model as this batch's kernels see it (pair tables staged or cold)
   float* epstat;      // [N][4] episodes, return_sum, length_sum, (spare)
   double* d_stats;
   float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
@@ -40,11 +41,11 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
               int mode, float* epstat, const float* inject) {
   const int team = threadIdx.x / (32 * W);
   uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
-  stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints), bar);
+  stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints_staged), bar);
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS> E(P, B, B.model_floats + team * B.ws_floats, team);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -115,7 +116,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   // ---- optional exports of the last forward pass
   if (B.c_ncon) {
     int ncon = E.p_misc()[MISC_NCON];
-    const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+    const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
     if (tl == 0) B.c_ncon[env] = ncon;
     for (int c = tl; c < ncon && c < B.c_cap; c += TEAM) {
       int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
@@ -149,8 +150,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32;
-  static constexpr bool PGS_HOIST = true;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80;
+  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -185,7 +186,7 @@ static int launch_W(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   static thread_local size_t configured = 0;
   if (configured < b->smem) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)); configured = b->smem; }
   int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
-  kern<<<grid, 32 * W * E, b->smem, s>>>(b->m->dm, b->v, b->tp, mode, b->epstat, inject);
+  kern<<<grid, 32 * W * E, b->smem, s>>>(b->dm, b->v, b->tp, mode, b->epstat, inject);
   g_launches++;
   CK(cudaGetLastError());
   return B2_OK;
@@ -246,7 +247,7 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
   CK(cudaMalloc(&m->d_ints, sizeof(int) * n_ints)); CK(cudaMalloc(&m->d_flts, sizeof(float) * n_flts));
   CK(cudaMemcpy(m->d_ints, ints, sizeof(int) * n_ints, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(m->d_flts, f32.data(), sizeof(float) * n_flts, cudaMemcpyHostToDevice));
-  dm.ints = m->d_ints; dm.flts = m->d_flts; dm.n_ints = n_ints; dm.n_flts = n_flts;
+  dm.ints = m->d_ints; dm.flts = m->d_flts; dm.n_ints = n_ints; dm.n_flts = n_flts; dm.n_ints_staged = n_ints;
   *out = m;
   return B2_OK;
 }
@@ -259,11 +260,11 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int keep_frames = 0, xfrc_body = -1; b->ninj = 1;
+  int keep_frames = 0, xfrc_body = -1, arena_rows = 80; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -284,14 +285,21 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
-  int raw_need = 2 * r4(dim[DD_npair]) + 10 * dim[DD_maxraw];
+  // narrow-phase capacities: active pairs after the cull, raw contact slots handed out to them
+  v.act_cap = r4(dim[DD_npair] < 128 ? dim[DD_npair] : 128); if (v.act_cap < 4) v.act_cap = 4;
+  v.raw_cap = dim[DD_maxraw] < 384 ? dim[DD_maxraw] : 384; if (v.raw_cap < 8) v.raw_cap = 8;
+  int raw_need = 3 * v.act_cap + 10 * v.raw_cap;
+  b->dm = m->dm;
+  if (cold) b->dm.n_ints_staged = m->h_ints[3];       // header word 3: where the pair tables start
   int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim, keep_frames)) ? 0 : 32 * dim[DD_nv];
-  (void)maxspan;
-  int arena = (o_arena > 0 ? o_arena : 4608) + scratch;
+  // default arena: J (rows x widest island) + tiled A for the task's typical row count, plus the A-build scratch
+  int typ = arena_rows < B2_ISLAND_ROWS ? arena_rows : B2_ISLAND_ROWS;
+  int arena_default = r4(typ * (maxspan | 1)) + 16 * ((((typ + 3) >> 2) * (((typ + 3) >> 2) + 1)) >> 1) + 64;
+  int arena = (o_arena > 0 ? o_arena : arena_default) + scratch;
   if (arena < raw_need) arena = raw_need;
   v.arena_floats = r4(arena);
   v.ws_floats = ws_layout(dim, v.con_cap, v.row_cap, v.arena_floats, b->nti, b->ntf, &v.off);
-  v.model_floats = model_smem_floats(m->dm.n_ints, m->dm.n_flts);
+  v.model_floats = model_smem_floats(b->dm.n_ints_staged, b->dm.n_flts);
   const int smem_max = 227 * 1024;
   int epb = (smem_max - v.model_floats * 4 - 16) / (v.ws_floats * 4);
   if (epb > (b->W == 1 ? 8 : 6)) epb = (b->W == 1 ? 8 : 6);

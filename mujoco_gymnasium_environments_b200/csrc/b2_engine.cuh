@@ -35,6 +35,7 @@ namespace b2 {
 struct DevModel {
   const int* ints; const float* flts;
   int n_ints, n_flts;
+  int n_ints_staged;               // ints copied into shared memory (all of them, or up to the pair tables when cold)
   int ioff[B2DEV_N_INT_FIELDS];
   int foff[B2DEV_N_FLT_FIELDS];
   int dim[DD_COUNT];
@@ -65,7 +66,7 @@ enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_U
 
 __host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 // model tables occupy the first model_floats of shared memory (ints first, then floats), padded to 32 floats
-__host__ __device__ inline int model_smem_floats(int n_ints, int n_flts) { return (r4(n_ints) + r4(n_flts) + 31) & ~31; }
+__host__ __device__ inline int model_smem_floats(int n_ints_staged, int n_flts) { return (r4(n_ints_staged) + r4(n_flts) + 31) & ~31; }
 
 // per-warp carve-up in floats; returns the slice size (multiple of 32 floats)
 __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int arena_floats, int nti, int ntf, WsOff* o) {
@@ -111,6 +112,7 @@ struct BatchView {
   unsigned long long* phase_cycles;                  // [16] per-phase clock64 sums (only with -DB2_PHASE_TIMING)
   unsigned long long seed;
   int arena_floats, con_cap, row_cap;
+  int act_cap, raw_cap;                              // narrow phase: active-pair list entries, raw contact slots
   int nsub;                                          // physics sub-steps for MODE_PHYS
   int env_offset;                                    // global index of env 0 (multi-GPU sharding keeps RNG streams fixed)
   int envs_per_block; int ws_floats; int model_floats;   // shared-memory slices, in floats
@@ -137,7 +139,7 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // over the team's warps; team_sync() is a named barrier private to the team.
 // HOIST: a warp sweeping a single island keeps its PGS rows in registers across iterations; COOPMIN: islands with more
 // rows than this are built (A = J M^-1 J') by the whole team.  Both are per-task tuning knobs (A/B-measured on B200).
-template <int W, bool HOIST = true, int COOPMIN = 32>
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -163,7 +165,9 @@ struct Engine {
   B2_WS_INT_FIELDS(X)
 #undef X
   __device__ __forceinline__ const int* I(int f) const { return (const int*)b2_smem + P.ioff[f]; }
-  __device__ __forceinline__ const float* F(int f) const { return b2_smem + r4(P.n_ints) + P.foff[f]; }
+  __device__ __forceinline__ const float* F(int f) const { return b2_smem + r4(P.n_ints_staged) + P.foff[f]; }
+  // candidate-pair tables: shared memory, or global memory (read-only, L2-resident) when the task leaves them cold
+  __device__ __forceinline__ const int* PI(int f) const { return COLD ? P.ints + P.ioff[f] : (const int*)b2_smem + P.ioff[f]; }
   __device__ __forceinline__ int dim(int k) const { return P.dim[k]; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int conCap() const { return B.con_cap; }
@@ -477,17 +481,19 @@ struct Engine {
       for (int c = 0; c < 3; c++) mat[3 * r + c] = xm[3 * r] * lm[c] + xm[3 * r + 1] * lm[3 + c] + xm[3 * r + 2] * lm[6 + c];
   }
   // candidate pairs are culled first (bounding spheres / plane distance) and the survivors compacted, in pair order,
-  // into an active list, so the narrow phase runs one *surviving* pair per lane
+  // into an active list, so the narrow phase runs one *surviving* pair per lane.  Raw contact slots are handed out to the
+  // active pairs by a prefix sum of their static maxima, so the arena only holds what a step can actually produce
+  // (capacities act_cap / raw_cap; what does not fit is counted as dropped).
   __device__ void collision(unsigned long long* counters) {
-    const int* pc1 = I(DI_pair_cg1); const int* pc2 = I(DI_pair_cg2); const int* pprm = I(DI_pair_prm);
-    const int* praw = I(DI_pair_rawadr); const int* pmax = I(DI_pair_maxcon); const int* cgtype = I(DI_cg_type);
+    const int* pc1 = PI(DI_pair_cg1); const int* pc2 = PI(DI_pair_cg2); const int* pprm = PI(DI_pair_prm);
+    const int* pmax = PI(DI_pair_maxcon); const int* cgtype = I(DI_cg_type);
     const int* cgbody = I(DI_cg_body); const float* cgpos = F(DF_cg_pos); const float* cgmat = F(DF_cg_mat);
     const float* cgsize = F(DF_cg_size); const float* cgrb = F(DF_cg_rbound); const float* prm = F(DF_prm);
-    int npair = dim(DD_npair);
-    // arena: [count per active pair | active pair ids | 10 floats per raw contact slot]
-    int* rcount = (int*)p_arena(); int* alist = rcount + r4(npair); float* rdata = p_arena() + 2 * r4(npair);
+    const int npair = dim(DD_npair), acap = B.act_cap, rcap = B.raw_cap;
+    // arena: [active pair ids | raw slot of each | contact count of each | 10 floats per raw contact slot]
+    int* alist = (int*)p_arena(); int* araw = alist + acap; int* rcount = araw + acap; float* rdata = p_arena() + 3 * acap;
     const unsigned lt = (1u << lane) - 1u;
-    int nact = 0;
+    int nact = 0, dropped = 0;
     for (int p0 = 0; p0 < npair; p0 += 32) {
       int p = p0 + lane; bool keep = false;
       if (p < npair) {
@@ -502,20 +508,37 @@ struct Engine {
         } else { float bd = cgrb[g1] + cgrb[g2] + margin; keep = !(dot(d, d) > bd * bd); }
       }
       unsigned m = __ballot_sync(B2_FULL, keep);
-      if (keep) alist[nact + __popc(m & lt)] = p;
-      nact += __popc(m);
+      int slot = nact + __popc(m & lt);
+      if (keep) { if (slot < acap) alist[slot] = p; else dropped += pmax[p]; }
+      nact = min(nact + __popc(m), acap);
+    }
+    sync();
+    // raw slots: exclusive prefix sum of the active pairs' maxima; a pair whose slots do not all fit gets none
+    int rbase = 0;
+    for (int k0 = 0; k0 < nact; k0 += 32) {
+      int k = k0 + lane; int n = (k < nact) ? pmax[alist[k]] : 0;
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(B2_FULL, incl, o); if (lane >= o) incl += v; }
+      int start = rbase + incl - n;
+      if (k < nact) { if (start + n <= rcap) araw[k] = start; else { araw[k] = -1; dropped += n; } }
+      rbase += __shfl_sync(B2_FULL, incl, 31);
     }
     sync();
     for (int k = lane; k < nact; k += 32) {
       int p = alist[k], g1 = pc1[p], g2 = pc2[p]; float margin = prm[B2DEV_PRM_STRIDE * pprm[p]];
-      V3 p1, p2; float m1[9], m2[9];
-      geom_pose(g1, p1, m1); geom_pose(g2, p2, m2);
-      rcount[k] = collide_pair(cgtype[g1], cgtype[g2], p1, m1, cgsize + 3 * g1, p2, m2, cgsize + 3 * g2, margin,
-                               rdata + B2_RAW * praw[p], pmax[p]);
+      int n = 0;
+      if (araw[k] >= 0) {
+        V3 p1, p2; float m1[9], m2[9];
+        geom_pose(g1, p1, m1); geom_pose(g2, p2, m2);
+        n = collide_pair(cgtype[g1], cgtype[g2], p1, m1, cgsize + 3 * g1, p2, m2, cgsize + 3 * g2, margin,
+                         rdata + B2_RAW * araw[k], pmax[p]);
+      }
+      rcount[k] = n;
     }
     sync();
     // ordered compaction (active list is in pair order == MuJoCo contact order)
-    int base = 0, dropped = 0;
+    int base = 0;
     for (int k0 = 0; k0 < nact; k0 += 32) {
       int k = k0 + lane; int n = (k < nact) ? rcount[k] : 0; int p = (k < nact) ? alist[k] : 0;
       int incl = n;
@@ -525,7 +548,7 @@ struct Engine {
       for (int q = 0; q < n; q++) {
         int c = start + q;
         if (c >= conCap()) { dropped++; continue; }
-        const float* src = rdata + B2_RAW * (praw[p] + q);
+        const float* src = rdata + B2_RAW * (araw[k] + q);
         float* dst = p_con() + B2_CON_STRIDE * c;
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         // frame: normal, then orthogonalised tangent hint (mju_makeFrame)
@@ -549,7 +572,7 @@ struct Engine {
   __device__ __forceinline__ int contact_island(int c) const {
     const int* bisl = I(DI_body_island); const int* cgbody = I(DI_cg_body);
     int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]);
-    int i2 = bisl[cgbody[I(DI_pair_cg2)[p]]], i1 = bisl[cgbody[I(DI_pair_cg1)[p]]];
+    int i2 = bisl[cgbody[PI(DI_pair_cg2)[p]]], i1 = bisl[cgbody[PI(DI_pair_cg1)[p]]];
     return i2 >= 0 ? i2 : i1;
   }
 
@@ -666,7 +689,7 @@ struct Engine {
   __device__ void fill_rows() {
     const int* limj = I(DI_lim_jnt); const int* jd = I(DI_jnt_dofadr); const int* jq = I(DI_jnt_qposadr);
     const int* disl = I(DI_dof_island); const int* cgbody = I(DI_cg_body);
-    const int* pc1 = I(DI_pair_cg1); const int* pc2 = I(DI_pair_cg2); const int* pprm = I(DI_pair_prm);
+    const int* pc1 = PI(DI_pair_cg1); const int* pc2 = PI(DI_pair_cg2); const int* pprm = PI(DI_pair_prm);
     const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum); const int* dbody = I(DI_dof_bodyid);
     const int* ridx = I(DI_body_rootidx); const int* cmask = I(DI_body_chainmask);
     const float* jrange = F(DF_jnt_range); const float* jmargin = F(DF_jnt_margin); const float* jsol = F(DF_jnt_solprm);
@@ -1242,7 +1265,7 @@ __device__ inline void stage_model(const DevModel& P, int* smi, float* smf, uint
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t bytes_i = (uint32_t)P.n_ints * 4u, bytes_f = (uint32_t)P.n_flts * 4u;
+    uint32_t bytes_i = (uint32_t)P.n_ints_staged * 4u, bytes_f = (uint32_t)P.n_flts * 4u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes_i + bytes_f) : "memory");
     uint32_t dst_i = (uint32_t)__cvta_generic_to_shared(smi), dst_f = (uint32_t)__cvta_generic_to_shared(smf);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_i),

@@ -31,8 +31,8 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20;
-  static constexpr bool PGS_HOIST = true;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72;
+  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -79,7 +79,7 @@ struct QuadrupedTask {
       else if (i < 49) {
         // foot *body* id compared with contact *geom* ids
         int fid = tp.ids[1 + i - 45]; int ncon = E.p_misc()[MISC_NCON];
-        const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+        const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         for (int c = 0; c < ncon; c++) {
           int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
           if (gid[pc1[p]] == fid || gid[pc2[p]] == fid) { v = 1.f; break; }
@@ -118,7 +118,7 @@ struct QuadrupedTask {
     int cc = 0;
     {
       int ncon = E.p_misc()[MISC_NCON];
-      const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+      const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
       for (int f = 0; f < 4; f++) {
         int fid = tp.ids[1 + f];
         for (int c = 0; c < ncon; c++) {
@@ -171,8 +171,8 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20;
-  static constexpr bool PGS_HOIST = false;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -255,7 +255,7 @@ struct DancingTask {
       else if (i < 71) v = clampf(E.p_rootcom()[3 * E.I(DI_body_rootidx)[torso] + i - 68] / 10.0f, -1.f, 1.f);
       else if (i < 73) {
         int foot = tp.ids[1 + i - 71], ncon = E.p_misc()[MISC_NCON];
-        const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+        const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         for (int c = 0; c < ncon; c++) {
           int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
           if ((g1 == foot && (g2 == tp.ids[3] || g2 == tp.ids[4])) || (g2 == foot && (g1 == tp.ids[3] || g1 == tp.ids[4]))) v = 1.f;
@@ -354,8 +354,8 @@ struct DancingTask {
 //      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
-  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32;
-  static constexpr bool PGS_HOIST = false;
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -446,8 +446,8 @@ struct SoccerTask {
       else if (i < 73) {
         // (dist, |friction[:2]|) of the last contact between a foot geom and geom 0 (:765-785)
         int foot = tp.ids[4 + ((i - 69) >> 1)], ncon = E.p_misc()[MISC_NCON];
-        const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
-        const int* pprm = E.I(DI_pair_prm); const float* prm = E.F(DF_prm);
+        const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+        const int* pprm = E.PI(DI_pair_prm); const float* prm = E.F(DF_prm);
         for (int c = 0; c < ncon; c++) {
           int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
           if ((g1 == foot && g2 == 0) || (g2 == foot && g1 == 0)) {
@@ -479,7 +479,7 @@ struct SoccerTask {
     if (bp.x > 24.0f && fabsf(bp.y) < 3.66f && bp.z < 2.44f) { reward += 10000.0f; ti[1] = 1; ti[2] += 1; }
     {
       int ncon = E.p_misc()[MISC_NCON]; bool touch = false;
-      const int* pc1 = E.I(DI_pair_cg1); const int* pc2 = E.I(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+      const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
       for (int c = 0; c < ncon && !touch; c++) {
         int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
         if (g1 == tp.ids[3] || g2 == tp.ids[3]) touch = robot_geom<EN>(tp, g1 == tp.ids[3] ? g2 : g1);

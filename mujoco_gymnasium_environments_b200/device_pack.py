@@ -39,9 +39,12 @@ INT_FIELDS = [
     "act_dofid", "act_ctrllimited", "act_forcelimited",
     "lim_jnt",
     "cg_type", "cg_body", "cg_geomid",
-    "pair_cg1", "pair_cg2", "pair_prm", "pair_rawadr", "pair_maxcon",
     "body_chainmask", "site_bodyid",
+    # candidate-pair tables come last: kernels whose task sets COLD_PAIRS leave them in global memory (L2) instead of
+    # staging them into shared memory (rescue: 3 175 pairs = 64 KB); header word 3 holds the offset where they start
+    "pair_cg1", "pair_cg2", "pair_prm", "pair_rawadr", "pair_maxcon",
 ]
+N_COLD_INT_FIELDS = 5
 FLT_FIELDS = [
     "opt",
     "body_pos", "body_quat", "body_ipos", "body_imat", "body_mass", "body_inertia", "body_invweight0",
@@ -265,7 +268,7 @@ def pack_device_model(m: ModelTables) -> Tuple[np.ndarray, np.ndarray]:
         table[ni + k] = (foff, a.size); pad = (-a.size) % 4
         flts.append(np.concatenate([a, np.zeros(pad)])); foff += a.size + pad
     h = np.zeros(head, np.int32)
-    h[0:4] = (B2DEV_MAGIC, ni, nf, 0)
+    h[0:4] = (B2DEV_MAGIC, ni, nf, int(table[ni - N_COLD_INT_FIELDS, 0]))
     h[4:4 + 2 * (ni + nf)] = table.ravel()
     return np.concatenate([h] + ints), np.concatenate(flts)
 
