@@ -28,6 +28,8 @@ WORKLOADS = {
                          "106 self-contact candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
     "humanoid_soccer": (4096, 1500, "humanoid_soccer_env: {n} envs/GPU lockstep, 1 Euler step (dt 20 ms), PGS-50, free ball + box field, "
                         "251 candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
+    "bipedal_rescue": (2048, 300, "bipedal_rescue_env: {n} envs/GPU lockstep, 1 RK4 step (dt 20 ms, 4 forward passes), PGS-50, 63 dofs, "
+                       "3175 candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
 }
 TASK = "quadruped_parkour"
 WORKLOAD = WORKLOADS[TASK][2]

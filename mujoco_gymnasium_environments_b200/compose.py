@@ -153,5 +153,6 @@ COMPOSERS = {
     "quadruped_parkour": quadruped_parkour_mjcf,
     "humanoid_dancing": lambda root: inline_mjcf("dancing", root),
     "humanoid_soccer": lambda root: inline_mjcf("soccer", root),
+    "bipedal_rescue": lambda root: inline_mjcf("rescue", root),
 }
 

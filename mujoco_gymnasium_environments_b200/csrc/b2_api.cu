@@ -150,7 +150,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32;
   static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
@@ -206,6 +206,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
     case TASK_QUADRUPED_PARKOUR: return launch_task<QuadrupedTask>(b, mode, inject, s);
     case TASK_HUMANOID_DANCING: return launch_task<DancingTask>(b, mode, inject, s);
     case TASK_HUMANOID_SOCCER: return launch_task<SoccerTask>(b, mode, inject, s);
+    case TASK_BIPEDAL_RESCUE: return launch_task<RescueTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -260,14 +261,15 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int keep_frames = 0, xfrc_body = -1, arena_rows = 80; bool cold = false; b->ninj = 1;
+  int keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
+    case TASK_BIPEDAL_RESCUE: B2_TASK_DIMS(RescueTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
@@ -280,13 +282,13 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
   b->W = (opts && opts->warps_per_env > 0) ? opts->warps_per_env : 3;
   if (b->W != 1 && b->W != 3) { delete b; return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3"); }
-  v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < 32 ? dim[DD_maxraw] : 32); if (v.con_cap < 1) v.con_cap = 1;
+  v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < task_con_cap ? dim[DD_maxraw] : task_con_cap); if (v.con_cap < 1) v.con_cap = 1;
   v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > B2_ISLAND_ROWS * 4) v.row_cap = B2_ISLAND_ROWS * 4;
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
   int maxspan = 0; const int* inum = m->h_ints.data() + m->dm.ioff[DI_island_dofnum];
   for (int k = 0; k < dim[DD_nisland]; k++) if (inum[k] > maxspan) maxspan = inum[k];
   // narrow-phase capacities: active pairs after the cull, raw contact slots handed out to them
-  v.act_cap = r4(dim[DD_npair] < 128 ? dim[DD_npair] : 128); if (v.act_cap < 4) v.act_cap = 4;
+  v.act_cap = r4(dim[DD_npair] < 256 ? dim[DD_npair] : 256); if (v.act_cap < 4) v.act_cap = 4;
   v.raw_cap = dim[DD_maxraw] < 384 ? dim[DD_maxraw] : 384; if (v.raw_cap < 8) v.raw_cap = 8;
   int raw_need = 3 * v.act_cap + 10 * v.raw_cap;
   b->dm = m->dm;

@@ -480,6 +480,13 @@ struct Engine {
 #pragma unroll
       for (int c = 0; c < 3; c++) mat[3 * r + c] = xm[3 * r] * lm[c] + xm[3 * r + 1] * lm[3 + c] + xm[3 * r + 2] * lm[6 + c];
   }
+  // true when the point c is farther than `reach` from the box geom (cg, on body b, centre cb)
+  __device__ __forceinline__ bool box_far(int cg, int b, V3 cb, V3 c, float reach) const {
+    const float* xm = p_xmat() + 9 * b; const float* lm = F(DF_cg_mat) + 9 * cg; const float* sz = F(DF_cg_size) + 3 * cg;
+    V3 dw = c - cb; V3 db = mulmatT(xm, dw); V3 dl = mulmatT(lm, db);      // into the body frame, then the geom frame
+    float ex = fmaxf(fabsf(dl.x) - sz[0], 0.f), ey = fmaxf(fabsf(dl.y) - sz[1], 0.f), ez = fmaxf(fabsf(dl.z) - sz[2], 0.f);
+    return ex * ex + ey * ey + ez * ez > reach * reach;
+  }
   // candidate pairs are culled first (bounding spheres / plane distance) and the survivors compacted, in pair order,
   // into an active list, so the narrow phase runs one *surviving* pair per lane.  Raw contact slots are handed out to the
   // active pairs by a prefix sum of their static maxima, so the arena only holds what a step can actually produce
@@ -505,7 +512,13 @@ struct Engine {
         if (cgtype[g1] == 0) {
           V3 n = mulmat(p_xmat() + 9 * b1, matcol(cgmat + 9 * g1, 2));
           keep = !(dot(d, n) > cgrb[g2] + margin);
-        } else { float bd = cgrb[g1] + cgrb[g2] + margin; keep = !(dot(d, d) > bd * bd); }
+        } else {
+          float bd = cgrb[g1] + cgrb[g2] + margin; keep = !(dot(d, d) > bd * bd);
+          // a long box has a huge bounding sphere: also test the other geom's bounding sphere against the box itself
+          // (pure pruning: the narrow phase would return nothing for these pairs)
+          if (keep && cgtype[g2] == GT_BOX) keep = !box_far(g2, b2, q2, q1, cgrb[g1] + margin);
+          if (keep && cgtype[g1] == GT_BOX) keep = !box_far(g1, b1, q1, q2, cgrb[g2] + margin);
+        }
       }
       unsigned m = __ballot_sync(B2_FULL, keep);
       int slot = nact + __popc(m & lt);

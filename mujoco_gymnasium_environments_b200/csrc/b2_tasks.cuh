@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -31,7 +31,7 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32;
   static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
@@ -171,7 +171,7 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32;
   static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
@@ -354,7 +354,7 @@ struct DancingTask {
 //      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
-  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84;
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32;
   static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
@@ -506,6 +506,167 @@ struct SoccerTask {
     tf[12] += norm(rp - pr);
     { const float* bv = E.p_qvel() + E.I(DI_jnt_dofadr)[tp.ids[10]]; tf[13] = fmaxf(tf[13], sqrtf(bv[0] * bv[0] + bv[1] * bv[1] + bv[2] * bv[2])); }
     st3(tf + 1, bp); st3(tf + 4, rp);
+    return reward;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ bipedal rescue
+// bipedal_rescue_env/rescue_env.py: step :416-471, reset :366-414, _randomize_initial_state :473-508,
+// _check_victim_interactions :510-543, _get_observation :545-600, _calculate_reward :602-668, _check_termination
+// :670-697, _update_episode_stats :699-706, helpers :708-775.  Quirks kept: the carry-capacity test
+// is made once before the victim loop (more than two victims can be picked up in one step), the first step of every
+// episode pays +inf (approach term against closest = inf), the attributes created with hasattr
+// (_prev_rescued_count, _prev_carried_count, _prev_safe_zone_distance, _fall_timer) survive reset.
+// ti: [0] current_step [1] rescued mask [2] carried mask [3] carrying flag [4] episode id [5] _prev_rescued_count + 1
+//     (0 = attribute absent) [6] _prev_carried_count + 1 [7] _fall_timer [8] has _prev_safe_zone_distance [9] falls
+//     [10] collisions [11] victims_rescued
+// tf: [0] return [1] current_energy [2] closest_victim_distance [3] _prev_safe_zone_distance [4,5] prev_robot_pos.xy
+//     [6] distance_traveled [7] energy_used [8] time_to_first_rescue (-1 = None)
+// ids: [0] torso body [1] victim1 body (victims are consecutive) [2] root_x joint (y, z follow) [3] first observed joint
+//      (26 consecutive) [4] victim1_x joint (victim joints are 6 apart, y = x + 1)
+// inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
+struct RescueTask {
+  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 124, CON_CAP = 48;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true;
+  static constexpr int NVICT = 5;
+
+  template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
+    const float* q = E.p_xquat() + 4 * torso;
+    return q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3] > 0.7f;
+  }
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
+      act_clipped[i] = a; E.p_ctrl()[i] = a;
+    }
+    E.sync();
+  }
+  // energy bookkeeping happens before mj_step (:424-427)
+  template <class EN> __device__ static void pre_physics(EN& E, const TaskParams&, int*, float* tf) {
+    if (E.lane == 0) {
+      const float* a = E.p_act(); float s = 0.f;
+      for (int i = 0; i < ACT; i++) s += fabsf(a[i]);
+      tf[1] -= s * 0.001f; tf[7] += s * 0.001f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+                                     const float* inject) {
+    E.reset_data();
+    if (E.lane == 0) {
+      const int* jq = E.I(DI_jnt_qposadr); float* q = E.p_qpos();
+      unsigned ep = (unsigned)ti[4]; unsigned ge = (unsigned)(B.env_offset + env);
+      auto draw = [&](int k, float lo, float hi) { return inject ? inject[k] : lo + (hi - lo) * rng_uniform(B.seed, ge, ep, (unsigned)k); };
+      q[jq[tp.ids[2]]] = draw(0, -5.f, 5.f); q[jq[tp.ids[2] + 1]] = draw(1, -5.f, 5.f); q[jq[tp.ids[2] + 2]] = 1.2f;
+      for (int v = 0; v < NVICT; v++) {
+        int jx = tp.ids[4] + 6 * v;
+        q[jq[jx]] += draw(2 + 2 * v, -1.f, 1.f); q[jq[jx + 1]] += draw(3 + 2 * v, -1.f, 1.f);
+      }
+      ti[0] = 0; ti[1] = 0; ti[2] = 0; ti[3] = 0; ti[4] = (int)(ep + 1); ti[9] = 0; ti[10] = 0; ti[11] = 0;
+      tf[0] = 0.f; tf[1] = 1000.0f; tf[2] = __int_as_float(0x7f800000); tf[6] = 0.f; tf[7] = 0.f; tf[8] = -1.f;
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void after_settle(EN& E, const TaskParams& tp, int*, float* tf) {
+    if (E.lane < 2) tf[4 + E.lane] = E.p_xpos()[3 * tp.ids[0] + E.lane];
+    E.sync();
+  }
+  // current_step += 1, then _check_victim_interactions, both before the observation (:432-438)
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, int* ti, float* tf) {
+    if (E.lane == 0) {
+      ti[0] += 1;
+      const float* xp = E.p_xpos(); float rx = xp[3 * tp.ids[0]], ry = xp[3 * tp.ids[0] + 1];
+      if (__popc(ti[2]) < 2) {                       // capacity is tested once, before the loop
+        for (int v = 0; v < NVICT; v++) {
+          if (((ti[1] | ti[2]) >> v) & 1) continue;
+          float dx = rx - xp[3 * (tp.ids[1] + v)], dy = ry - xp[3 * (tp.ids[1] + v) + 1];
+          float d = sqrtf(dx * dx + dy * dy);
+          if (d < 1.0f && d < 0.8f) { ti[2] |= 1 << v; ti[3] = 1; }
+        }
+      }
+      if (ti[3]) {
+        float dx = rx - 20.0f, dy = ry;
+        if (sqrtf(dx * dx + dy * dy) < 3.0f) {
+          // victims_rescued is a list: len() counts every drop-off
+          int n = __popc(ti[2]);
+          if (n > 0 && tf[8] < 0.f) tf[8] = (float)ti[0] * 0.02f;
+          ti[11] += n; ti[1] |= ti[2]; ti[2] = 0; ti[3] = 0;
+        }
+      }
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
+    const int torso = tp.ids[0];
+    const int* ti = E.p_ti(); const float* tf = E.p_tf();
+    const int* jq = E.I(DI_jnt_qposadr); const int* jd = E.I(DI_jnt_dofadr);
+    const float* xp = E.p_xpos();
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 52) { int j = tp.ids[3] + (i >> 1); v = (i & 1) ? E.p_qvel()[jd[j]] : E.p_qpos()[jq[j]]; }
+      else if (i < 55) v = xp[3 * torso + i - 52];
+      else if (i < 59) v = E.p_xquat()[4 * torso + i - 55];
+      else if (i < 65) v = E.p_qvel()[jd[tp.ids[2]] + i - 59];
+      else if (i == 65) { int n = min(E.p_misc()[MISC_NCON], 10); for (int c = 0; c < n; c++) v += fabsf(E.p_con()[B2_CON_STRIDE * c]); }
+      else if (i < 69) v = 0.f;
+      else if (i < 89) {
+        int k = (i - 69) >> 2, f = (i - 69) & 3;
+        v = f < 2 ? xp[3 * (tp.ids[1] + k) + f] : (f == 2 ? (float)((ti[1] >> k) & 1) : (float)((ti[2] >> k) & 1));
+      } else if (i < 92) { const float sz[3] = {20.0f, 0.0f, 0.0f}; v = sz[i - 89] - xp[3 * torso + i - 89]; }
+      else if (i == 92) v = tf[1] / 1000.0f;
+      else if (i == 93) v = 1.0f - (float)ti[0] / (float)MAX_STEPS;
+      else if (i == 94) v = (float)__popc(ti[2]);
+      else if (i == 95) v = (float)ti[11];
+      else { const float fz[6] = {-5.0f, -3.0f, 0.0f, 8.0f, 6.0f, 0.0f}; v = fz[i - 96] - xp[3 * torso + (i - 96) % 3]; }
+      obs[i] = v;
+    }
+  }
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    const int torso = tp.ids[0];
+    const float* xp = E.p_xpos(); float rx = xp[3 * torso], ry = xp[3 * torso + 1];
+    float reward = 0.f;
+    int nres = ti[11], ncar = __popc(ti[2]);
+    if (ti[5] > 0) { int d = nres - (ti[5] - 1); if (d > 0) reward += 5000.0f * (float)d; }
+    ti[5] = nres + 1;
+    if (ti[6] > 0) { int d = ncar - (ti[6] - 1); if (d > 0) reward += 1000.0f * (float)d; }
+    ti[6] = ncar + 1;
+    float mind = __int_as_float(0x7f800000);
+    for (int v = 0; v < NVICT; v++) {
+      if (((ti[1] | ti[2]) >> v) & 1) continue;
+      float dx = rx - xp[3 * (tp.ids[1] + v)], dy = ry - xp[3 * (tp.ids[1] + v) + 1];
+      mind = fminf(mind, sqrtf(dx * dx + dy * dy));
+    }
+    if (mind < tf[2] && mind < 10.0f) reward += 100.0f * (tf[2] - mind);       // +inf on the first step of an episode
+    tf[2] = mind;
+    if (ti[3]) {
+      float dx = rx - 20.0f, dy = ry, sd = sqrtf(dx * dx + dy * dy);
+      if (ti[8] && sd < tf[3]) reward += 200.0f * (tf[3] - sd);
+      tf[3] = sd; ti[8] = 1;
+    }
+    bool up = upright(E, torso);
+    if (up) reward += 50.0f; else { reward += -500.0f; ti[9] += 1; }
+    float s = 0.f;
+    for (int i = 0; i < ACT; i++) s += fabsf(act[i]);
+    if (s * 0.001f < 0.5f) reward += 10.0f;
+    { float dx = rx + 5.0f, dy = ry + 3.0f; if (sqrtf(dx * dx + dy * dy) < 1.5f) reward += -200.0f; }
+    { float dx = rx - 8.0f, dy = ry - 6.0f; if (sqrtf(dx * dx + dy * dy) < 1.2f) reward += -200.0f; }
+    {
+      int n = min(E.p_misc()[MISC_NCON], 20); bool hit = false;
+      for (int c = 0; c < n; c++) if (fabsf(E.p_con()[B2_CON_STRIDE * c]) > 0.1f) hit = true;
+      if (hit) { reward += -100.0f; ti[10] += 1; }
+    }
+    reward += -1.0f;
+    tf[0] += reward;
+    int term = (ti[11] == NVICT);
+    // the reference returns at the first true test: the fall timer only moves when "all rescued" was false
+    if (!term) { if (!up) { ti[7] += 1; if (ti[7] > 100) term = 1; } else ti[7] = 0; }
+    if (tf[1] <= 0.f) term = 1;
+    if (fabsf(rx) > 25.0f || fabsf(ry) > 25.0f) term = 1;
+    *terminated = term; *truncated = ti[0] >= MAX_STEPS;
+    { float dx = rx - tf[4], dy = ry - tf[5]; tf[6] += sqrtf(dx * dx + dy * dy); }
+    tf[4] = rx; tf[5] = ry;
     return reward;
   }
 };

@@ -130,6 +130,33 @@ def _soccer_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- bipedal rescue
+_RESCUE_JOINTS = ["neck_pitch", "neck_yaw", "right_shoulder_pitch", "right_shoulder_roll", "right_elbow", "right_wrist",     # rescue_env.py:298-308
+                  "right_finger1_joint", "right_finger2_joint", "left_shoulder_pitch", "left_shoulder_roll", "left_elbow",
+                  "left_wrist", "left_finger1_joint", "left_finger2_joint", "right_hip_roll", "right_hip_pitch",
+                  "right_hip_yaw", "right_knee_joint", "right_ankle_pitch", "right_ankle_roll", "left_hip_roll",
+                  "left_hip_pitch", "left_hip_yaw", "left_knee_joint", "left_ankle_pitch", "left_ankle_roll"]
+
+
+def _rescue_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_BIPEDAL_RESCUE
+    vb = [t.name2id("body", f"victim{i}") for i in range(1, 6)]
+    assert vb == list(range(vb[0], vb[0] + 5)), "victim bodies must be consecutive"
+    jids = [t.name2id("joint", n) for n in _RESCUE_JOINTS]
+    assert jids == list(range(jids[0], jids[0] + 26)), "observed joints must be consecutive"
+    rx = t.name2id("joint", "root_x")
+    assert (t.name2id("joint", "root_y"), t.name2id("joint", "root_z")) == (rx + 1, rx + 2)
+    vx = [t.name2id("joint", f"victim{i}_x") for i in range(1, 6)]
+    vy = [t.name2id("joint", f"victim{i}_y") for i in range(1, 6)]
+    assert vx == [vx[0] + 6 * k for k in range(5)] and vy == [x + 1 for x in vx]
+    for k, v in enumerate([t.name2id("body", "torso"), vb[0], rx, jids[0], vx[0]]):
+        d.ids[k] = v
+    for k in range(26):
+        d.act_lo[k] = -100.0; d.act_hi[k] = 100.0
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -152,4 +179,11 @@ TASKS: Dict[str, TaskSpec] = {
         observation_space=lambda t: Box(np.full(80, -1.0, np.float32), np.full(80, 1.0, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "ball_position", "robot_position", "goal_distance", "ball_contact", "robot_upright",
                    "goal_scored"]),
+    "bipedal_rescue": TaskSpec(
+        name="bipedal_rescue", task_id=capi.TASK_BIPEDAL_RESCUE, obs_dim=102, act_dim=26, max_episode_steps=10000,
+        frame_skip=1, render_fps=50, bytes_per_env_step=2190, describe=_rescue_desc,
+        action_space=lambda t: Box(np.full(26, -100.0, np.float32), np.full(26, 100.0, np.float32), dtype=np.float32),
+        observation_space=lambda t: Box(np.full(102, -np.inf, np.float32), np.full(102, np.inf, np.float32), dtype=np.float32),
+        info_keys=["episode_stats", "robot_position", "victims_remaining", "victims_carried", "energy_remaining",
+                   "robot_upright"]),
 }

@@ -613,4 +613,194 @@ class HumanoidSoccerRef:
         return False
 
 
-TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef}
+class BipedalRescueRef:
+    """bipedal_rescue_env/rescue_env.py restated: __init__ :35-119, _get_model_indices :279-322, reset :366-414,
+    step :416-471, _randomize_initial_state :473-508, _check_victim_interactions :510-543, _get_observation :545-600,
+    _calculate_reward :602-668, _check_termination :670-697, _update_episode_stats :699-706, helpers :708-775."""
+
+    JOINT_NAMES = ["neck_pitch", "neck_yaw", "right_shoulder_pitch", "right_shoulder_roll", "right_elbow", "right_wrist",
+                   "right_finger1_joint", "right_finger2_joint", "left_shoulder_pitch", "left_shoulder_roll", "left_elbow",
+                   "left_wrist", "left_finger1_joint", "left_finger2_joint", "right_hip_roll", "right_hip_pitch",
+                   "right_hip_yaw", "right_knee_joint", "right_ankle_pitch", "right_ankle_roll", "left_hip_roll",
+                   "left_hip_pitch", "left_hip_yaw", "left_knee_joint", "left_ankle_pitch", "left_ankle_roll"]
+    FIRE = [(np.array([-5.0, -3.0, 0.0]), 1.5), (np.array([8.0, 6.0, 0.0]), 1.2)]
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("bipedal_rescue")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.dt = 0.02; self.max_episode_steps = 10000; self.current_step = 0
+        self.safe_zone_radius = 3.0; self.safe_zone_pos = np.array([20.0, 0.0, 0.0])
+        self.carry_capacity = 2; self.energy_limit = 1000.0; self.current_energy = self.energy_limit
+        self.num_victims = 5
+        self.victims_rescued = []; self.victims_carried = []
+        self.torso_id = t.name2id("body", "torso")
+        self.victim_ids = [t.name2id("body", f"victim{i}") for i in range(1, 6)]
+        self.joint_indices = [t.name2id("joint", n) for n in self.JOINT_NAMES]
+        self.jnt_qposadr = np.asarray(t.jnt_qposadr); self.jnt_dofadr = np.asarray(t.jnt_dofadr)
+        self.action_low = np.full(26, -100.0); self.action_high = np.full(26, 100.0)
+        self.episode_stats = dict(victims_rescued=0, distance_traveled=0.0, energy_used=0.0, time_to_first_rescue=None, falls=0, collisions=0)
+        self.prev_robot_pos = None
+        self.closest_victim_distance = float("inf")
+        self.carrying_victims = False
+        self.np_random = np.random.default_rng(seed)
+
+    def reset(self, seed=None, draws=None):
+        if seed is not None:
+            self.np_random = np.random.default_rng(seed)
+        d = self.data
+        ref.mj_resetData(self.model, d)
+        self.current_step = 0; self.current_energy = self.energy_limit
+        self.victims_rescued = []; self.victims_carried = []; self.carrying_victims = False
+        self.closest_victim_distance = float("inf")
+        self.episode_stats = dict(victims_rescued=0, distance_traveled=0.0, energy_used=0.0, time_to_first_rescue=None, falls=0, collisions=0)
+        it = iter(draws) if draws is not None else None
+        U = (lambda lo, hi: float(next(it))) if it is not None else (lambda lo, hi: self.np_random.uniform(lo, hi))
+        t = self.tables
+        d.qpos[self.jnt_qposadr[t.name2id("joint", "root_x")]] = U(-5.0, 5.0)
+        d.qpos[self.jnt_qposadr[t.name2id("joint", "root_y")]] = U(-5.0, 5.0)
+        d.qpos[self.jnt_qposadr[t.name2id("joint", "root_z")]] = 1.2
+        for i in range(1, self.num_victims + 1):
+            jx = t.name2id("joint", f"victim{i}_x"); jy = t.name2id("joint", f"victim{i}_y")
+            if jx >= 0 and jy >= 0:
+                xo = U(-1.0, 1.0); yo = U(-1.0, 1.0)
+                d.qpos[self.jnt_qposadr[jx]] += xo; d.qpos[self.jnt_qposadr[jy]] += yo
+        ref.mj_step(self.model, d, 10)
+        obs = self._get_observation()
+        self.prev_robot_pos = d.xpos[self.torso_id].copy()
+        return obs, dict(episode_stats=dict(self.episode_stats))
+
+    def step(self, action):
+        d = self.data
+        action = np.clip(np.asarray(action, np.float64), self.action_low, self.action_high)
+        d.ctrl[:len(action)] = action
+        energy_cost = float(np.sum(np.abs(action))) * 0.001
+        self.current_energy -= energy_cost
+        self.episode_stats["energy_used"] += energy_cost
+        ref.mj_step(self.model, d)
+        self.current_step += 1
+        self._check_victim_interactions()
+        obs = self._get_observation()
+        reward = self._calculate_reward(action)
+        terminated = self._check_termination()
+        truncated = self.current_step >= self.max_episode_steps
+        robot_pos = d.xpos[self.torso_id]
+        self.episode_stats["distance_traveled"] += float(np.linalg.norm(robot_pos[:2] - self.prev_robot_pos[:2]))
+        info = dict(episode_stats=dict(self.episode_stats), victims_carried=len(self.victims_carried),
+                    energy_remaining=self.current_energy, robot_upright=self._is_robot_upright())
+        self.prev_robot_pos = robot_pos.copy()
+        return obs, reward, terminated, truncated, info
+
+    def _check_victim_interactions(self):
+        d = self.data
+        robot_pos = d.xpos[self.torso_id]
+        if len(self.victims_carried) < self.carry_capacity:
+            for i in range(len(self.victim_ids)):
+                if i not in self.victims_rescued and i not in self.victims_carried:
+                    distance = np.linalg.norm(robot_pos[:2] - d.xpos[self.victim_ids[i]][:2])
+                    if distance < 1.0 and distance < 0.8:          # _check_gripper_contact is a second distance test (:753-758)
+                        self.victims_carried.append(i); self.carrying_victims = True
+        if self.carrying_victims:
+            if np.linalg.norm(robot_pos[:2] - self.safe_zone_pos[:2]) < self.safe_zone_radius:
+                for v in self.victims_carried:
+                    self.victims_rescued.append(v)
+                    self.episode_stats["victims_rescued"] += 1
+                    if self.episode_stats["time_to_first_rescue"] is None:
+                        self.episode_stats["time_to_first_rescue"] = self.current_step * self.dt
+                self.victims_carried = []; self.carrying_victims = False
+
+    def _is_robot_upright(self):
+        w, x, y, z = self.data.xquat[self.torso_id]
+        return (w*w - x*x - y*y + z*z) > 0.7
+
+    def _get_observation(self):
+        d = self.data
+        obs = []
+        for j in self.joint_indices:
+            if j < len(d.qpos):
+                obs.extend([d.qpos[self.jnt_qposadr[j]], d.qvel[self.jnt_dofadr[j]] if self.jnt_dofadr[j] < len(d.qvel) else 0.0])
+            else:
+                obs.extend([0.0, 0.0])
+        robot_pos = d.xpos[self.torso_id]
+        obs.extend(robot_pos); obs.extend(d.xquat[self.torso_id])
+        vs = self.jnt_dofadr[self.tables.name2id("joint", "root_x")]
+        obs.extend(d.qvel[vs:vs + 6])
+        forces = np.zeros(4)
+        cons = self.data.contact
+        for i in range(min(d.ncon, 10)):
+            forces[0] += abs(cons[i].dist)
+        obs.extend(forces)
+        for i in range(self.num_victims):
+            vp = d.xpos[self.victim_ids[i]]
+            obs.extend([vp[0], vp[1], 1.0 if i in self.victims_rescued else 0.0, 1.0 if i in self.victims_carried else 0.0])
+        obs.extend(self.safe_zone_pos - robot_pos)
+        obs.append(self.current_energy / self.energy_limit)
+        obs.append(1.0 - (self.current_step / self.max_episode_steps))
+        obs.append(len(self.victims_carried)); obs.append(len(self.victims_rescued))
+        for pos, _ in self.FIRE:
+            obs.extend(pos - robot_pos)
+        return np.array(obs, dtype=np.float32)
+
+    def _calculate_reward(self, action):
+        d = self.data
+        reward = 0.0
+        if hasattr(self, "_prev_rescued_count"):
+            new = len(self.victims_rescued) - self._prev_rescued_count
+            if new > 0:
+                reward += 5000.0 * new
+        self._prev_rescued_count = len(self.victims_rescued)
+        if hasattr(self, "_prev_carried_count"):
+            new = len(self.victims_carried) - self._prev_carried_count
+            if new > 0:
+                reward += 1000.0 * new
+        self._prev_carried_count = len(self.victims_carried)
+        robot_pos = d.xpos[self.torso_id]
+        mind = float("inf")
+        for i in range(self.num_victims):
+            if i not in self.victims_rescued and i not in self.victims_carried:
+                mind = min(mind, float(np.linalg.norm(robot_pos[:2] - d.xpos[self.victim_ids[i]][:2])))
+        if mind < self.closest_victim_distance and mind < 10.0:
+            reward += 100.0 * (self.closest_victim_distance - mind)
+        self.closest_victim_distance = mind
+        if self.carrying_victims:
+            sd = float(np.linalg.norm(robot_pos[:2] - self.safe_zone_pos[:2]))
+            if hasattr(self, "_prev_safe_zone_distance") and sd < self._prev_safe_zone_distance:
+                reward += 200.0 * (self._prev_safe_zone_distance - sd)
+            self._prev_safe_zone_distance = sd
+        if self._is_robot_upright():
+            reward += 50.0
+        else:
+            reward += -500.0; self.episode_stats["falls"] += 1
+        if float(np.sum(np.abs(action))) * 0.001 < 0.5:
+            reward += 10.0
+        for pos, radius in self.FIRE:
+            if np.linalg.norm(robot_pos[:2] - pos[:2]) < radius:
+                reward += -200.0
+        cons = d.contact
+        if any(abs(cons[i].dist) > 0.1 for i in range(min(d.ncon, 20))):
+            reward += -100.0; self.episode_stats["collisions"] += 1
+        reward += -1.0
+        return float(reward)
+
+    def _check_termination(self):
+        if len(self.victims_rescued) == self.num_victims:
+            return True
+        if not self._is_robot_upright():
+            if not hasattr(self, "_fall_timer"):
+                self._fall_timer = 0
+            self._fall_timer += 1
+            if self._fall_timer > 100:
+                return True
+        else:
+            self._fall_timer = 0
+        if self.current_energy <= 0:
+            return True
+        p = self.data.xpos[self.torso_id]
+        if abs(p[0]) > 25 or abs(p[1]) > 25:
+            return True
+        return False
+
+
+TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef,
+         "bipedal_rescue": BipedalRescueRef}

@@ -33,6 +33,10 @@ def make_inject(task, rng, n):
         inj[:, 3:32] = rng.uniform(-.1, .1, (n, 29)); inj[:, 32] = rng.uniform(-2, 2, n); inj[:, 33] = rng.uniform(0, 2, n)
         inj[:, 34] = rng.uniform(0, 2 * np.pi, n); inj[:, 35] = rng.uniform(.05, .15, n)
         return inj
+    if task == "bipedal_rescue":
+        inj = np.zeros((n, 12), np.float32)
+        inj[:, 0:2] = rng.uniform(-5, 5, (n, 2)); inj[:, 2:] = rng.uniform(-1, 1, (n, 10))
+        return inj
     raise KeyError(task)
 
 
@@ -41,7 +45,7 @@ def ref_reset(task, env, inj):
         return env.reset(randomize=(float(inj[0]), float(inj[1])))
     if task == "humanoid_dancing":
         return env.reset(sequence=[(int(inj[2 * k]), float(inj[2 * k + 1])) for k in range(20)])
-    if task == "humanoid_soccer":
+    if task in ("humanoid_soccer", "bipedal_rescue"):
         return env.reset(draws=[float(x) for x in inj])
 
 
@@ -129,7 +133,7 @@ def main():
     print("stats", env.episode_stats())
     env.close()
     # ---------------- throughput
-    for N in (4096, 8192):
+    for N in ((2048,) if task == "bipedal_rescue" else (4096, 8192)):
         for sc in (0.02, 1.0):
             env = B200VectorEnv(task, N, device=0, seed=1)
             env.reset()
