@@ -89,6 +89,17 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def _finite(x):
+    """JSON has no Infinity / NaN (rescue pays +inf on the first step of every episode): non-finite floats become null."""
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    if isinstance(x, float) and (x != x or x in (float("inf"), float("-inf"))):
+        return None
+    return x
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,7 +229,7 @@ def main():
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
             episode_stats={k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped",
                                               "rows_dropped", "arena_overflows", "solver_iters", "substeps")})
-        print(json.dumps(out))
+        print(json.dumps(_finite(out)))
     env.close()
     if world > 1:
         dist.destroy_process_group()
