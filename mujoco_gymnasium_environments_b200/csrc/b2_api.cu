@@ -45,7 +45,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS> E(P, B, B.model_floats + team * B.ws_floats, team);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -61,6 +61,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
     if (tl < 8) E.p_xfrc()[tl] = 0.f;
     if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; }
+    if (!Task::DYN_ISLANDS && w0) E.static_islands();
     for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
     for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
   }
@@ -150,8 +151,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32;
-  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -242,7 +243,7 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
   for (int k = 0; k < DO_COUNT; k++) dm.opt[k] = (float)opt[k];
   if (dm.dim[DD_integrator] != 0 && dm.dim[DD_integrator] != 1) { delete m; return fail(B2_ERR_UNSUPPORTED, "integrator must be Euler or RK4"); }
   if (dm.dim[DD_solver] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the PGS solver is built in this round"); }
-  if (dm.dim[DD_nisland] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "too many islands"); }
+  if (dm.dim[DD_ntree] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "more than 16 kinematic trees"); }
   std::vector<float> f32(n_flts);
   for (int i = 0; i < n_flts; i++) f32[i] = (float)flts[i];
   CK(cudaMalloc(&m->d_ints, sizeof(int) * n_ints)); CK(cudaMalloc(&m->d_flts, sizeof(float) * n_flts));
@@ -261,11 +262,11 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32; bool cold = false; b->ninj = 1;
+  int keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -296,7 +297,8 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim, keep_frames)) ? 0 : 32 * dim[DD_nv];
   // default arena: J (rows x widest island) + tiled A for the task's typical row count, plus the A-build scratch
   int typ = arena_rows < B2_ISLAND_ROWS ? arena_rows : B2_ISLAND_ROWS;
-  int arena_default = r4(typ * (maxspan | 1)) + 16 * ((((typ + 3) >> 2) * (((typ + 3) >> 2) + 1)) >> 1) + 64;
+  int span = arena_span > 0 && arena_span < maxspan ? arena_span : maxspan;      // dofs of the widest island the arena is sized for
+  int arena_default = r4(typ * (span | 1)) + 16 * ((((typ + 3) >> 2) * (((typ + 3) >> 2) + 1)) >> 1) + 64;
   int arena = (o_arena > 0 ? o_arena : arena_default) + scratch;
   if (arena < raw_need) arena = raw_need;
   v.arena_floats = r4(arena);

@@ -55,14 +55,14 @@ extern __shared__ __align__(128) float b2_smem[];
 #define B2_WS_FLOAT_FIELDS(X) X(qpos) X(qvel) X(warm) X(ctrl) X(qapp) X(xpos) X(xmat) X(cdof) X(rootcom) \
   X(xquat) X(xipos) X(cvel) X(cacc) X(cinert) X(M) X(LD) X(invD) X(qfs) X(qas) X(qfc) X(qacc) X(tmp) X(con) \
   X(row_R) X(row_b) X(row_f) X(row_res) X(arena) X(red) X(time) X(tf) X(act) X(rk_q0) X(rk_v0) X(rk_sv) X(rk_sa) X(xfrc) X(LD2) X(invD2)
-#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_warp) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
+#define B2_WS_INT_FIELDS(X) X(lim_row) X(con_row) X(row_info) X(isl_n) X(isl_nl) X(isl_warp) X(isl_nd) X(isl_col0) X(tree_isl) X(tree_col0) X(dof_col) X(col_dof) X(isl_adr) X(isl_J) X(isl_A) X(isl_ldj) X(misc) X(ti)
 
 struct WsOff {
 #define X(n) int n;
   B2_WS_FLOAT_FIELDS(X) B2_WS_INT_FIELDS(X)
 #undef X
 };
-enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_COUNT = 8 };
+enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_NISL = 6, MISC_COUNT = 8 };
 
 __host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 // model tables occupy the first model_floats of shared memory (ints first, then floats), padded to 32 floats
@@ -85,7 +85,9 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   t.qacc = take(nv); t.tmp = take(nv);
   t.con = take(con_cap * B2_CON_STRIDE); t.lim_row = take(2 * (nlim > 0 ? nlim : 1)); t.con_row = take(con_cap);
   t.row_info = take(row_cap); t.row_R = take(row_cap); t.row_b = take(row_cap); t.row_f = take(row_cap); t.row_res = take(row_cap);
-  t.isl_n = take(B2_MAX_ISLANDS); t.isl_nl = take(B2_MAX_ISLANDS); t.isl_warp = take(B2_MAX_ISLANDS); t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
+  t.isl_n = take(B2_MAX_ISLANDS); t.isl_nl = take(B2_MAX_ISLANDS); t.isl_warp = take(B2_MAX_ISLANDS); t.isl_nd = take(B2_MAX_ISLANDS);
+  t.isl_col0 = take(B2_MAX_ISLANDS + 4); t.tree_isl = take(B2_MAX_ISLANDS); t.tree_col0 = take(B2_MAX_ISLANDS); t.dof_col = take(nv); t.col_dof = take(nv);
+  t.isl_adr = take(B2_MAX_ISLANDS + 4); t.isl_J = take(B2_MAX_ISLANDS);
   t.isl_A = take(B2_MAX_ISLANDS); t.isl_ldj = take(B2_MAX_ISLANDS);
   t.red = take(16); t.misc = take(MISC_COUNT); t.time = take(4); t.ti = take(nti > 0 ? nti : 1); t.tf = take(ntf > 0 ? ntf : 1);
   t.act = take(40);
@@ -139,7 +141,9 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // over the team's warps; team_sync() is a named barrier private to the team.
 // HOIST: a warp sweeping a single island keeps its PGS rows in registers across iterations; COOPMIN: islands with more
 // rows than this are built (A = J M^-1 J') by the whole team.  Both are per-task tuning knobs (A/B-measured on B200).
-template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false>
+// DYN: islands are re-formed every forward pass from the active contacts (needed when moving trees can touch each other);
+// otherwise they are the model's static islands, set up once per launch.
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -582,19 +586,104 @@ struct Engine {
     sync();
   }
 
+  // island of contact c: the island of its moving body (geom 2's tree when it has one, else geom 1's)
   __device__ __forceinline__ int contact_island(int c) const {
-    const int* bisl = I(DI_body_island); const int* cgbody = I(DI_cg_body);
+    const int* btree = I(DI_body_tree); const int* cgbody = I(DI_cg_body);
     int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]);
-    int i2 = bisl[cgbody[PI(DI_pair_cg2)[p]]], i1 = bisl[cgbody[PI(DI_pair_cg1)[p]]];
-    return i2 >= 0 ? i2 : i1;
+    int t2 = btree[cgbody[PI(DI_pair_cg2)[p]]], t1 = btree[cgbody[PI(DI_pair_cg1)[p]]];
+    return p_tree_isl()[t2 >= 0 ? t2 : t1];
+  }
+  // column -> dof of island k.  Islands made of one tree (or of adjacent trees) cover a contiguous dof range, which
+  // is the common case; then the map is an add instead of a shared-memory load.
+  struct Cols {
+    const int* map; int d0; bool contig;
+    __device__ __forceinline__ int dof(int c) const { return (!DYN || contig) ? d0 + c : map[c]; }
+  };
+  __device__ __forceinline__ Cols island_cols(int k) const {
+    Cols q; q.map = p_col_dof() + p_isl_col0()[k];
+    if (!DYN) { q.d0 = p_isl_col0()[k]; q.contig = true; return q; }       // static islands are contiguous dof ranges
+    int nd = p_isl_nd()[k];
+    q.d0 = q.map[0]; q.contig = q.map[nd - 1] - q.d0 == nd - 1;
+    return q;
+  }
+  // static islands (models whose moving trees never share a candidate pair): set up once per launch
+  __device__ void static_islands() {
+    const int* disl = I(DI_dof_island); const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum);
+    const int* tadr = I(DI_tree_dofadr);
+    int ntree = dim(DD_ntree), nv = dim(DD_nv), nisl = dim(DD_nisland);
+    if (lane < ntree) { p_tree_isl()[lane] = disl[tadr[lane]]; p_tree_col0()[lane] = tadr[lane] - iadr[disl[tadr[lane]]]; }
+    if (lane < nisl) { p_isl_nd()[lane] = inum[lane]; p_isl_col0()[lane] = iadr[lane]; }
+    if (lane == 0) { p_isl_col0()[nisl] = nv; p_misc()[MISC_NISL] = nisl; }
+    for (int d = lane; d < nv; d += 32) { p_dof_col()[d] = d - iadr[disl[d]]; p_col_dof()[d] = d; }
+    sync();
+  }
+  // ---- islands of this forward pass: kinematic trees joined by a contact between two moving bodies (union-find over at
+  // most 16 trees, by one lane), numbered by their smallest tree; an island's columns are its trees' dofs in tree order.
+  // Islands are exactly decoupled blocks of the constraint problem, so solving them separately, each in MuJoCo's row
+  // order, is the same computation as MuJoCo's single sweep over all rows.
+  __device__ void make_islands() {
+    const int* btree = I(DI_body_tree); const int* cgbody = I(DI_cg_body); const int* pc1 = PI(DI_pair_cg1); const int* pc2 = PI(DI_pair_cg2);
+    const int* tadr = I(DI_tree_dofadr); const int* tnum = I(DI_tree_dofnum); const int* dtree = I(DI_dof_tree);
+    if (!DYN) return;
+    int ntree = dim(DD_ntree), nv = dim(DD_nv), ncon = p_misc()[MISC_NCON];
+    int* lab = p_tree_isl();
+    if (ntree == 1) {                              // one tree: one island, columns = dofs
+      if (lane == 0) { lab[0] = 0; p_tree_col0()[0] = 0; p_isl_nd()[0] = nv; p_isl_col0()[0] = 0; p_isl_col0()[1] = nv; p_misc()[MISC_NISL] = 1; }
+      if (p_col_dof()[nv - 1] != nv - 1 || p_dof_col()[nv - 1] != nv - 1) { for (int d = lane; d < nv; d += 32) { p_dof_col()[d] = d; p_col_dof()[d] = d; } }
+      sync();
+      return;
+    }
+    if (lane < ntree) lab[lane] = lane;
+    sync();
+    // lanes look their contacts' trees up in parallel; only contacts between two moving bodies reach the serial union
+    for (int c0 = 0; c0 < ncon; c0 += 32) {
+      int c = c0 + lane; int a = -1, b = -1;
+      if (c < ncon) { int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]); a = btree[cgbody[pc1[p]]]; b = btree[cgbody[pc2[p]]]; }
+      unsigned m = __ballot_sync(B2_FULL, a >= 0 && b >= 0 && a != b);
+      while (m) {
+        int src = __ffs(m) - 1; m &= m - 1;
+        int ua = __shfl_sync(B2_FULL, a, src), ub = __shfl_sync(B2_FULL, b, src);
+        if (lane == 0) {
+          while (lab[ua] != ua) ua = lab[ua];
+          while (lab[ub] != ub) ub = lab[ub];
+          if (ua != ub) lab[max(ua, ub)] = min(ua, ub);
+        }
+      }
+    }
+    sync();
+    if (lane == 0) {
+      int nisl = 0;
+      for (int t = 0; t < ntree; t++) {            // roots are the smallest tree of their set: number islands in tree order
+        int r = t; while (lab[r] != r) r = lab[r];
+        if (r == t) { p_isl_warp()[t] = nisl; p_isl_nd()[nisl] = 0; nisl++; }     // isl_warp doubles as root -> island id here
+        p_tree_col0()[t] = r;                                                       // remember the root
+      }
+      for (int t = 0; t < ntree; t++) {
+        int k = p_isl_warp()[p_tree_col0()[t]];
+        lab[t] = -1 - k;                           // final ids are written below (kept negative until every root is read)
+        p_tree_col0()[t] = p_isl_nd()[k]; p_isl_nd()[k] += tnum[t];
+      }
+      int col0 = 0;
+      for (int k = 0; k < nisl; k++) { p_isl_col0()[k] = col0; col0 += p_isl_nd()[k]; }
+      p_isl_col0()[nisl] = col0;
+      for (int t = 0; t < ntree; t++) lab[t] = -1 - lab[t];
+      p_misc()[MISC_NISL] = nisl;
+    }
+    sync();
+    for (int d = lane; d < nv; d += 32) {
+      int t = dtree[d], k = lab[t], c = p_tree_col0()[t] + (d - tadr[t]);
+      p_dof_col()[d] = c; p_col_dof()[p_isl_col0()[k] + c] = d;
+    }
+    sync();
   }
 
   // ---- B.5 rows: joint limits then pyramidal contacts, stably partitioned by island
   __device__ void make_rows(unsigned long long* counters) {
     const int* limj = I(DI_lim_jnt); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
-    const int* disl = I(DI_dof_island);
+    const int* dtree = I(DI_dof_tree);
     const float* jrange = F(DF_jnt_range); const float* jmargin = F(DF_jnt_margin);
-    int nlim = dim(DD_nlim), nisl = dim(DD_nisland), ncon = p_misc()[MISC_NCON];
+    make_islands();
+    int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON];
     if (lane < B2_MAX_ISLANDS) p_isl_n()[lane] = 0;
     sync();
     const int maxrows = B2_ISLAND_ROWS;
@@ -605,7 +694,7 @@ struct Engine {
       int j = valid ? limj[k] : 0;
       float q = p_qpos()[jq[j]], mg = jmargin[j];
       bool lo = valid && (q - jrange[2 * j] < mg), hi = valid && (jrange[2 * j + 1] - q < mg);
-      int isl = valid ? disl[jd[j]] : -1 - lane;
+      int isl = valid ? p_tree_isl()[dtree[jd[j]]] : -1 - lane;
       unsigned peers = __match_any_sync(B2_FULL, isl);
       unsigned lomask = __ballot_sync(B2_FULL, lo), himask = __ballot_sync(B2_FULL, hi);
       int before = __popc(lomask & peers & lt) + __popc(himask & peers & lt);
@@ -641,11 +730,10 @@ struct Engine {
     // island bases and arena carve-up: J (n x ldj) then packed A (n(n+1)/2); one island may spill its A to HBM
     if (lane == 0) {
       int adr = 0, used = 0, ovf = 0, cut = 0;
-      const int* inum = I(DI_island_dofnum);
       int scratch = scratch_in_arena();
       for (int k = 0; k < nisl; k++) {
         int n = min(p_isl_n()[k], maxrows);
-        int ldj = inum[k] | 1;
+        int ldj = p_isl_nd()[k] | 1;
         // rows that do not fit (row buffer, or J + packed A in what is left of the arena) are cut from the island's tail:
         // the last contacts go first, the joint limits last; every cut is counted
         int avail = arenaFloats() - scratch - used - 8;
@@ -701,18 +789,18 @@ struct Engine {
   // ---- fill J (island-dense), per-row parameters, aref, b, warm-start force
   __device__ void fill_rows() {
     const int* limj = I(DI_lim_jnt); const int* jd = I(DI_jnt_dofadr); const int* jq = I(DI_jnt_qposadr);
-    const int* disl = I(DI_dof_island); const int* cgbody = I(DI_cg_body);
+    const int* dtree = I(DI_dof_tree); const int* cgbody = I(DI_cg_body);
     const int* pc1 = PI(DI_pair_cg1); const int* pc2 = PI(DI_pair_cg2); const int* pprm = PI(DI_pair_prm);
-    const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum); const int* dbody = I(DI_dof_bodyid);
+    const int* dbody = I(DI_dof_bodyid);
     const int* ridx = I(DI_body_rootidx); const int* cmask = I(DI_body_chainmask);
     const float* jrange = F(DF_jnt_range); const float* jmargin = F(DF_jnt_margin); const float* jsol = F(DF_jnt_solprm);
     const float* dinvw = F(DF_dof_invweight0); const float* binvw = F(DF_body_invweight0); const float* prm = F(DF_prm);
-    int nlim = dim(DD_nlim), nisl = dim(DD_nisland), ncon = p_misc()[MISC_NCON], nmw = dim(DD_nmaskw);
+    int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON], nmw = dim(DD_nmaskw);
     float timestep = P.opt[DO_timestep], impratio = P.opt[DO_impratio];
     // row_info: limits  -> (joint << 2) | side ; contacts -> 0x40000000 | (contact << 2) | dir
     for (int k = tl; k < 2 * nlim; k += TEAM) {
       int r = p_lim_row()[k]; if (r < 0) continue;
-      int j = limj[k >> 1], isl = disl[jd[j]];
+      int j = limj[k >> 1], isl = p_tree_isl()[dtree[jd[j]]];
       if (r >= p_isl_n()[isl]) continue;
       p_row_info()[p_isl_adr()[isl] + r] = (j << 2) | (k & 1);
     }
@@ -726,10 +814,10 @@ struct Engine {
     // J entries
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n) continue;
-      int d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k]; float* J = p_arena() + p_isl_J()[k];
-      int e0 = p_isl_adr()[k];
+      int nd = p_isl_nd()[k], ldj = p_isl_ldj()[k]; float* J = p_arena() + p_isl_J()[k];
+      int e0 = p_isl_adr()[k]; const Cols cols = island_cols(k);
       for (int item = tl; item < n * nd; item += TEAM) {
-        int i = item / nd, c = item - i * nd, d = d0 + c;
+        int i = item / nd, c = item - i * nd, d = cols.dof(c);
         int info = p_row_info()[e0 + i]; float val = 0.f;
         if (info & 0x40000000) {
           int ci = (info >> 2) & 0x0fffffff, dir = info & 3;
@@ -772,7 +860,7 @@ struct Engine {
         solref0 = pr[7]; solref1 = pr[8]; simp = pr + 9;
       } else {
         int j = info >> 2, side = info & 1; float q = p_qpos()[jq[j]];
-        isl = disl[jd[j]];
+        isl = p_tree_isl()[dtree[jd[j]]];
         pos = side ? jrange[2 * j + 1] - q : q - jrange[2 * j]; margin = jmargin[j]; da = dinvw[jd[j]];
         solref0 = jsol[8 * j]; solref1 = jsol[8 * j + 1]; simp = jsol + 8 * j + 2;
       }
@@ -803,10 +891,10 @@ struct Engine {
         K = 1.f / fmaxf(dmax * dmax * tc * tc * solref1 * solref1, B2_MINVAL); B = 2.f / fmaxf(dmax * tc, B2_MINVAL);
       } else { K = -solref0 / (dmax * dmax); B = -solref1 / dmax; }
       // J row products with qvel, qacc_smooth, qacc_warmstart
-      int d0 = iadr[isl], nd = inum[isl], ldj = p_isl_ldj()[isl];
+      int nd = p_isl_nd()[isl], ldj = p_isl_ldj()[isl]; const Cols cols = island_cols(isl);
       const float* Jr = p_arena() + p_isl_J()[isl] + (e - p_isl_adr()[isl]) * ldj;
       float vel = 0.f, ja = 0.f, jw = 0.f;
-      for (int c = 0; c < nd; c++) { float jv = Jr[c]; vel = fmaf(jv, p_qvel()[d0 + c], vel); ja = fmaf(jv, p_qas()[d0 + c], ja); jw = fmaf(jv, p_warm()[d0 + c], jw); }
+      for (int c = 0; c < nd; c++) { float jv = Jr[c]; int d = cols.dof(c); vel = fmaf(jv, p_qvel()[d], vel); ja = fmaf(jv, p_qas()[d], ja); jw = fmaf(jv, p_warm()[d], jw); }
       float aref = -B * vel - K * imp * (pos - margin);
       p_row_R()[e] = R;
       p_row_b()[e] = ja - aref;
@@ -853,53 +941,63 @@ struct Engine {
   // phase 2: A(i, j) = J_i . x_j for all rows i >= j0, four rows at a time sharing the loads of the column.
   // Islands with more than 32 rows are built by the whole team: one warp runs phase 1, all warps split the row groups of
   // phase 2 (two team barriers per column block); small islands are built by the warp they are assigned to.
+  // the column scratch is indexed by dof (32 floats per dof of the model): islands own disjoint dofs, so warps building
+  // different islands never collide and the sparse solves need no column translation
   __device__ __forceinline__ void build_A_solve(int k, int j0, float* scratch) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
-    const int* iadr = I(DI_island_dofadr); const int* inum = I(DI_island_dofnum);
     const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
-    const float* LDp = p_LD();
-    int n = p_isl_n()[k], d0 = iadr[k], nd = inum[k], ldj = p_isl_ldj()[k];
+    const float* LDp = p_LD(); const Cols cols = island_cols(k);
+    int n = p_isl_n()[k], nd = p_isl_nd()[k], ldj = p_isl_ldj()[k];
     const float* J = p_arena() + p_isl_J()[k];
     int j = j0 + lane; bool valid = j < n;
-    float* x = scratch + lane;   // column, stride 32: lane-contiguous, conflict-free
-    for (int c = 0; c < nd; c++) x[32 * c] = valid ? J[j * ldj + c] : 0.f;
+    float* x = scratch + lane;   // x[32 * dof]: lane-contiguous, conflict-free
+    for (int c = 0; c < nd; c++) x[32 * cols.dof(c)] = valid ? J[j * ldj + c] : 0.f;
     // x <- L^-T x (gather from descendants, highest dof first), then x <- L^-1 D^-1 x (gather from ancestors):
-    // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent
+    // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent.
+    // Columns are the island's dofs (trees in order, dofs ascending), so descending columns visit descendants first.
     for (int jj = nd - 1; jj >= 0; jj--) {
-      int dn = dnum[d0 + jj]; const int* dp = dpack + dadr[d0 + jj];
-      float s0 = x[32 * jj], s1 = 0.f; int q = 0;
+      int dj = cols.dof(jj); int dn = dnum[dj]; const int* dp = dpack + dadr[dj];
+      float s0 = x[32 * dj], s1 = 0.f; int q = 0;
       for (; q + 2 <= dn; q += 2) {
         int p0 = dp[q], p1 = dp[q + 1];
-        s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * ((p1 & 0xffff) - d0)], s1);
+        s0 = fmaf(-LDp[p0 >> 16], x[32 * (p0 & 0xffff)], s0); s1 = fmaf(-LDp[p1 >> 16], x[32 * (p1 & 0xffff)], s1);
       }
-      if (q < dn) { int p0 = dp[q]; s0 = fmaf(-LDp[p0 >> 16], x[32 * ((p0 & 0xffff) - d0)], s0); }
-      x[32 * jj] = s0 + s1;
+      if (q < dn) { int p0 = dp[q]; s0 = fmaf(-LDp[p0 >> 16], x[32 * (p0 & 0xffff)], s0); }
+      x[32 * dj] = s0 + s1;
     }
     for (int i = 0; i < nd; i++) {
-      int a = madr[d0 + i], dn = ddepth[d0 + i];
-      float s0 = x[32 * i] * p_invD()[d0 + i], s1 = 0.f; int m = 1;
+      int di = cols.dof(i); int a = madr[di], dn = ddepth[di];
+      float s0 = x[32 * di] * p_invD()[di], s1 = 0.f; int m = 1;
       for (; m + 1 <= dn; m += 2) {
-        s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0); s1 = fmaf(-LDp[a + m + 1], x[32 * (mcol[a + m + 1] - d0)], s1);
+        s0 = fmaf(-LDp[a + m], x[32 * mcol[a + m]], s0); s1 = fmaf(-LDp[a + m + 1], x[32 * mcol[a + m + 1]], s1);
       }
-      if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * (mcol[a + m] - d0)], s0);
-      x[32 * i] = s0 + s1;
+      if (m <= dn) s0 = fmaf(-LDp[a + m], x[32 * mcol[a + m]], s0);
+      x[32 * di] = s0 + s1;
     }
   }
   // rows i = j0 + 4 * (g0 + gs * t), t = 0, 1, ...
   __device__ __forceinline__ void build_A_dots(int k, int j0, const float* scratch, int g0, int gs) {
-    const int* inum = I(DI_island_dofnum);
-    int n = p_isl_n()[k], nd = inum[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
-    const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k);
+    int n = p_isl_n()[k], nd = p_isl_nd()[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
+    const float* J = p_arena() + p_isl_J()[k]; float* A = island_A(k); const Cols cols = island_cols(k);
     int j = j0 + lane; bool valid = j < n;
     const float* x = scratch + lane;
     for (int i = j0 + 4 * g0; i < n; i += 4 * gs) {
       const float* J0 = J + i * ldj; const float* J1 = J + min(i + 1, n - 1) * ldj;
       const float* J2 = J + min(i + 2, n - 1) * ldj; const float* J3 = J + min(i + 3, n - 1) * ldj;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (!DYN || cols.contig) {
+        const float* xd = x + 32 * cols.d0;
 #pragma unroll 2
-      for (int c = 0; c < nd; c++) {
-        float xc = x[32 * c];
-        s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
+        for (int c = 0; c < nd; c++) {
+          float xc = xd[32 * c];
+          s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
+        }
+      } else {
+#pragma unroll 2
+        for (int c = 0; c < nd; c++) {
+          float xc = x[32 * cols.map[c]];
+          s0 = fmaf(J0[c], xc, s0); s1 = fmaf(J1[c], xc, s1); s2 = fmaf(J2[c], xc, s2); s3 = fmaf(J3[c], xc, s3);
+        }
       }
       if (valid) {
         float sv[4] = {s0, s1, s2, s3};
@@ -916,8 +1014,7 @@ struct Engine {
     }
   }
   __device__ void build_A() {
-    const int* iadr = I(DI_island_dofadr);
-    int nisl = dim(DD_nisland);
+    int nisl = p_misc()[MISC_NISL];
     // zero the tiles (rows / columns past n stay zero)
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n) continue;
@@ -930,7 +1027,7 @@ struct Engine {
     if (W > 1) {
       for (int k = 0; k < nisl; k++) {
         int n = p_isl_n()[k]; if (n <= COOPMIN) continue;
-        float* scratch = scratch_base() + 32 * iadr[k];
+        float* scratch = scratch_base();
         int turn = p_isl_warp()[k];
         for (int j0 = 0; j0 < n; j0 += 32) {
           if (wl == turn) build_A_solve(k, j0, scratch);
@@ -943,7 +1040,7 @@ struct Engine {
     }
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n || (W > 1 && n > COOPMIN) || p_isl_warp()[k] != wl) continue;
-      float* scratch = scratch_base() + 32 * iadr[k];
+      float* scratch = scratch_base();
       for (int j0 = 0; j0 < n; j0 += 32) { build_A_solve(k, j0, scratch); sync(); build_A_dots(k, j0, scratch, 0, 1); sync(); }
     }
     team_sync();
@@ -1020,7 +1117,7 @@ struct Engine {
     if (nb & 1) sweep_block(w, A, M, nb - 1, nb - 1, qa, la, qb, lb, improvement);
   }
   __device__ void solve_pgs(unsigned long long* counters) {
-    int nisl = dim(DD_nisland), iters = dim(DD_iterations);
+    int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
     float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
     float* res = p_row_res(); float* red = p_red();
     // residual r = A f + b, and warm-start acceptance: cost(f) = 1/2 f'A f + f'b > 0 -> cold start
@@ -1105,13 +1202,13 @@ struct Engine {
 
   // ---- qfrc_constraint = J' f, also copied into qacc as the right-hand side of the pass-1 solve
   __device__ void qfrc_constraint() {
-    const int* disl = I(DI_dof_island); const int* iadr = I(DI_island_dofadr);
+    const int* dtree = I(DI_dof_tree);
     int nv = dim(DD_nv);
 #pragma unroll 1
     for (int d = lane; d < nv; d += 32) {
-      int k = disl[d]; int n = p_isl_n()[k]; float s0 = 0.f, s1 = 0.f;
+      int k = p_tree_isl()[dtree[d]]; int n = p_isl_n()[k]; float s0 = 0.f, s1 = 0.f;
       if (n && p_misc()[MISC_NEFC] > 0) {
-        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = d - iadr[k]; const float* J = p_arena() + p_isl_J()[k]; const float* f = p_row_f() + e0;
+        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = p_dof_col()[d]; const float* J = p_arena() + p_isl_J()[k]; const float* f = p_row_f() + e0;
         int i = 0;
         for (; i + 2 <= n; i += 2) { s0 = fmaf(J[i * ldj + c], f[i], s0); s1 = fmaf(J[(i + 1) * ldj + c], f[i + 1], s1); }
         if (i < n) s0 = fmaf(J[i * ldj + c], f[i], s0);

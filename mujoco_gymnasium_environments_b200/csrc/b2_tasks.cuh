@@ -31,8 +31,8 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32;
-  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -171,8 +171,8 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -354,8 +354,8 @@ struct DancingTask {
 //      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
-  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false;
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -526,8 +526,8 @@ struct SoccerTask {
 //      (26 consecutive) [4] victim1_x joint (victim joints are 6 apart, y = x + 1)
 // inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
 struct RescueTask {
-  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 124, CON_CAP = 48;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true;
+  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {

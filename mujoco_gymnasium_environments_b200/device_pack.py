@@ -29,7 +29,7 @@ OPTS = ["timestep", "gx", "gy", "gz", "tolerance", "impratio", "meaninertia", "p
 INT_FIELDS = [
     "dims",
     "body_parentid", "body_rootidx", "body_jntadr", "body_jntnum", "body_dofadr", "body_dofnum", "body_lastdof",
-    "body_childadr", "body_childnum", "body_child", "body_island", "level_adr", "level_body",
+    "body_childadr", "body_childnum", "body_child", "body_island", "body_tree", "level_adr", "level_body",
     "root_bodyadr", "root_bodynum",
     "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid",
     "dof_bodyid", "dof_Madr", "dof_depth", "dof_isrot", "dof_island", "dof_tree", "dof_actadr", "dof_actnum",
@@ -89,6 +89,7 @@ def build_device_tables(m: ModelTables) -> Dict[str, np.ndarray]:
     for k in ("body_lastdof", "body_childadr", "body_childnum", "body_child", "level_adr", "level_body"):
         T[k] = i32(D[k])
     T["body_island"] = i32(body_island)
+    T["body_tree"] = i32(A["body_treeid"])          # -1 for static bodies; islands are formed per step from the active contacts
     T["root_bodyadr"] = i32(root_adr); T["root_bodynum"] = i32(root_num)
     T["jnt_type"] = i32(A["jnt_type"]); T["jnt_qposadr"] = i32(A["jnt_qposadr"]); T["jnt_dofadr"] = i32(A["jnt_dofadr"])
     T["jnt_bodyid"] = i32(A["jnt_bodyid"])
