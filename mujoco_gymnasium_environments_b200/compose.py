@@ -154,5 +154,6 @@ COMPOSERS = {
     "humanoid_dancing": lambda root: inline_mjcf("dancing", root),
     "humanoid_soccer": lambda root: inline_mjcf("soccer", root),
     "bipedal_rescue": lambda root: inline_mjcf("rescue", root),
+    "humanoid_construction": lambda root: inline_mjcf("construction", root),
 }
 

@@ -208,6 +208,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
     case TASK_HUMANOID_DANCING: return launch_task<DancingTask>(b, mode, inject, s);
     case TASK_HUMANOID_SOCCER: return launch_task<SoccerTask>(b, mode, inject, s);
     case TASK_BIPEDAL_RESCUE: return launch_task<RescueTask>(b, mode, inject, s);
+    case TASK_HUMANOID_CONSTRUCTION: return launch_task<ConstructionTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -242,7 +243,7 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
   const double* opt = flts + dm.foff[DF_opt];
   for (int k = 0; k < DO_COUNT; k++) dm.opt[k] = (float)opt[k];
   if (dm.dim[DD_integrator] != 0 && dm.dim[DD_integrator] != 1) { delete m; return fail(B2_ERR_UNSUPPORTED, "integrator must be Euler or RK4"); }
-  if (dm.dim[DD_solver] != 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "only the PGS solver is built in this round"); }
+  if (dm.dim[DD_solver] != 0 && dm.dim[DD_solver] != 2) { delete m; return fail(B2_ERR_UNSUPPORTED, "solver must be PGS or Newton"); }
   if (dm.dim[DD_ntree] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "more than 16 kinematic trees"); }
   std::vector<float> f32(n_flts);
   for (int i = 0; i < n_flts; i++) f32[i] = (float)flts[i];
@@ -271,6 +272,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
     case TASK_BIPEDAL_RESCUE: B2_TASK_DIMS(RescueTask); break;
+    case TASK_HUMANOID_CONSTRUCTION: B2_TASK_DIMS(ConstructionTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
@@ -294,7 +296,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   int raw_need = 3 * v.act_cap + 10 * v.raw_cap;
   b->dm = m->dm;
   if (cold) b->dm.n_ints_staged = m->h_ints[3];       // header word 3: where the pair tables start
-  int scratch = (32 * dim[DD_nv] <= dead_block_floats(dim, keep_frames)) ? 0 : 32 * dim[DD_nv];
+  int scratch = (dim[DD_solver] == 2 || 32 * dim[DD_nv] <= dead_block_floats(dim, keep_frames)) ? 0 : 32 * dim[DD_nv];   // Newton builds no A
   // default arena: J (rows x widest island) + tiled A for the task's typical row count, plus the A-build scratch
   int typ = arena_rows < B2_ISLAND_ROWS ? arena_rows : B2_ISLAND_ROWS;
   int span = arena_span > 0 && arena_span < maxspan ? arena_span : maxspan;      // dofs of the widest island the arena is sized for

@@ -737,16 +737,18 @@ struct Engine {
         // rows that do not fit (row buffer, or J + packed A in what is left of the arena) are cut from the island's tail:
         // the last contacts go first, the joint limits last; every cut is counted
         int avail = arenaFloats() - scratch - used - 8;
+        const bool newton = dim(DD_solver) == 2; const int ndk = p_isl_nd()[k];
         if (adr + n > rowCap()) { n = max(rowCap() - adr, 0); ovf++; }
-        if (r4(n * ldj) + a_floats(n) > avail) {
+        if (r4(n * ldj) + (newton ? newton_floats(n, ndk) : a_floats(n)) > avail) {
           float hb = (float)ldj + 2.0f;
-          int nf = avail > 0 ? (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) + 4 : 0;
-          while (nf > 0 && r4(nf * ldj) + a_floats(nf) > avail) nf--;
+          int nf = avail > 0 ? (newton ? (avail - newton_floats(0, ndk)) / (ldj + 1) : (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) + 4) : 0;
+          if (nf < 0) nf = 0;
+          while (nf > 0 && r4(nf * ldj) + (newton ? newton_floats(nf, ndk) : a_floats(nf)) > avail) nf--;
           n = min(n, nf); ovf++;
         }
         { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
         cut += min(p_isl_n()[k], maxrows) - n;
-        int needJ = r4(n * ldj), needA = a_floats(n);
+        int needJ = r4(n * ldj), needA = newton ? newton_floats(n, ndk) : a_floats(n);
         int aoff = used + needJ;
         p_isl_n()[k] = n; p_isl_adr()[k] = adr; p_isl_ldj()[k] = ldj; p_isl_J()[k] = used; p_isl_A()[k] = aoff;
         adr += n; used += needJ + (aoff >= 0 ? needA : 0);
@@ -778,7 +780,7 @@ struct Engine {
   __device__ __forceinline__ int max_span() const { return dim(DD_maxspan); }
   // A-build scratch: 32 floats per dof; in the dead block [xmat .. cinert] when it fits, else at the arena tail
   __device__ __forceinline__ int scratch_in_arena() const {
-    return (32 * dim(DD_nv) <= dead_block_floats(P.dim, B.keep_frames)) ? 0 : 32 * dim(DD_nv);
+    return (dim(DD_solver) == 2 || 32 * dim(DD_nv) <= dead_block_floats(P.dim, B.keep_frames)) ? 0 : 32 * dim(DD_nv);
   }
   __device__ __forceinline__ float* scratch_base() const {
     int sc = scratch_in_arena();
@@ -1200,6 +1202,174 @@ struct Engine {
     team_sync();
   }
 
+  // ---- Newton solver (mj_solNewton restated for the one-sided quadratic rows of limits and pyramidal contacts), one warp
+  // per island:  minimise  1/2 (a - a_s)' M (a - a_s) + sum_i 1/2 D_i min(0, J_i a - aref_i)^2  over the island's
+  // accelerations with the exact Hessian H = M + J' diag(D active) J (dense Cholesky in shared memory, nd <= 64) and an
+  // exact line search on the piecewise-quadratic cost (safeguarded Newton on its derivative).  The optimum is unique, so
+  // parity with the fp64 oracle is on the converged solution, not on the iteration path.  Leaves efc_force in row_f.
+  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return 2 * nd * nd + 9 * r4(nd) + r4(n) + 8; }
+  __device__ __noinline__ void solve_newton(unsigned long long* counters) {
+    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
+    const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
+    const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
+    int itmax = 0;
+    for (int k = 0; k < nisl; k++) {
+      const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+      const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
+      const float* J = p_arena() + p_isl_J()[k]; const Cols cols = island_cols(k);
+      float* Md = island_A(k); float* H = Md + nd * nd; float* a = H + nd * nd; float* as = a + ndp; float* fs = as + ndp;
+      float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
+      float* wrm = y + ndp; float* jv = wrm + ndp;
+      float* Dr = p_row_R() + e0; float* aref = p_row_res() + e0; float* jar = p_row_f() + e0; const float* bb = p_row_b() + e0;
+      // dense M of the island, a_smooth, qfrc_smooth, warm start
+      for (int q = lane; q < nd * nd; q += 32) Md[q] = 0.f;
+      sync();
+      for (int c = lane; c < nd; c += 32) {
+        int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
+        for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; float v = p_M()[m0 + u]; Md[c * nd + ca] = v; Md[ca * nd + c] = v; }
+        as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d];
+      }
+      sync();
+      for (int i = lane; i < n; i += 32) {
+        const float* Ji = J + i * ldj; float s = 0.f;
+        for (int c = 0; c < nd; c++) s = fmaf(Ji[c], as[c], s);
+        aref[i] = s - bb[i]; Dr[i] = 1.0f / Dr[i];
+      }
+      sync();
+      // start from the cheaper of qacc_warmstart and qacc_smooth
+      float cw = 0.f, cs = 0.f;
+      for (int i = lane; i < n; i += 32) {
+        const float* Ji = J + i * ldj; float sw = 0.f, ss = 0.f;
+        for (int c = 0; c < nd; c++) { sw = fmaf(Ji[c], wrm[c], sw); ss = fmaf(Ji[c], as[c], ss); }
+        sw -= aref[i]; ss -= aref[i];
+        if (sw < 0.f) cw += 0.5f * Dr[i] * sw * sw;
+        if (ss < 0.f) cs += 0.5f * Dr[i] * ss * ss;
+      }
+      for (int c = lane; c < nd; c += 32) {
+        float mw = 0.f;
+        for (int u = 0; u < nd; u++) mw = fmaf(Md[c * nd + u], wrm[u] - as[u], mw);
+        cw += 0.5f * mw * (wrm[c] - as[c]);
+      }
+      cw = warp_sum(cw); cs = warp_sum(cs);
+      for (int c = lane; c < nd; c += 32) a[c] = (cw < cs) ? wrm[c] : as[c];
+      sync();
+      int it = 0;
+      for (; it < iters; it++) {
+        for (int i = lane; i < n; i += 32) {
+          const float* Ji = J + i * ldj; float s = 0.f;
+          for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
+          jar[i] = s - aref[i];
+        }
+        sync();
+        float g2 = 0.f;
+        for (int c = lane; c < nd; c += 32) {
+          float m = 0.f;
+          for (int u = 0; u < nd; u++) m = fmaf(Md[c * nd + u], a[u], m);
+          float g = m - fs[c];
+          for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) g = fmaf(J[i * ldj + c], Dr[i] * x, g); }
+          Ma[c] = m; grad[c] = g; g2 = fmaf(g, g, g2);
+        }
+        g2 = warp_sum(g2);
+        if (scale * sqrtf(g2) < tol) break;
+        // H = M + J' diag(D active) J, lower triangle, then symmetric diagonal scaling H <- S H S with S = diag(H_ii^-1/2):
+        // joint inertias span six orders of magnitude (finger hinges vs the free root), which fp32 Cholesky does not survive
+        // unscaled; the scaled matrix has a unit diagonal
+        for (int q = lane; q < nd * nd; q += 32) {
+          int r = q / nd, c = q - r * nd;
+          if (c > r) continue;
+          float h = Md[q];
+          for (int i = 0; i < n; i++) if (jar[i] < 0.f) h = fmaf(J[i * ldj + r] * Dr[i], J[i * ldj + c], h);
+          H[q] = h;
+        }
+        sync();
+        for (int c = lane; c < nd; c += 32) Mv[c] = rsqrtf(fmaxf(H[c * nd + c], 1e-30f));      // Mv doubles as the scale vector here
+        sync();
+        for (int q = lane; q < nd * nd; q += 32) { int r = q / nd, c = q - r * nd; if (c <= r) H[q] *= Mv[r] * Mv[c]; }
+        sync();
+        // Cholesky H = L L' in place (right-looking; lanes over the rows below the pivot)
+        for (int p = 0; p < nd; p++) {
+          float dk = sqrtf(fmaxf(H[p * nd + p], 1e-7f)), inv = 1.0f / dk;
+          sync();
+          for (int i = p + 1 + lane; i < nd; i += 32) H[i * nd + p] *= inv;
+          if (lane == 0) H[p * nd + p] = dk;
+          sync();
+          for (int i = p + 1 + lane; i < nd; i += 32) {
+            float lip = H[i * nd + p];
+            for (int c = p + 1; c <= i; c++) H[i * nd + c] = fmaf(-lip, H[c * nd + p], H[i * nd + c]);
+          }
+          sync();
+        }
+        // search = -H^-1 grad: L y = -grad, L' s = y (one pivot per step, dot products spread over the lanes)
+        for (int r = 0; r < nd; r++) {
+          float sdot = 0.f;
+          for (int c = lane; c < r; c += 32) sdot = fmaf(H[r * nd + c], y[c], sdot);
+          sdot = warp_sum(sdot);
+          if (lane == 0) y[r] = (-grad[r] * Mv[r] - sdot) / H[r * nd + r];
+          sync();
+        }
+        for (int r = nd - 1; r >= 0; r--) {
+          float sdot = 0.f;
+          for (int c = r + 1 + lane; c < nd; c += 32) sdot = fmaf(H[c * nd + r], srch[c], sdot);
+          sdot = warp_sum(sdot);
+          if (lane == 0) srch[r] = (y[r] - sdot) / H[r * nd + r];
+          sync();
+        }
+        for (int c = lane; c < nd; c += 32) srch[c] *= Mv[c];                                   // undo the scaling: s = S (S H S)^-1 S (-g)
+        sync();
+        float q1 = 0.f, q2 = 0.f;
+        for (int c = lane; c < nd; c += 32) {
+          float m = 0.f;
+          for (int u = 0; u < nd; u++) m = fmaf(Md[c * nd + u], srch[u], m);
+          Mv[c] = m; q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], m, q2);
+        }
+        for (int i = lane; i < n; i += 32) {
+          const float* Ji = J + i * ldj; float sj = 0.f;
+          for (int c = 0; c < nd; c++) sj = fmaf(Ji[c], srch[c], sj);
+          jv[i] = sj;
+        }
+        q1 = warp_sum(q1); q2 = warp_sum(q2);
+        sync();
+        // exact minimisation along the search direction
+        float alpha = 0.f, lo = 0.f, hi = -1.f;
+        for (int ls = 0; ls < 40; ls++) {
+          float d1 = 0.f, d2 = 0.f;
+          for (int i = lane; i < n; i += 32) { float x = fmaf(alpha, jv[i], jar[i]); if (x < 0.f) { float t = Dr[i] * jv[i]; d1 = fmaf(t, x, d1); d2 = fmaf(t, jv[i], d2); } }
+          d1 = warp_sum(d1) + q1 + alpha * q2; d2 = warp_sum(d2) + q2;
+          if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
+          if (d1 < 0.f) lo = alpha; else hi = alpha;
+          float na = alpha - d1 / d2;
+          if (hi > 0.f && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+          if (na < 0.f) na = 0.f;
+          bool done = fabsf(na - alpha) < 1e-7f * (1.0f + fabsf(alpha));
+          alpha = na;
+          if (done) break;
+        }
+        float impr = 0.f;
+        for (int c = lane; c < nd; c += 32) { float da = alpha * srch[c]; a[c] += da; impr += fabsf(da); }
+        impr = warp_sum(impr);
+        sync();
+        if (impr == 0.f) { it++; break; }
+      }
+      // efc_force at the solution
+      for (int i = lane; i < n; i += 32) {
+        const float* Ji = J + i * ldj; float s = 0.f;
+        for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
+        s -= aref[i];
+        jar[i] = s < 0.f ? -Dr[i] * s : 0.f;
+      }
+      sync();
+      itmax = max(itmax, it);
+    }
+    if (lane == 0) p_red()[wl] = (float)itmax;
+    team_sync();
+    if (tl == 0) {
+      int itall = 0;
+      for (int q = 0; q < W; q++) itall = max(itall, (int)p_red()[q]);
+      p_misc()[MISC_ITERS] = itall; if (counters) atomicAdd(&counters[CTR_SOLVER_ITERS], (unsigned long long)itall);
+    }
+    team_sync();
+  }
+
   // ---- qfrc_constraint = J' f, also copied into qacc as the right-hand side of the pass-1 solve
   __device__ void qfrc_constraint() {
     const int* dtree = I(DI_dof_tree);
@@ -1296,7 +1466,12 @@ struct Engine {
               if (wl == 2) factor(h, true);
             }
           } else if (pass == 1) {
-            if (p_misc()[MISC_NEFC] > 0) { fill_rows(); B2_TICK(9); build_A(); B2_TICK(10); solve_pgs(counters); B2_TICK(11); }
+            if (p_misc()[MISC_NEFC] > 0) {
+              fill_rows(); B2_TICK(9);
+              if (dim(DD_solver) == 2) solve_newton(counters);
+              else { build_A(); B2_TICK(10); solve_pgs(counters); }
+              B2_TICK(11);
+            }
             else if (tl == 0) p_misc()[MISC_ITERS] = 0;
             if (wl == 0) qfrc_constraint();
           } else {

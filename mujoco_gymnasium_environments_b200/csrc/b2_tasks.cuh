@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4, TASK_HUMANOID_CONSTRUCTION = 5 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -667,6 +667,85 @@ struct RescueTask {
     *terminated = term; *truncated = ti[0] >= MAX_STEPS;
     { float dx = rx - tf[4], dy = ry - tf[5]; tf[6] += sqrtf(dx * dx + dy * dy); }
     tf[4] = rx; tf[5] = ry;
+    return reward;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ humanoid construction
+// humanoid_construction_env/construction_env.py: reset :547-584, step :586-623, _get_observation :625-659,
+// _calculate_reward :661-700, _update_task_progress :702-719, _check_terminated :721-737.  RK4 at 2 ms,
+// MuJoCo's default solver (Newton, 100 iterations, 1e-8).  The observation has 135 entries (the reference declares 125,
+// SURVEY F11) and is taken after reward / termination; reset neither settles nor calls mj_forward.
+// ti: [0] current_step [1] current_task (0 stack_blocks, 1 operate_crane, 2 transport_material, 3 build_structure)
+//     [2] episode id [3] tasks_completed
+// tf: [0] total_reward [1] task_progress [2] wind_strength [3] rain_intensity [4] temperature
+// ids: [0] humanoid body      inject: task index, wind, rain, temperature
+struct ConstructionTask {
+  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 64, ARENA_SPAN = 40;
+  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
+      act_clipped[i] = a; E.p_ctrl()[i] = a;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView& B, int env, int* ti, float* tf,
+                                     const float* inject) {
+    E.reset_data();
+    if (E.lane == 0) {
+      unsigned ep = (unsigned)ti[2]; unsigned ge = (unsigned)(B.env_offset + env);
+      auto draw = [&](int k, float lo, float hi) { return inject ? inject[k] : lo + (hi - lo) * rng_uniform(B.seed, ge, ep, (unsigned)k); };
+      ti[0] = 0; ti[1] = inject ? (int)inject[0] : min(3, (int)(4.0f * rng_uniform(B.seed, ge, ep, 0))); ti[2] = (int)(ep + 1);
+      tf[0] = 0.f; tf[1] = 0.f; tf[2] = draw(1, 0.f, 5.f); tf[3] = draw(2, 0.f, 0.5f); tf[4] = draw(3, 15.f, 35.f);
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  // current_step += 1 and _update_task_progress precede the reward (:597-600)
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams&, int* ti, float* tf) {
+    if (E.lane == 0) {
+      ti[0] += 1;
+      float pr = 0.f;
+      if (ti[1] == 1) pr = fminf(1.0f, (float)ti[0] / 500.0f); else if (ti[1] == 2) pr = fminf(1.0f, (float)ti[0] / 300.0f);
+      tf[1] = pr;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void observe(EN& E, const TaskParams&, float* obs) {
+    const int* ti = E.p_ti(); const float* tf = E.p_tf();
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 30) v = E.p_qpos()[i];
+      else if (i < 60) v = E.p_qvel()[i - 30];
+      else if (i >= 90 && i < 94) v = (ti[1] == i - 90) ? 1.f : 0.f;
+      else if (i == 94) v = tf[1];
+      else if (i == 100) v = tf[2] / 10.0f;
+      else if (i == 101) v = tf[3];
+      else if (i == 102) v = tf[4] / 50.0f;
+      else if (i == 110) v = 1.0f;
+      obs[i] = v;
+    }
+  }
+  // the kernel observes before this hook; the reference observes after it, but nothing the observation reads changes here
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    float reward = 0.f;
+    if (ti[1] == 0) reward += tf[1] * 500.0f; else if (ti[1] == 1) reward += 20.0f; else if (ti[1] == 2) reward += 30.0f; else reward += tf[1] * 100.0f;
+    reward += 1.0f;
+    float s = 0.f;
+    for (int i = 0; i < ACT; i++) s += fabsf(act[i]);
+    reward += -0.2f * s;
+    float z = E.p_xpos()[3 * tp.ids[0] + 2];
+    reward += z > 1.0f ? 5.0f : -2000.0f;
+    int term = 0;
+    if (z < 0.5f) term = 1;
+    else if (tf[1] >= 1.0f) { ti[3] += 1; term = 1; }
+    *terminated = term; *truncated = ti[0] >= MAX_STEPS;
+    tf[0] += reward;
     return reward;
   }
 };

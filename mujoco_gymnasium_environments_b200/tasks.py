@@ -157,6 +157,16 @@ def _rescue_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- humanoid construction
+def _construction_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_HUMANOID_CONSTRUCTION
+    d.ids[0] = t.name2id("body", "humanoid")             # construction_env.py:512
+    for k in range(33):
+        d.act_lo[k] = -200.0; d.act_hi[k] = 200.0
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -186,4 +196,11 @@ TASKS: Dict[str, TaskSpec] = {
         observation_space=lambda t: Box(np.full(102, -np.inf, np.float32), np.full(102, np.inf, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "robot_position", "victims_remaining", "victims_carried", "energy_remaining",
                    "robot_upright"]),
+    "humanoid_construction": TaskSpec(
+        name="humanoid_construction", task_id=capi.TASK_HUMANOID_CONSTRUCTION, obs_dim=135, act_dim=33, max_episode_steps=3000,
+        frame_skip=1, render_fps=50, bytes_per_env_step=3222, describe=_construction_desc,
+        action_space=lambda t: Box(np.full(33, -200.0, np.float32), np.full(33, 200.0, np.float32), dtype=np.float32),
+        # the reference declares 125 entries but returns 135: the actual length is exposed
+        observation_space=lambda t: Box(np.full(135, -np.inf, np.float32), np.full(135, np.inf, np.float32), dtype=np.float32),
+        info_keys=["task", "task_progress", "blocks_placed", "safety_violations", "episode_stats", "weather"]),
 }

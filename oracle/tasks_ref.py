@@ -802,5 +802,101 @@ class BipedalRescueRef:
         return False
 
 
+class HumanoidConstructionRef:
+    """humanoid_construction_env/construction_env.py restated: __init__ :32-153, reset :547-584, step :586-623,
+    _get_observation :625-659, _calculate_reward :661-700, _update_task_progress :702-719, _check_terminated :721-737."""
+
+    TASK_TYPES = ["stack_blocks", "operate_crane", "transport_material", "build_structure"]
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("humanoid_construction")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.max_episode_steps = 3000; self.current_step = 0
+        self.max_blocks = 20; self.blocks_placed = 0; self.safety_violations = 0; self.hard_hat_on = True
+        self.current_task = None; self.task_progress = 0.0
+        self.wind_strength = 0.0; self.rain_intensity = 0.0; self.temperature = 20.0
+        self.humanoid_id = t.name2id("body", "humanoid")
+        self.action_low = np.full(33, -200.0); self.action_high = np.full(33, 200.0)
+        self.episode_stats = dict(tasks_completed=0, total_reward=0.0)
+        self.np_random = np.random.default_rng(seed)
+
+    def reset(self, seed=None, draws=None):
+        if seed is not None:
+            self.np_random = np.random.default_rng(seed)
+        ref.mj_resetData(self.model, self.data)
+        self.current_step = 0; self.blocks_placed = 0; self.safety_violations = 0
+        if draws is None:
+            draws = (int(self.np_random.integers(0, 4)), self.np_random.uniform(0, 5), self.np_random.uniform(0, 0.5), self.np_random.uniform(15, 35))
+        self.current_task = self.TASK_TYPES[int(draws[0])]
+        self.task_progress = 0.0
+        self.episode_stats = dict(tasks_completed=0, total_reward=0.0)
+        self.wind_strength = float(draws[1]); self.rain_intensity = float(draws[2]); self.temperature = float(draws[3])
+        return self._get_observation(), dict(task=self.current_task)
+
+    def step(self, action):
+        d = self.data
+        action = np.clip(np.asarray(action, np.float64), self.action_low, self.action_high)
+        d.ctrl[:] = action
+        ref.mj_step(self.model, d)
+        self.current_step += 1
+        self._update_task_progress()
+        reward = self._calculate_reward(action)
+        terminated = self._check_terminated()
+        truncated = self.current_step >= self.max_episode_steps
+        obs = self._get_observation()
+        self.episode_stats["total_reward"] += reward
+        return obs, reward, terminated, truncated, dict(task=self.current_task, task_progress=self.task_progress)
+
+    def _get_observation(self):
+        d = self.data
+        obs = []
+        obs.extend(d.qpos[:30]); obs.extend(d.qvel[:30]); obs.extend([0.0] * 30)
+        one = [0.0] * 4; one[self.TASK_TYPES.index(self.current_task)] = 1.0
+        obs.extend(one); obs.append(self.task_progress); obs.extend([0.0] * 5)
+        obs.append(self.wind_strength / 10.0); obs.append(self.rain_intensity); obs.append(self.temperature / 50.0)
+        obs.extend([0.0] * 7); obs.append(float(self.hard_hat_on)); obs.append(float(self.safety_violations) / 10.0)
+        obs.extend([0.0] * 3); obs.append(float(self.blocks_placed) / self.max_blocks); obs.extend([0.0] * 19)
+        return np.array(obs, dtype=np.float32)
+
+    def _calculate_reward(self, action):
+        reward = 0.0
+        if self.current_task == "stack_blocks":
+            reward += self.task_progress * 500.0
+        elif self.current_task == "operate_crane":
+            reward += 200.0 * 0.1
+        elif self.current_task == "transport_material":
+            reward += 300.0 * 0.1
+        else:
+            reward += self.task_progress * 100
+        if self.hard_hat_on:
+            reward += 100.0 * 0.01
+        reward -= self.safety_violations * 100
+        reward += -0.2 * float(np.sum(np.abs(action)))
+        z = self.data.xpos[self.humanoid_id][2]
+        reward += 50.0 * 0.1 if z > 1.0 else -2000.0
+        return float(reward)
+
+    def _update_task_progress(self):
+        if self.current_task == "stack_blocks":
+            self.task_progress = min(1.0, self.blocks_placed / 5)
+        elif self.current_task == "operate_crane":
+            self.task_progress = min(1.0, self.current_step / 500)
+        elif self.current_task == "transport_material":
+            self.task_progress = min(1.0, self.current_step / 300)
+        else:
+            self.task_progress = min(1.0, self.blocks_placed / 10)
+
+    def _check_terminated(self):
+        if self.data.xpos[self.humanoid_id][2] < 0.5:
+            return True
+        if self.task_progress >= 1.0:
+            self.episode_stats["tasks_completed"] += 1
+            return True
+        return self.safety_violations > 3
+
+
+
 TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef,
-         "bipedal_rescue": BipedalRescueRef}
+         "bipedal_rescue": BipedalRescueRef, "humanoid_construction": HumanoidConstructionRef}

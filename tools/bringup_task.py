@@ -37,6 +37,10 @@ def make_inject(task, rng, n):
         inj = np.zeros((n, 12), np.float32)
         inj[:, 0:2] = rng.uniform(-5, 5, (n, 2)); inj[:, 2:] = rng.uniform(-1, 1, (n, 10))
         return inj
+    if task == "humanoid_construction":
+        inj = np.zeros((n, 4), np.float32)
+        inj[:, 0] = rng.integers(0, 4, n); inj[:, 1] = rng.uniform(0, 5, n); inj[:, 2] = rng.uniform(0, .5, n); inj[:, 3] = rng.uniform(15, 35, n)
+        return inj
     raise KeyError(task)
 
 
@@ -47,6 +51,8 @@ def ref_reset(task, env, inj):
         return env.reset(sequence=[(int(inj[2 * k]), float(inj[2 * k + 1])) for k in range(20)])
     if task in ("humanoid_soccer", "bipedal_rescue"):
         return env.reset(draws=[float(x) for x in inj])
+    if task == "humanoid_construction":
+        return env.reset(draws=tuple(float(x) for x in inj))
 
 
 def main():
@@ -133,7 +139,7 @@ def main():
     print("stats", env.episode_stats())
     env.close()
     # ---------------- throughput
-    for N in ((2048,) if task == "bipedal_rescue" else (4096, 8192)):
+    for N in ((2048,) if task in ("bipedal_rescue", "humanoid_construction") else (4096, 8192)):
         for sc in (0.02, 1.0):
             env = B200VectorEnv(task, N, device=0, seed=1)
             env.reset()
