@@ -1207,7 +1207,30 @@ struct Engine {
   // accelerations with the exact Hessian H = M + J' diag(D active) J (dense Cholesky in shared memory, nd <= 64) and an
   // exact line search on the piecewise-quadratic cost (safeguarded Newton on its derivative).  The optimum is unique, so
   // parity with the fp64 oracle is on the converged solution, not on the iteration path.  Leaves efc_force in row_f.
-  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return 2 * nd * nd + 9 * r4(nd) + r4(n) + 8; }
+#ifndef B2_NEWTON_RTOL
+#define B2_NEWTON_RTOL 1e-6f
+#endif
+#ifndef B2_NEWTON_AFLOOR
+#define B2_NEWTON_AFLOOR 1.0f
+#endif
+  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
+  // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
+  // shared-memory atomics (one warp, <= a few hundred entries)
+  __device__ __forceinline__ void newton_mulM(const Cols& cols, int nd, const float* x, float* y) {
+    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
+    for (int c = lane; c < nd; c += 32) y[c] = 0.f;
+    sync();
+    for (int c = lane; c < nd; c += 32) {
+      int d = cols.dof(c), m0 = madr[d], dep = ddepth[d]; float xc = x[c], s = 0.f;
+      for (int u = 0; u <= dep; u++) {
+        int ca = p_dof_col()[mcol[m0 + u]]; float v = p_M()[m0 + u];
+        s = fmaf(v, x[ca], s);
+        if (ca != c) atomicAdd(&y[ca], v * xc);
+      }
+      atomicAdd(&y[c], s);
+    }
+    sync();
+  }
   __device__ __noinline__ void solve_newton(unsigned long long* counters) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
@@ -1215,28 +1238,25 @@ struct Engine {
     int itmax = 0;
     for (int k = 0; k < nisl; k++) {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
-      const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k];
+      const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
       const float* J = p_arena() + p_isl_J()[k]; const Cols cols = island_cols(k);
-      float* Md = island_A(k); float* H = Md + nd * nd; float* a = H + nd * nd; float* as = a + ndp; float* fs = as + ndp;
+      float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;   // H: packed lower triangle
       float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
       float* wrm = y + ndp; float* jv = wrm + ndp;
       float* Dr = p_row_R() + e0; float* aref = p_row_res() + e0; float* jar = p_row_f() + e0; const float* bb = p_row_b() + e0;
-      // dense M of the island, a_smooth, qfrc_smooth, warm start
-      for (int q = lane; q < nd * nd; q += 32) Md[q] = 0.f;
+      for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d]; }
       sync();
-      for (int c = lane; c < nd; c += 32) {
-        int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
-        for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; float v = p_M()[m0 + u]; Md[c * nd + ca] = v; Md[ca * nd + c] = v; }
-        as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d];
-      }
-      sync();
+      // D = 1/R, capped at 1e8: MuJoCo floors R at 1e-15 (a body that cannot move along the row), and a penalty that
+      // stiff puts J'D(Ja - aref) below fp32 resolution; the cap changes the constrained acceleration by <= force * 1e-8
       for (int i = lane; i < n; i += 32) {
         const float* Ji = J + i * ldj; float s = 0.f;
         for (int c = 0; c < nd; c++) s = fmaf(Ji[c], as[c], s);
-        aref[i] = s - bb[i]; Dr[i] = 1.0f / Dr[i];
+        aref[i] = s - bb[i]; Dr[i] = fminf(1.0f / Dr[i], 1e8f);
       }
-      sync();
       // start from the cheaper of qacc_warmstart and qacc_smooth
+      for (int c = lane; c < nd; c += 32) y[c] = wrm[c] - as[c];
+      sync();
+      newton_mulM(cols, nd, y, Mv);
       float cw = 0.f, cs = 0.f;
       for (int i = lane; i < n; i += 32) {
         const float* Ji = J + i * ldj; float sw = 0.f, ss = 0.f;
@@ -1245,14 +1265,11 @@ struct Engine {
         if (sw < 0.f) cw += 0.5f * Dr[i] * sw * sw;
         if (ss < 0.f) cs += 0.5f * Dr[i] * ss * ss;
       }
-      for (int c = lane; c < nd; c += 32) {
-        float mw = 0.f;
-        for (int u = 0; u < nd; u++) mw = fmaf(Md[c * nd + u], wrm[u] - as[u], mw);
-        cw += 0.5f * mw * (wrm[c] - as[c]);
-      }
+      for (int c = lane; c < nd; c += 32) cw += 0.5f * Mv[c] * y[c];
       cw = warp_sum(cw); cs = warp_sum(cs);
       for (int c = lane; c < nd; c += 32) a[c] = (cw < cs) ? wrm[c] : as[c];
       sync();
+      newton_mulM(cols, nd, a, Ma);
       int it = 0;
       for (; it < iters; it++) {
         for (int i = lane; i < n; i += 32) {
@@ -1263,65 +1280,67 @@ struct Engine {
         sync();
         float g2 = 0.f;
         for (int c = lane; c < nd; c += 32) {
-          float m = 0.f;
-          for (int u = 0; u < nd; u++) m = fmaf(Md[c * nd + u], a[u], m);
-          float g = m - fs[c];
+          float g = Ma[c] - fs[c];
           for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) g = fmaf(J[i * ldj + c], Dr[i] * x, g); }
-          Ma[c] = m; grad[c] = g; g2 = fmaf(g, g, g2);
+          grad[c] = g; g2 = fmaf(g, g, g2);
         }
         g2 = warp_sum(g2);
         if (scale * sqrtf(g2) < tol) break;
         // H = M + J' diag(D active) J, lower triangle, then symmetric diagonal scaling H <- S H S with S = diag(H_ii^-1/2):
-        // joint inertias span six orders of magnitude (finger hinges vs the free root), which fp32 Cholesky does not survive
+        // joint inertias span orders of magnitude (finger hinges vs the crane), which fp32 Cholesky does not survive
         // unscaled; the scaled matrix has a unit diagonal
-        for (int q = lane; q < nd * nd; q += 32) {
-          int r = q / nd, c = q - r * nd;
-          if (c > r) continue;
-          float h = Md[q];
+        for (int q = lane; q < nh; q += 32) {
+          int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+          while (r * (r + 1) / 2 > q) r--;
+          while ((r + 1) * (r + 2) / 2 <= q) r++;
+          int c = q - r * (r + 1) / 2; float h = 0.f;
           for (int i = 0; i < n; i++) if (jar[i] < 0.f) h = fmaf(J[i * ldj + r] * Dr[i], J[i * ldj + c], h);
           H[q] = h;
         }
         sync();
-        for (int c = lane; c < nd; c += 32) Mv[c] = rsqrtf(fmaxf(H[c * nd + c], 1e-30f));      // Mv doubles as the scale vector here
+        for (int c = lane; c < nd; c += 32) {
+          int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
+          for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); H[r * (r + 1) / 2 + cc] += p_M()[m0 + u]; }
+        }
         sync();
-        for (int q = lane; q < nd * nd; q += 32) { int r = q / nd, c = q - r * nd; if (c <= r) H[q] *= Mv[r] * Mv[c]; }
+        for (int c = lane; c < nd; c += 32) Mv[c] = rsqrtf(fmaxf(H[c * (c + 1) / 2 + c], 1e-30f));   // Mv doubles as the scale vector here
+        sync();
+        for (int r = 0; r < nd; r++) { float sr = Mv[r]; float* Hr = H + r * (r + 1) / 2; for (int c = lane; c <= r; c += 32) Hr[c] *= sr * Mv[c]; }
         sync();
         // Cholesky H = L L' in place (right-looking; lanes over the rows below the pivot)
         for (int p = 0; p < nd; p++) {
-          float dk = sqrtf(fmaxf(H[p * nd + p], 1e-7f)), inv = 1.0f / dk;
+          const int pp = p * (p + 1) / 2;
+          float dk = sqrtf(fmaxf(H[pp + p], 1e-7f)), inv = 1.0f / dk;
           sync();
-          for (int i = p + 1 + lane; i < nd; i += 32) H[i * nd + p] *= inv;
-          if (lane == 0) H[p * nd + p] = dk;
+          for (int i = p + 1 + lane; i < nd; i += 32) H[i * (i + 1) / 2 + p] *= inv;
+          if (lane == 0) H[pp + p] = dk;
           sync();
           for (int i = p + 1 + lane; i < nd; i += 32) {
-            float lip = H[i * nd + p];
-            for (int c = p + 1; c <= i; c++) H[i * nd + c] = fmaf(-lip, H[c * nd + p], H[i * nd + c]);
+            float* Hi = H + i * (i + 1) / 2; float lip = Hi[p];
+            for (int c = p + 1; c <= i; c++) Hi[c] = fmaf(-lip, H[c * (c + 1) / 2 + p], Hi[c]);
           }
           sync();
         }
         // search = -H^-1 grad: L y = -grad, L' s = y (one pivot per step, dot products spread over the lanes)
         for (int r = 0; r < nd; r++) {
-          float sdot = 0.f;
-          for (int c = lane; c < r; c += 32) sdot = fmaf(H[r * nd + c], y[c], sdot);
+          const float* Hr = H + r * (r + 1) / 2; float sdot = 0.f;
+          for (int c = lane; c < r; c += 32) sdot = fmaf(Hr[c], y[c], sdot);
           sdot = warp_sum(sdot);
-          if (lane == 0) y[r] = (-grad[r] * Mv[r] - sdot) / H[r * nd + r];
+          if (lane == 0) y[r] = (-grad[r] * Mv[r] - sdot) / Hr[r];
           sync();
         }
         for (int r = nd - 1; r >= 0; r--) {
           float sdot = 0.f;
-          for (int c = r + 1 + lane; c < nd; c += 32) sdot = fmaf(H[c * nd + r], srch[c], sdot);
+          for (int c = r + 1 + lane; c < nd; c += 32) sdot = fmaf(H[c * (c + 1) / 2 + r], srch[c], sdot);
           sdot = warp_sum(sdot);
-          if (lane == 0) srch[r] = (y[r] - sdot) / H[r * nd + r];
+          if (lane == 0) srch[r] = (y[r] - sdot) / H[r * (r + 1) / 2 + r];
           sync();
         }
         for (int c = lane; c < nd; c += 32) srch[c] *= Mv[c];                                   // undo the scaling: s = S (S H S)^-1 S (-g)
         sync();
+        newton_mulM(cols, nd, srch, Mv);
         float q1 = 0.f, q2 = 0.f;
-        for (int c = lane; c < nd; c += 32) {
-          float m = 0.f;
-          for (int u = 0; u < nd; u++) m = fmaf(Md[c * nd + u], srch[u], m);
-          Mv[c] = m; q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], m, q2);
-        }
+        for (int c = lane; c < nd; c += 32) { q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], Mv[c], q2); }
         for (int i = lane; i < n; i += 32) {
           const float* Ji = J + i * ldj; float sj = 0.f;
           for (int c = 0; c < nd; c++) sj = fmaf(Ji[c], srch[c], sj);
@@ -1337,6 +1356,7 @@ struct Engine {
           d1 = warp_sum(d1) + q1 + alpha * q2; d2 = warp_sum(d2) + q2;
           if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
           if (d1 < 0.f) lo = alpha; else hi = alpha;
+          if (!(d2 > 0.f)) break;
           float na = alpha - d1 / d2;
           if (hi > 0.f && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
           if (na < 0.f) na = 0.f;
@@ -1344,20 +1364,33 @@ struct Engine {
           alpha = na;
           if (done) break;
         }
-        float impr = 0.f;
-        for (int c = lane; c < nd; c += 32) { float da = alpha * srch[c]; a[c] += da; impr += fabsf(da); }
-        impr = warp_sum(impr);
+        // fp32 termination: the step no longer moves any acceleration by more than 1e-6 of the largest one (the gradient
+        // test above cannot fire once the stiff rows' rounding noise exceeds the tolerance)
+        float dmx = 0.f, amx = B2_NEWTON_AFLOOR;
+        for (int c = lane; c < nd; c += 32) { float da = alpha * srch[c]; a[c] += da; Ma[c] = fmaf(alpha, Mv[c], Ma[c]); dmx = fmaxf(dmx, fabsf(da)); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { dmx = fmaxf(dmx, __shfl_xor_sync(0xffffffffu, dmx, o)); amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o)); }
         sync();
-        if (impr == 0.f) { it++; break; }
+#ifdef B2_NEWTON_DEBUG
+        if (it >= iters - 6 && lane == 0) printf("newton blk %d wb %d isl %d nd %d n %d it %d |g| %.4g alpha %.6g dmx %.4g amx %.4g q1 %.4g q2 %.4g\n", (int)blockIdx.x, wb, k, nd, n, it, sqrtf(g2), alpha, dmx, amx, q1, q2);
+#endif
+        if (dmx <= B2_NEWTON_RTOL * amx) { it++; break; }
       }
-      // efc_force at the solution
+      // efc_force at the solution (reporting only: a stiff row's force is below fp32 resolution of J a - aref).  The
+      // constraint force that drives the step comes from the optimality condition instead, qfrc_constraint =
+      // M a - qfrc_smooth = M (a - a_smooth), which is accurate to fp32 in a whatever the row stiffness.
       for (int i = lane; i < n; i += 32) {
         const float* Ji = J + i * ldj; float s = 0.f;
         for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
         s -= aref[i];
         jar[i] = s < 0.f ? -Dr[i] * s : 0.f;
       }
+      for (int c = lane; c < nd; c += 32) y[c] = a[c] - as[c];
       sync();
+      newton_mulM(cols, nd, y, Mv);
+      for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); p_qfc()[d] = Mv[c]; p_qacc()[d] = Mv[c]; }
+      sync();
+      if (it >= iters && lane == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
       itmax = max(itmax, it);
     }
     if (lane == 0) p_red()[wl] = (float)itmax;
@@ -1371,13 +1404,14 @@ struct Engine {
   }
 
   // ---- qfrc_constraint = J' f, also copied into qacc as the right-hand side of the pass-1 solve
-  __device__ void qfrc_constraint() {
+  __device__ void qfrc_constraint(bool newton) {
     const int* dtree = I(DI_dof_tree);
     int nv = dim(DD_nv);
 #pragma unroll 1
     for (int d = lane; d < nv; d += 32) {
       int k = p_tree_isl()[dtree[d]]; int n = p_isl_n()[k]; float s0 = 0.f, s1 = 0.f;
-      if (n && p_misc()[MISC_NEFC] > 0) {
+      if (newton) { if (n && p_misc()[MISC_NEFC] > 0) continue; }
+      else if (n && p_misc()[MISC_NEFC] > 0) {
         int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = p_dof_col()[d]; const float* J = p_arena() + p_isl_J()[k]; const float* f = p_row_f() + e0;
         int i = 0;
         for (; i + 2 <= n; i += 2) { s0 = fmaf(J[i * ldj + c], f[i], s0); s1 = fmaf(J[(i + 1) * ldj + c], f[i + 1], s1); }
@@ -1473,7 +1507,7 @@ struct Engine {
               B2_TICK(11);
             }
             else if (tl == 0) p_misc()[MISC_ITERS] = 0;
-            if (wl == 0) qfrc_constraint();
+            if (wl == 0) qfrc_constraint(dim(DD_solver) == 2);
           } else {
             if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
           }
