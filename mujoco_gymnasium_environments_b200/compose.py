@@ -133,16 +133,41 @@ def inline_mjcf(task: str, root: str) -> str:
     _install_stubs()
     sys.path.insert(0, os.path.join(root, pkg))
     cwd = os.getcwd()
-    os.chdir("/tmp")          # martial arts rewrites an asset file relative to its module; keep our tree clean
+    os.chdir("/tmp")
+    # martial arts writes its scene to <module dir>/assets/martial_arts_scene.xml and reads it back before building the
+    # model (martial_arts_env.py:379-381, 134-148); the reference tree is read-only, so writes under it go to memory
+    import builtins, io
+    real_open, real_makedirs, written = builtins.open, os.makedirs, {}
+
+    class _MemFile(io.StringIO):
+        def __init__(self, path): super().__init__(); self._path = path
+        def close(self): written[self._path] = self.getvalue(); super().close()
+
+    def mem_open(path, mode="r", *a, **k):
+        ap = os.path.abspath(path) if isinstance(path, (str, os.PathLike)) else path
+        if isinstance(ap, str) and ap.startswith(os.path.abspath(root)):
+            if "w" in mode:
+                return _MemFile(ap)
+            if ap in written:
+                return io.StringIO(written[ap])
+        return real_open(path, mode, *a, **k)
+
+    def mem_makedirs(path, *a, **k):
+        if os.path.abspath(path).startswith(os.path.abspath(root)):
+            return None
+        return real_makedirs(path, *a, **k)
+
+    builtins.open, os.makedirs = mem_open, mem_makedirs
     try:
         m = importlib.import_module(mod)
         try:
             getattr(m, cls)()
         except _Captured as c:
             return c.xml
-        except OSError as e:   # read-only reference tree: martial arts writes its scene file before loading it
+        except OSError as e:
             raise RuntimeError(f"{task}: constructor failed before the model was built: {e}")
     finally:
+        builtins.open, os.makedirs = real_open, real_makedirs
         os.chdir(cwd)
         sys.path.pop(0)
     raise RuntimeError(f"{task}: constructor finished without building a model")
@@ -155,5 +180,6 @@ COMPOSERS = {
     "humanoid_soccer": lambda root: inline_mjcf("soccer", root),
     "bipedal_rescue": lambda root: inline_mjcf("rescue", root),
     "humanoid_construction": lambda root: inline_mjcf("construction", root),
+    "humanoid_martial_arts": lambda root: inline_mjcf("martial_arts", root),
 }
 

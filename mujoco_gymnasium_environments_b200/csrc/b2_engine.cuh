@@ -1211,7 +1211,10 @@ struct Engine {
 #define B2_NEWTON_RTOL 1e-6f
 #endif
 #ifndef B2_NEWTON_AFLOOR
-#define B2_NEWTON_AFLOOR 1.0f
+#define B2_NEWTON_AFLOOR 10.0f
+#endif
+#ifndef B2_NEWTON_NOISE
+#define B2_NEWTON_NOISE 5e-7f
 #endif
   __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
   // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
@@ -1336,7 +1339,8 @@ struct Engine {
           if (lane == 0) srch[r] = (y[r] - sdot) / H[r * (r + 1) / 2 + r];
           sync();
         }
-        for (int c = lane; c < nd; c += 32) srch[c] *= Mv[c];                                   // undo the scaling: s = S (S H S)^-1 S (-g)
+        // undo the scaling, s = S (S H S)^-1 S (-g); y <- fp32 noise floor of each acceleration, (|f_smooth| + |M a|) / H_cc
+        for (int c = lane; c < nd; c += 32) { float sc = Mv[c]; srch[c] *= sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); }
         sync();
         newton_mulM(cols, nd, srch, Mv);
         float q1 = 0.f, q2 = 0.f;
@@ -1351,9 +1355,12 @@ struct Engine {
         // exact minimisation along the search direction
         float alpha = 0.f, lo = 0.f, hi = -1.f;
         for (int ls = 0; ls < 40; ls++) {
-          float d1 = 0.f, d2 = 0.f;
-          for (int i = lane; i < n; i += 32) { float x = fmaf(alpha, jv[i], jar[i]); if (x < 0.f) { float t = Dr[i] * jv[i]; d1 = fmaf(t, x, d1); d2 = fmaf(t, jv[i], d2); } }
+          float d1 = 0.f, d2 = 0.f, dn = 0.f;
+          for (int i = lane; i < n; i += 32) { float x = fmaf(alpha, jv[i], jar[i]); if (x < 0.f) { float t = Dr[i] * jv[i]; d1 = fmaf(t, x, d1); d2 = fmaf(t, jv[i], d2); dn += fabsf(t * x); } }
           d1 = warp_sum(d1) + q1 + alpha * q2; d2 = warp_sum(d2) + q2;
+          // a slope at alpha = 0 that is below the rounding noise of its own terms carries no information: take the plain
+          // Newton step (the direction is noise-sized too) instead of searching on noise
+          if (ls == 0) { dn = warp_sum(dn); if (fabsf(d1) <= 2.4e-7f * (dn + fabsf(q1))) { alpha = 1.0f; break; } }
           if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
           if (d1 < 0.f) lo = alpha; else hi = alpha;
           if (!(d2 > 0.f)) break;
@@ -1364,17 +1371,20 @@ struct Engine {
           alpha = na;
           if (done) break;
         }
-        // fp32 termination: the step no longer moves any acceleration by more than 1e-6 of the largest one (the gradient
-        // test above cannot fire once the stiff rows' rounding noise exceeds the tolerance)
-        float dmx = 0.f, amx = B2_NEWTON_AFLOOR;
-        for (int c = lane; c < nd; c += 32) { float da = alpha * srch[c]; a[c] += da; Ma[c] = fmaf(alpha, Mv[c], Ma[c]); dmx = fmaxf(dmx, fabsf(da)); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
+        // fp32 termination: no acceleration moves by more than 1e-6 of the island's largest one plus its own rounding
+        // floor (the gradient test above cannot fire once the stiff rows' rounding noise exceeds the tolerance)
+        float amx = B2_NEWTON_AFLOOR;
+        for (int c = lane; c < nd; c += 32) { a[c] = fmaf(alpha, srch[c], a[c]); Ma[c] = fmaf(alpha, Mv[c], Ma[c]); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) { dmx = fmaxf(dmx, __shfl_xor_sync(0xffffffffu, dmx, o)); amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o)); }
+        for (int o = 16; o; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+        bool moving = false;
+        for (int c = lane; c < nd; c += 32) moving |= fabsf(alpha * srch[c]) > fmaf(B2_NEWTON_RTOL, amx, B2_NEWTON_NOISE * y[c]);
+        moving = __any_sync(0xffffffffu, moving);
         sync();
 #ifdef B2_NEWTON_DEBUG
-        if (it >= iters - 6 && lane == 0) printf("newton blk %d wb %d isl %d nd %d n %d it %d |g| %.4g alpha %.6g dmx %.4g amx %.4g q1 %.4g q2 %.4g\n", (int)blockIdx.x, wb, k, nd, n, it, sqrtf(g2), alpha, dmx, amx, q1, q2);
+        if (it >= iters - 6 && lane == 0) printf("newton blk %d wb %d isl %d nd %d n %d it %d |g| %.4g alpha %.6g amx %.4g q1 %.4g q2 %.4g\n", (int)blockIdx.x, wb, k, nd, n, it, sqrtf(g2), alpha, amx, q1, q2);
 #endif
-        if (dmx <= B2_NEWTON_RTOL * amx) { it++; break; }
+        if (!moving) { it++; break; }
       }
       // efc_force at the solution (reporting only: a stiff row's force is below fp32 resolution of J a - aref).  The
       // constraint force that drives the step comes from the optimality condition instead, qfrc_constraint =

@@ -538,7 +538,7 @@ static int sphere_box(RawCon *c, const real *pos1, real r1, const real *pos2, co
 /* signed distance of point p (cylinder frame) to the solid cylinder (radius r, half height h); closest surface point
  * cp and outward direction n at it */
 static real point_cylinder(const real *p, real r, real h, real *cp, real *n) {
-  real rho = sqrt(p[0]*p[0] + p[1]*p[1]), az = fabs(p[2]), sz = p[2] < 0 ? -1.0 : 1.0;
+  real rho = sqrt(p[0]*p[0] + p[1]*p[1]), az = fabs(p[2]), sz = p[2] < -1e-6 ? -1.0 : 1.0;   /* mid-plane ties leave upwards */
   real ux = 1, uy = 0;
   if (rho > MINVAL) { ux = p[0] / rho; uy = p[1] / rho; }
   if (az <= h && rho <= r) {                       /* inside: leave through the nearer of cap and side */
@@ -569,22 +569,78 @@ static int sphere_cylinder(RawCon *c, const real *pos1, real r1, const real *pos
   for (int k = 0; k < 3; k++) { c->pos[k] += pos2[k]; c->frame[3+k] = 0; }
   return 1;
 }
-/* capsule (geom1) vs cylinder (geom2): one contact, the deeper of the two end spheres (first end on ties) */
+/* capsule (geom1) vs cylinder (geom2): one contact at the segment point nearest the cylinder.  The signed distance
+ * f(t) of the segment point c + a t to the solid cylinder is convex in t: coarse bracket from 9 samples, ternary
+ * refinement, then the middle of the sub-level set {f <= fmin + 1e-5}, so that a plateau (segment parallel to the side
+ * or to a cap) yields the centre of the contact patch whatever the rounding. */
+static real capcyl_f(const real *c0, const real *a, real t, const real *size2) {
+  real p[3] = {c0[0] + a[0]*t, c0[1] + a[1]*t, c0[2] + a[2]*t}, cp[3], n[3];
+  return point_cylinder(p, size2[0], size2[1], cp, n);
+}
 static int capsule_cylinder(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
                             const real *mat2, const real *size2, real margin) {
-  real ax[3] = {mat1[2], mat1[5], mat1[8]}; RawCon t[2]; int have = 0;
-  for (int s = 0; s < 2; s++) {
-    real sg = s ? -size1[1] : size1[1], p[3] = {pos1[0] + ax[0]*sg, pos1[1] + ax[1]*sg, pos1[2] + ax[2]*sg};
-    if (sphere_cylinder(&t[s], p, size1[0], pos2, mat2, size2, margin)) have |= 1 << s;
+  real ax[3] = {mat1[2], mat1[5], mat1[8]}, dif[3] = {pos1[0]-pos2[0], pos1[1]-pos2[1], pos1[2]-pos2[2]}, c0[3], a[3];
+  to_local(c0, mat2, dif); to_local(a, mat2, ax);
+  real l = size1[1], fb = 0; int ib = 0;
+  for (int i = 0; i <= 8; i++) { real f = capcyl_f(c0, a, -l + 0.25*l*i, size2); if (i == 0 || f < fb) { fb = f; ib = i; } }
+  real lo = -l + 0.25*l*(ib > 0 ? ib - 1 : 0), hi = -l + 0.25*l*(ib < 8 ? ib + 1 : 8);
+  for (int it = 0; it < 24; it++) {
+    real w = (hi - lo) / 3.0, m1 = lo + w, m2 = hi - w;
+    if (capcyl_f(c0, a, m1, size2) <= capcyl_f(c0, a, m2, size2)) hi = m2; else lo = m1;
   }
-  if (!have) return 0;
-  int pick = (have == 3) ? (t[1].dist < t[0].dist ? 1 : 0) : (have == 1 ? 0 : 1);
-  *c = t[pick];
-  return 1;
+  real tm = 0.5*(lo + hi), lev = capcyl_f(c0, a, tm, size2) + 1e-5, tl = -l, tr = l;
+  if (capcyl_f(c0, a, -l, size2) > lev) {
+    real x = -l, y = tm;
+    for (int it = 0; it < 24; it++) { real mid = 0.5*(x + y); if (capcyl_f(c0, a, mid, size2) <= lev) y = mid; else x = mid; }
+    tl = y;
+  }
+  if (capcyl_f(c0, a, l, size2) > lev) {
+    real x = tm, y = l;
+    for (int it = 0; it < 24; it++) { real mid = 0.5*(x + y); if (capcyl_f(c0, a, mid, size2) <= lev) x = mid; else y = mid; }
+    tr = x;
+  }
+  real ts = 0.5*(tl + tr), p[3] = {pos1[0] + ax[0]*ts, pos1[1] + ax[1]*ts, pos1[2] + ax[2]*ts};
+  return sphere_cylinder(c, p, size1[0], pos2, mat2, size2, margin);
 }
-/* cylinder (geom1) vs box (geom2): one contact at the box vertex deepest in the cylinder (first vertex on ties) */
+/* signed distance of p (box frame) to the solid box with half sizes s; closest surface point cp, outward normal n */
+static real point_box(const real *p, const real *s, real *cp, real *n) {
+  real d[3] = {fabs(p[0]) - s[0], fabs(p[1]) - s[1], fabs(p[2]) - s[2]};
+  n[0] = n[1] = n[2] = 0;
+  if (d[0] <= 0 && d[1] <= 0 && d[2] <= 0) {       /* inside: leave through the nearest face (x, y, z on ties) */
+    int k = 0; if (d[1] > d[k]) k = 1; if (d[2] > d[k]) k = 2;
+    real sg = p[k] < 0 ? -1.0 : 1.0;
+    cp[0] = p[0]; cp[1] = p[1]; cp[2] = p[2]; cp[k] = sg*s[k]; n[k] = sg;
+    return d[k];
+  }
+  real v[3];
+  for (int k = 0; k < 3; k++) { cp[k] = p[k] < -s[k] ? -s[k] : (p[k] > s[k] ? s[k] : p[k]); v[k] = p[k] - cp[k]; }
+  real dd = norm3(v);
+  n[0] = v[0]/dd; n[1] = v[1]/dd; n[2] = v[2]/dd;
+  return dd;
+}
+/* eight points per cylinder rim, visited 0,90,180,270 then 45,135,225,315 degrees so that the first four of a cap lying
+ * flat are its symmetric support */
+static const real RIM_C[8] = {1, 0, -1, 0, 0.70710678118654752, -0.70710678118654752, -0.70710678118654752, 0.70710678118654752};
+static const real RIM_S[8] = {0, 1, 0, -1, 0.70710678118654752, 0.70710678118654752, -0.70710678118654752, -0.70710678118654752};
+/* cylinder (geom1) vs box (geom2): up to four contacts.  Rim points of the cylinder (top cap first) that lie within the
+ * margin of the box, then the box vertex deepest in the cylinder (first vertex on ties). */
 static int cylinder_box(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
                         const real *mat2, const real *size2, real margin) {
+  int cnt = 0;
+  for (int j = 0; j < 16 && cnt < 4; j++) {
+    real pl[3] = {size1[0]*RIM_C[j & 7], size1[0]*RIM_S[j & 7], j < 8 ? size1[1] : -size1[1]}, w[3], pb[3], cp[3], n[3];
+    mulmatvec3(w, mat1, pl);
+    for (int k = 0; k < 3; k++) w[k] += pos1[k] - pos2[k];
+    to_local(pb, mat2, w);
+    real dd = point_box(pb, size2, cp, n);
+    if (dd > margin) continue;
+    real posl[3] = {cp[0] + n[0]*dd*0.5, cp[1] + n[1]*dd*0.5, cp[2] + n[2]*dd*0.5}, nl[3] = {-n[0], -n[1], -n[2]};
+    c[cnt].dist = dd;
+    mulmatvec3(c[cnt].frame, mat2, nl); mulmatvec3(c[cnt].pos, mat2, posl);
+    for (int k = 0; k < 3; k++) { c[cnt].pos[k] += pos2[k]; c[cnt].frame[3+k] = 0; }
+    cnt++;
+  }
+  if (cnt >= 4) return cnt;
   real best = 1e300, bcp[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
   for (int i = 0; i < 8; i++) {
     real v[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])}, w[3], pl[3], cp[3], n[3];
@@ -594,11 +650,56 @@ static int cylinder_box(RawCon *c, const real *pos1, const real *mat1, const rea
     real dd = point_cylinder(pl, size1[0], size1[1], cp, n);
     if (dd < best) { best = dd; memcpy(bcp, cp, sizeof(cp)); memcpy(bn, n, sizeof(n)); }
   }
-  if (best > margin) return 0;
+  if (best > margin) return cnt;
   real posl[3] = {bcp[0] + bn[0]*best*0.5, bcp[1] + bn[1]*best*0.5, bcp[2] + bn[2]*best*0.5};
+  c[cnt].dist = best;
+  mulmatvec3(c[cnt].frame, mat1, bn); mulmatvec3(c[cnt].pos, mat1, posl);
+  for (int k = 0; k < 3; k++) { c[cnt].pos[k] += pos1[k]; c[cnt].frame[3+k] = 0; }
+  return cnt + 1;
+}
+/* cylinder vs cylinder: one contact, the deepest of (side against side at the closest points of the two axes when both
+ * lie strictly inside the segments; rim points of 1 in 2; rim points of 2 in 1).  A later candidate replaces the
+ * current one only if it is deeper by more than 1e-6, so exact ties keep the first in both precisions. */
+static int cylinder_cylinder(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
+                             const real *mat2, const real *size2, real margin) {
+  real best = 1e300, bpos[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
+  real a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
+  real dif[3] = {pos2[0]-pos1[0], pos2[1]-pos1[1], pos2[2]-pos1[2]};
+  real cab = dot3(a1, a2), u = dot3(a1, dif), v = dot3(a2, dif), det = 1.0 - cab*cab, x1, x2; int side = 0;
+  if (det > 1e-6) { x1 = (u - cab*v) / det; x2 = (cab*u - v) / det; side = fabs(x1) < size1[1] && fabs(x2) < size2[1]; }
+  else {                                            /* parallel axes: middle of the overlap */
+    real lo = u - size2[1] > -size1[1] ? u - size2[1] : -size1[1], hi = u + size2[1] < size1[1] ? u + size2[1] : size1[1];
+    x1 = 0.5*(lo + hi); x2 = (cab < 0 ? -1.0 : 1.0) * (x1 - u); side = lo < hi;
+  }
+  if (side) {
+    real q1[3], q2[3], d[3];
+    for (int k = 0; k < 3; k++) { q1[k] = pos1[k] + a1[k]*x1; q2[k] = pos2[k] + a2[k]*x2; d[k] = q2[k] - q1[k]; }
+    real dd = norm3(d);
+    if (dd > 1e-9) {
+      best = dd - size1[0] - size2[0];
+      for (int k = 0; k < 3; k++) { bn[k] = d[k]/dd; bpos[k] = q1[k] + bn[k]*(size1[0] + 0.5*best); }
+    }
+  }
+  for (int g = 0; g < 2; g++) {
+    const real *pa = g ? pos2 : pos1, *ma = g ? mat2 : mat1, *sa = g ? size2 : size1;     /* the cylinder whose rim is sampled */
+    const real *pb = g ? pos1 : pos2, *mb = g ? mat1 : mat2, *sb = g ? size1 : size2;     /* the solid it is tested against */
+    for (int j = 0; j < 16; j++) {
+      real pl[3] = {sa[0]*RIM_C[j & 7], sa[0]*RIM_S[j & 7], j < 8 ? sa[1] : -sa[1]}, w[3], q[3], cp[3], n[3];
+      mulmatvec3(w, ma, pl);
+      for (int k = 0; k < 3; k++) w[k] += pa[k] - pb[k];
+      to_local(q, mb, w);
+      real dd = point_cylinder(q, sb[0], sb[1], cp, n);
+      if (dd < best - 1e-6) {
+        real posl[3] = {cp[0] + n[0]*dd*0.5, cp[1] + n[1]*dd*0.5, cp[2] + n[2]*dd*0.5}, nw[3];
+        best = dd;
+        mulmatvec3(bpos, mb, posl); mulmatvec3(nw, mb, n);
+        for (int k = 0; k < 3; k++) { bpos[k] += pb[k]; bn[k] = g ? nw[k] : -nw[k]; }   /* normal from geom 1 to geom 2 */
+      }
+    }
+  }
+  if (best > margin) return 0;
   c->dist = best;
-  mulmatvec3(c->frame, mat1, bn); mulmatvec3(c->pos, mat1, posl);
-  for (int k = 0; k < 3; k++) { c->pos[k] += pos1[k]; c->frame[3+k] = 0; }
+  for (int k = 0; k < 3; k++) { c->pos[k] = bpos[k]; c->frame[k] = bn[k]; c->frame[3+k] = 0; }
   return 1;
 }
 
@@ -787,6 +888,7 @@ int ref_collide_raw(int t1, int t2, const double *p1, const double *m1, const do
     else if (t2 == B2_GEOM_CYLINDER) n = capsule_cylinder(raw, p1, m1, s1, p2, m2, s2, margin);
     else if (t2 == B2_GEOM_BOX) n = capsule_box(raw, p1, m1, s1, p2, m2, s2, margin);
   } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) n = cylinder_box(raw, p1, m1, s1, p2, m2, s2, margin);
+  else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_CYLINDER) n = cylinder_cylinder(raw, p1, m1, s1, p2, m2, s2, margin);
   else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) n = box_box(raw, p1, m1, s1, p2, m2, s2, margin);
   for (int k = 0; k < n && k < 8; k++) { out80[10*k] = raw[k].dist; memcpy(out80 + 10*k + 1, raw[k].pos, 3*sizeof(real)); memcpy(out80 + 10*k + 4, raw[k].frame, 6*sizeof(real)); }
   return n;
@@ -818,6 +920,8 @@ static int collide_pair(const RefModel *m, const RefData *d, int g1, int g2, rea
     }
   } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) {
     return cylinder_box(out, p1, m1, s1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_CYLINDER) {
+    return cylinder_cylinder(out, p1, m1, s1, p2, m2, s2, margin);
   } else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) {
     return box_box(out, p1, m1, s1, p2, m2, s2, margin);
   }

@@ -39,7 +39,9 @@ def both(H, R, t1, t2, p1, m1, s1, p2, m2, s2, margin):
 
 SIZES = {0: lambda r: [0, 0, 0], 2: lambda r: [r.uniform(.03, .2), 0, 0], 3: lambda r: [r.uniform(.03, .1), r.uniform(.05, .3), 0],
          5: lambda r: [r.uniform(.5, 3), r.uniform(.05, .2), 0], 6: lambda r: list(r.uniform(.03, .25, 3))}
-PAIRS = [(0, 2), (0, 3), (0, 6), (2, 2), (2, 3), (2, 6), (2, 5), (3, 3), (3, 5), (5, 6), (3, 6), (6, 6)]
+PAIRS = [(0, 2), (0, 3), (0, 5), (0, 6), (2, 2), (2, 3), (2, 6), (2, 5), (3, 3), (3, 5), (5, 5), (5, 6), (3, 6), (6, 6)]
+# cylinders come in two shapes: flat discs (dancing floor, rescue wheels) and the martial-arts dummies (r 0.2, half height 0.5)
+TALL = lambda r: [r.uniform(.1, .3), r.uniform(.3, .6), 0]
 
 
 @pytest.mark.parametrize("pair", PAIRS)
@@ -54,12 +56,15 @@ def test_fp32_narrow_phase_matches_oracle(libs, pair):
     ncontact = 0
     for it in range(3000):
         s1 = SIZES[t1](rng); s2 = SIZES[t2](rng)
+        tall = it % 2 == 1
+        if tall and t1 == 5: s1 = TALL(rng)
+        if tall and t2 == 5: s2 = TALL(rng)
         m1 = quat_to_mat(rq()).ravel(); m2 = quat_to_mat(rq()).ravel()
         if it % 4 == 0 and t1 != 0:      # axis-aligned / parallel configurations (plateaus, ties)
             m1 = np.eye(3).ravel()
             if it % 8 == 0:
                 m2 = np.eye(3).ravel()
-        scale = 1.5 if t1 == 5 else 0.3 if t1 == 0 else 0.25
+        scale = (0.4 if tall else 1.5) if t1 == 5 else 0.3 if t1 == 0 else (0.4 if (tall and t2 == 5) else 0.25)
         p2 = rng.normal(size=3) * scale
         n32, o32, n64, o64 = both(H, R, t1, t2, np.zeros(3), m1, s1, p2, m2, s2, 0.01)
         assert n32 == n64, (pair, it, n32, n64)          # contact counts are bit-exact
