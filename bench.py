@@ -32,6 +32,9 @@ WORKLOADS = {
                        "3175 candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
     "humanoid_construction": (2048, 300, "humanoid_construction_env: {n} envs/GPU lockstep, 1 RK4 step (dt 2 ms, 4 forward passes), Newton-100, "
                               "99 dofs in 12 trees, 1202 candidate pairs, uniform random actions over action_space x {s}, same-step auto-reset"),
+    "humanoid_martial_arts": (4096, 1500, "humanoid_martial_arts_env: {n} envs/GPU lockstep, 1 Euler step (dt 16.67 ms), Newton-50, 47 dofs in 4 trees "
+                              "(free humanoid, two free cylinder dummies, hinged board), 294 candidate pairs, uniform random actions over action_space x {s}, "
+                              "same-step auto-reset"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the task's default size, from the
 # `ncu --set full` captures summarised under profiles/ (r01_e quadruped, r01_f dancing, r01_g soccer, r01_h rescue).

@@ -20,7 +20,7 @@ typedef struct B2Model B2Model;
 typedef struct B2Batch B2Batch;
 
 enum { B2_OK = 0, B2_ERR_ARG = -1, B2_ERR_CUDA = -2, B2_ERR_LAYOUT = -3, B2_ERR_UNSUPPORTED = -4 };
-enum { B2_TASK_NONE = 0, B2_TASK_QUADRUPED_PARKOUR = 1, B2_TASK_HUMANOID_DANCING = 2, B2_TASK_HUMANOID_SOCCER = 3, B2_TASK_BIPEDAL_RESCUE = 4, B2_TASK_HUMANOID_CONSTRUCTION = 5 };
+enum { B2_TASK_NONE = 0, B2_TASK_QUADRUPED_PARKOUR = 1, B2_TASK_HUMANOID_DANCING = 2, B2_TASK_HUMANOID_SOCCER = 3, B2_TASK_BIPEDAL_RESCUE = 4, B2_TASK_HUMANOID_CONSTRUCTION = 5, B2_TASK_HUMANOID_MARTIAL_ARTS = 6 };
 
 /* Replaces mujoco.MjModel.from_xml_string(...) (quadruped_parkour_env/parkour_env.py:100 and the six sibling call
  * sites): takes the packed device tables produced by the Python-side compiler (device_pack.pack_device_model) and

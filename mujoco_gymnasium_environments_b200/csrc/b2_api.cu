@@ -68,18 +68,19 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   E.team_sync();
 
   // one loop, one call site of the physics: [reset ->] n sub-steps -> task epilogue [-> auto-reset -> settle steps]
-  int nsub = 0, stage = 0;
+  // (nfwd: a reset that ends with mj_forward instead of settle steps, Task::RESET_FORWARD)
+  int nsub = 0, nfwd = 0, stage = 0;
   if (mode == MODE_PHYS) nsub = B.nsub;
   else if (mode == MODE_FORWARD) nsub = 1;
   else if (mode == MODE_RESET) {
     if (w0) Task::reset_state(E, tp, B, env, s_ti, s_tf, inject ? inject + (size_t)Task::NINJ * env : nullptr);
-    E.team_sync(); nsub = Task::SETTLE; stage = 1;
+    E.team_sync(); nsub = Task::SETTLE; nfwd = Task::RESET_FORWARD ? 1 : 0; stage = 1;
   } else {
     if (w0) { Task::apply_action(E, tp, B.action + (size_t)env * B.act_dim, s_act); Task::pre_physics(E, tp, s_ti, s_tf); }
     E.team_sync(); nsub = Task::FRAME_SKIP;
   }
   while (true) {
-    if (nsub > 0) { E.step(ctr, mode != MODE_FORWARD); nsub--; continue; }
+    if (nsub > 0 || (Task::RESET_FORWARD && nfwd > 0)) { E.step(ctr, nsub > 0 && mode != MODE_FORWARD); if (nsub > 0) nsub--; else nfwd--; continue; }
     if (mode == MODE_PHYS || mode == MODE_FORWARD) break;
     if (stage == 0) {   // end of the control step
       if (w0) {
@@ -106,8 +107,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
         Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
       }
       E.team_sync();
-      nsub = Task::SETTLE; stage = 1;
-      if (nsub == 0) { if (w0) { Task::after_settle(E, tp, s_ti, s_tf); Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); } break; }
+      nsub = Task::SETTLE; nfwd = Task::RESET_FORWARD ? 1 : 0; stage = 1;
+      if (nsub == 0 && nfwd == 0) { if (w0) { Task::after_settle(E, tp, s_ti, s_tf); Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); } break; }
     } else {            // end of the settle steps of a reset
       if (w0) { Task::after_settle(E, tp, s_ti, s_tf); Task::observe(E, tp, B.obs + (size_t)env * B.obs_dim); }
       break;
@@ -152,7 +153,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0;
-  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -209,6 +210,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
     case TASK_HUMANOID_SOCCER: return launch_task<SoccerTask>(b, mode, inject, s);
     case TASK_BIPEDAL_RESCUE: return launch_task<RescueTask>(b, mode, inject, s);
     case TASK_HUMANOID_CONSTRUCTION: return launch_task<ConstructionTask>(b, mode, inject, s);
+    case TASK_HUMANOID_MARTIAL_ARTS: return launch_task<MartialArtsTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -273,6 +275,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
     case TASK_BIPEDAL_RESCUE: B2_TASK_DIMS(RescueTask); break;
     case TASK_HUMANOID_CONSTRUCTION: B2_TASK_DIMS(ConstructionTask); break;
+    case TASK_HUMANOID_MARTIAL_ARTS: B2_TASK_DIMS(MartialArtsTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;

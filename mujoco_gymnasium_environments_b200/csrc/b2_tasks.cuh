@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4, TASK_HUMANOID_CONSTRUCTION = 5 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4, TASK_HUMANOID_CONSTRUCTION = 5, TASK_HUMANOID_MARTIAL_ARTS = 6 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -32,7 +32,7 @@ struct TaskParams {
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
   static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32, ARENA_SPAN = 0;
-  static constexpr bool PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -172,7 +172,7 @@ struct QuadrupedTask {
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
   static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -355,7 +355,7 @@ struct DancingTask {
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
   static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -527,7 +527,7 @@ struct SoccerTask {
 // inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
 struct RescueTask {
   static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -682,7 +682,7 @@ struct RescueTask {
 // ids: [0] humanoid body      inject: task index, wind, rain, temperature
 struct ConstructionTask {
   static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 64, ARENA_SPAN = 40;
-  static constexpr bool PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -744,6 +744,87 @@ struct ConstructionTask {
     int term = 0;
     if (z < 0.5f) term = 1;
     else if (tf[1] >= 1.0f) { ti[3] += 1; term = 1; }
+    *terminated = term; *truncated = ti[0] >= MAX_STEPS;
+    tf[0] += reward;
+    return reward;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ martial arts
+// humanoid_martial_arts_env/martial_arts_env.py: reset :442-487, step :489-523, _get_observation :525-560,
+// _calculate_reward :562-606, _check_termination :608-621.  One Euler step of 16.67 ms, Newton-50/1e-10.
+// qpos[0:7] is dummy #1's free joint: reset drops that dummy next to the humanoid.  cvel[:3] (angular) is
+// what the reference calls the linear velocity and vice versa; both are the last forward pass's values.  Reset ends with
+// mj_forward (RESET_FORWARD).  The observation has 113 entries (85 declared) and precedes the reward, which
+// advances stance_stability_time.
+// ti: [0] current_step [1] techniques_performed [2] episode id [3] falls
+// tf: [0] total reward [1] stance_stability_time
+// ids: [0] torso [1] right_hand [2] left_hand [3] right_ankle [4] left_ankle [5] dummy1 [6] dummy2     inject: dx, dy
+struct MartialArtsTask {
+  static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 47;
+  static constexpr bool RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], -1.0f, 1.0f);
+      act_clipped[i] = a; E.p_ctrl()[i] = a * tp.act_hi[i];          // action * actuator_ctrlrange[:, 1] (:495)
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams&, const BatchView& B, int env, int* ti, float* tf,
+                                     const float* inject) {
+    E.reset_data();
+    if (E.lane == 0) {
+      unsigned ep = (unsigned)ti[2]; unsigned ge = (unsigned)(B.env_offset + env);
+      float dx = inject ? inject[0] : -0.5f + rng_uniform(B.seed, ge, ep, 0u), dy = inject ? inject[1] : -0.5f + rng_uniform(B.seed, ge, ep, 1u);
+      float* q = E.p_qpos();
+      q[0] = 0.0f + dx; q[1] = 0.0f + dy; q[2] = 1.4f; q[3] = 1.f; q[4] = 0.f; q[5] = 0.f; q[6] = 0.f;
+      ti[0] = 0; ti[1] = 0; ti[2] = (int)(ep + 1); ti[3] = 0; tf[0] = 0.f; tf[1] = 0.f;
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams&, int* ti, float*) {
+    if (E.lane == 0) ti[0] += 1;
+    E.sync();
+  }
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
+    const float* tf = E.p_tf(); const int torso = tp.ids[0];
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 3) v = E.p_xpos()[3 * torso + i];
+      else if (i < 7) v = E.p_xquat()[4 * torso + i - 3];
+      else if (i < 13) v = E.p_cvel()[6 * torso + i - 7];
+      else if (i < 56) v = E.p_qpos()[7 + i - 13];
+      else if (i < 97) v = E.p_qvel()[6 + i - 56];
+      else if (i < 100) v = E.p_xpos()[3 * tp.ids[5] + i - 97];
+      else if (i < 103) v = E.p_xpos()[3 * tp.ids[6] + i - 100];
+      else if (i == 104) v = -2.0f;
+      else if (i == 105) v = 1.0f;
+      else if (i == 112) v = tf[1];
+      obs[i] = v;
+    }
+  }
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float* act, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    const float dt = 0.01667f;
+    const float* xp = E.p_xpos(); const float* cv = E.p_cvel(); const int torso = tp.ids[0];
+    auto n3 = [&](const float* v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    float reward = 100.0f * fminf(1.0f, xp[3 * torso + 2] / 1.75f);
+    if (n3(cv + 6 * tp.ids[1]) > 2.0f || n3(cv + 6 * tp.ids[2]) > 2.0f) { reward += 500.f; ti[1] += 1; }
+    if (n3(cv + 6 * tp.ids[3]) > 3.0f || n3(cv + 6 * tp.ids[4]) > 3.0f) { reward += 800.f; ti[1] += 1; }
+    if (n3(cv + 6 * torso + 3) < 0.5f) { tf[1] += dt; reward += 200.f * dt; }
+    float s = 0.f;
+    for (int i = 0; i < ACT; i++) s += fabsf(act[i]);
+    reward -= s * 0.01f;
+    float ddx = xp[3 * tp.ids[5]] - xp[3 * torso], ddy = xp[3 * tp.ids[5] + 1] - xp[3 * torso + 1];      // active_dummy_idx stays 0
+    float dist = sqrtf(ddx * ddx + ddy * ddy);
+    if (dist < 2.0f) reward += 50.f * (2.0f - dist);
+    int term = 0;
+    if (xp[3 * torso + 2] < 0.5f) { ti[3] += 1; term = 1; }
+    else if (fabsf(xp[3 * torso]) > 5.5f || fabsf(xp[3 * torso + 1]) > 5.5f) term = 1;
     *terminated = term; *truncated = ti[0] >= MAX_STEPS;
     tf[0] += reward;
     return reward;

@@ -3,3 +3,4 @@ from .humanoid_dancing import HumanoidDancingEnv  # noqa: F401
 from .humanoid_soccer import HumanoidSoccerEnv  # noqa: F401
 from .bipedal_rescue import BipedalRescueEnv  # noqa: F401
 from .humanoid_construction import HumanoidConstructionEnv  # noqa: F401
+from .humanoid_martial_arts import HumanoidMartialArtsEnv  # noqa: F401

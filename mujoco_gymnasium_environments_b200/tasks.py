@@ -167,6 +167,18 @@ def _construction_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- humanoid martial arts
+def _martial_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_HUMANOID_MARTIAL_ARTS
+    for k, name in enumerate(["torso", "right_hand", "left_hand", "right_ankle", "left_ankle", "dummy1", "dummy2"]):
+        d.ids[k] = t.name2id("body", name)                # martial_arts_env.py:383-395
+    hi = np.asarray(t.act_ctrlrange, np.float64).reshape(-1, 2)[:, 1]
+    for k in range(28):
+        d.act_lo[k] = -1.0; d.act_hi[k] = float(hi[k])   # act_hi carries actuator_ctrlrange[:, 1] (:495), the action box is [-1, 1]
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -203,4 +215,11 @@ TASKS: Dict[str, TaskSpec] = {
         # the reference declares 125 entries but returns 135: the actual length is exposed
         observation_space=lambda t: Box(np.full(135, -np.inf, np.float32), np.full(135, np.inf, np.float32), dtype=np.float32),
         info_keys=["task", "task_progress", "blocks_placed", "safety_violations", "episode_stats", "weather"]),
+    "humanoid_martial_arts": TaskSpec(
+        name="humanoid_martial_arts", task_id=capi.TASK_HUMANOID_MARTIAL_ARTS, obs_dim=113, act_dim=28, max_episode_steps=6000,
+        frame_skip=1, render_fps=60, bytes_per_env_step=1786, describe=_martial_desc,
+        action_space=lambda t: Box(np.full(28, -1.0, np.float32), np.full(28, 1.0, np.float32), dtype=np.float32),
+        # the reference declares 85 entries but returns 113: the actual length is exposed
+        observation_space=lambda t: Box(np.full(113, -np.inf, np.float32), np.full(113, np.inf, np.float32), dtype=np.float32),
+        info_keys=["episode_stats", "combo_chain", "stance_stability", "current_step"]),
 }

@@ -898,5 +898,93 @@ class HumanoidConstructionRef:
 
 
 
+class HumanoidMartialArtsRef:
+    """humanoid_martial_arts_env/martial_arts_env.py restated: __init__ :40-132, reset :442-487, step :489-523,
+    _get_observation :525-560, _calculate_reward :562-606, _check_termination :608-621.  One Euler step of
+    16.67 ms per env.step, Newton-50.  ``qpos[0:7]`` is the free joint of dummy #1, so reset moves that dummy,
+    not the humanoid; ``cvel[:3]`` is the angular part and ``cvel[3:]`` the linear part of MuJoCo's com-based velocity, used
+    by the reference under the opposite names; the observation has 113 entries (the space declares 85)."""
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("humanoid_martial_arts")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.dt = 0.01667; self.max_episode_steps = 6000; self.current_step = 0
+        self.robot_height = 1.75; self.balance_reward = 100.0
+        self.torso = t.name2id("body", "torso"); self.right_hand = t.name2id("body", "right_hand")
+        self.left_hand = t.name2id("body", "left_hand"); self.right_foot = t.name2id("body", "right_ankle")
+        self.left_foot = t.name2id("body", "left_ankle")
+        self.dummy1 = t.name2id("body", "dummy1"); self.dummy2 = t.name2id("body", "dummy2")
+        self.ctrl_hi = np.asarray(t.act_ctrlrange, np.float64).reshape(-1, 2)[:, 1].copy()
+        self.combo_len = 0; self.stance_stability_time = 0.0; self.technique_accuracy = 0.0; self.active_dummy_idx = 0
+        self.episode_stats = dict(techniques_performed=0, falls=0)
+        self.np_random = np.random.default_rng(seed)
+
+    def reset(self, seed=None, draws=None):
+        if seed is not None:
+            self.np_random = np.random.default_rng(seed)
+        m, d = self.model, self.data
+        ref.mj_resetData(m, d)
+        if draws is None:
+            draws = (self.np_random.uniform(-0.5, 0.5), self.np_random.uniform(-0.5, 0.5))
+        d.qpos[0:3] = [0.0 + float(draws[0]), 0.0 + float(draws[1]), 1.4]
+        d.qpos[3:7] = [1, 0, 0, 0]
+        self.current_step = 0; self.combo_len = 0; self.stance_stability_time = 0.0; self.technique_accuracy = 0.0
+        self.active_dummy_idx = 0
+        self.episode_stats = dict(techniques_performed=0, falls=0)
+        ref.mj_forward(m, d)
+        return self._get_observation(), dict(current_step=0)
+
+    def step(self, action):
+        d = self.data
+        action = np.clip(np.asarray(action, np.float64), -1.0, 1.0)
+        d.ctrl[:] = action * self.ctrl_hi
+        ref.mj_step(self.model, d)
+        self.current_step += 1
+        obs = self._get_observation()
+        reward = self._calculate_reward(action)
+        terminated = self._check_termination()
+        truncated = self.current_step >= self.max_episode_steps
+        return obs, reward, terminated, truncated, dict(current_step=self.current_step, stance_stability=self.stance_stability_time)
+
+    def _get_observation(self):
+        d = self.data
+        obs = []
+        obs.extend(d.xpos[self.torso]); obs.extend(d.xquat[self.torso])
+        obs.extend(d.cvel[self.torso][:3]); obs.extend(d.cvel[self.torso][3:])
+        obs.extend(d.qpos[7:]); obs.extend(d.qvel[6:])
+        obs.extend(d.xpos[self.dummy1]); obs.extend(d.xpos[self.dummy2]); obs.extend([0.0, -2.0, 1.0])
+        obs.extend([0.0, 0.0, 0.0, 0.0])
+        obs.append(self.technique_accuracy); obs.append(self.combo_len); obs.append(self.stance_stability_time)
+        return np.array(obs, dtype=np.float32)
+
+    def _calculate_reward(self, action):
+        d = self.data
+        reward = 0.0
+        reward += self.balance_reward * min(1.0, d.xpos[self.torso][2] / self.robot_height)
+        if np.linalg.norm(d.cvel[self.right_hand][:3]) > 2.0 or np.linalg.norm(d.cvel[self.left_hand][:3]) > 2.0:
+            reward += 500; self.episode_stats["techniques_performed"] += 1
+        if np.linalg.norm(d.cvel[self.right_foot][:3]) > 3.0 or np.linalg.norm(d.cvel[self.left_foot][:3]) > 3.0:
+            reward += 800; self.episode_stats["techniques_performed"] += 1
+        if np.linalg.norm(d.cvel[self.torso][3:]) < 0.5:
+            self.stance_stability_time += self.dt
+            reward += 200 * self.dt
+        reward -= float(np.sum(np.abs(action))) * 0.01
+        dummy = d.xpos[self.dummy1 if self.active_dummy_idx == 0 else self.dummy2]
+        distance = float(np.linalg.norm(dummy[:2] - d.xpos[self.torso][:2]))
+        if distance < 2.0:
+            reward += 50 * (2.0 - distance)
+        return float(reward)
+
+    def _check_termination(self):
+        p = self.data.xpos[self.torso]
+        if p[2] < 0.5:
+            self.episode_stats["falls"] += 1
+            return True
+        return bool(abs(p[0]) > 5.5 or abs(p[1]) > 5.5)
+
+
 TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef,
-         "bipedal_rescue": BipedalRescueRef, "humanoid_construction": HumanoidConstructionRef}
+         "bipedal_rescue": BipedalRescueRef, "humanoid_construction": HumanoidConstructionRef,
+         "humanoid_martial_arts": HumanoidMartialArtsRef}

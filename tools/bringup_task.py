@@ -41,6 +41,8 @@ def make_inject(task, rng, n):
         inj = np.zeros((n, 4), np.float32)
         inj[:, 0] = rng.integers(0, 4, n); inj[:, 1] = rng.uniform(0, 5, n); inj[:, 2] = rng.uniform(0, .5, n); inj[:, 3] = rng.uniform(15, 35, n)
         return inj
+    if task == "humanoid_martial_arts":
+        return rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
     raise KeyError(task)
 
 
@@ -51,7 +53,7 @@ def ref_reset(task, env, inj):
         return env.reset(sequence=[(int(inj[2 * k]), float(inj[2 * k + 1])) for k in range(20)])
     if task in ("humanoid_soccer", "bipedal_rescue"):
         return env.reset(draws=[float(x) for x in inj])
-    if task == "humanoid_construction":
+    if task in ("humanoid_construction", "humanoid_martial_arts"):
         return env.reset(draws=tuple(float(x) for x in inj))
 
 
