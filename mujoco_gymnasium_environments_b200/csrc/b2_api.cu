@@ -45,7 +45,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER> E(P, B, B.model_floats + team * B.ws_floats, team);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -153,6 +153,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr int SOLVER = -1;
   static constexpr bool RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
@@ -265,11 +266,11 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
+  int task_solver = -1, keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -279,6 +280,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
+  if (task_solver >= 0 && task_solver != dim[DD_solver]) { delete b; return fail(B2_ERR_UNSUPPORTED, "the task kernel is compiled for a different <option solver> than the model's"); }
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;

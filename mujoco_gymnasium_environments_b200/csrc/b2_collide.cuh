@@ -152,6 +152,7 @@ __device__ __noinline__ int c_capsule_cylinder(float* dst, V3 p1, const float* m
                                                const float* s2, float margin) {
   V3 ax = matcol(m1, 2), c0 = mulmatT(m2, p1 - p2), a = mulmatT(m2, ax);
   float l = s1[1], fb = 0.f; int ib = 0;
+  if (capcyl_f(c0, a, 0.f, s2) - l - s1[0] > margin) return 0;       // the distance is 1-Lipschitz along the segment
   for (int i = 0; i <= 8; i++) { float f = capcyl_f(c0, a, -l + 0.25f * l * (float)i, s2); if (i == 0 || f < fb) { fb = f; ib = i; } }
   float lo = -l + 0.25f * l * (float)(ib > 0 ? ib - 1 : 0), hi = -l + 0.25f * l * (float)(ib < 8 ? ib + 1 : 8);
   for (int it = 0; it < 24; it++) {

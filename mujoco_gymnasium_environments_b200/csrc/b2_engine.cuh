@@ -143,7 +143,9 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // rows than this are built (A = J M^-1 J') by the whole team.  Both are per-task tuning knobs (A/B-measured on B200).
 // DYN: islands are re-formed every forward pass from the active contacts (needed when moving trees can touch each other);
 // otherwise they are the model's static islands, set up once per launch.
-template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true>
+// SOLVER: 0 the task's model uses PGS, 2 Newton (the other solver is not compiled into that kernel), -1 decided at run time
+// from the model (physics-only batches).
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -173,6 +175,7 @@ struct Engine {
   // candidate-pair tables: shared memory, or global memory (read-only, L2-resident) when the task leaves them cold
   __device__ __forceinline__ const int* PI(int f) const { return COLD ? P.ints + P.ioff[f] : (const int*)b2_smem + P.ioff[f]; }
   __device__ __forceinline__ int dim(int k) const { return P.dim[k]; }
+  __device__ __forceinline__ bool newton() const { return SOLVER < 0 ? P.dim[DD_solver] == 2 : SOLVER == 2; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int conCap() const { return B.con_cap; }
   __device__ __forceinline__ int rowCap() const { return B.row_cap; }
@@ -737,7 +740,7 @@ struct Engine {
         // rows that do not fit (row buffer, or J + packed A in what is left of the arena) are cut from the island's tail:
         // the last contacts go first, the joint limits last; every cut is counted
         int avail = arenaFloats() - scratch - used - 8;
-        const bool newton = dim(DD_solver) == 2; const int ndk = p_isl_nd()[k];
+        const bool newton = this->newton(); const int ndk = p_isl_nd()[k];
         if (adr + n > rowCap()) { n = max(rowCap() - adr, 0); ovf++; }
         if (r4(n * ldj) + (newton ? newton_floats(n, ndk) : a_floats(n)) > avail) {
           float hb = (float)ldj + 2.0f;
@@ -780,7 +783,7 @@ struct Engine {
   __device__ __forceinline__ int max_span() const { return dim(DD_maxspan); }
   // A-build scratch: 32 floats per dof; in the dead block [xmat .. cinert] when it fits, else at the arena tail
   __device__ __forceinline__ int scratch_in_arena() const {
-    return (dim(DD_solver) == 2 || 32 * dim(DD_nv) <= dead_block_floats(P.dim, B.keep_frames)) ? 0 : 32 * dim(DD_nv);
+    return (newton() || 32 * dim(DD_nv) <= dead_block_floats(P.dim, B.keep_frames)) ? 0 : 32 * dim(DD_nv);
   }
   __device__ __forceinline__ float* scratch_base() const {
     int sc = scratch_in_arena();
@@ -1512,12 +1515,12 @@ struct Engine {
           } else if (pass == 1) {
             if (p_misc()[MISC_NEFC] > 0) {
               fill_rows(); B2_TICK(9);
-              if (dim(DD_solver) == 2) solve_newton(counters);
+              if (newton()) solve_newton(counters);
               else { build_A(); B2_TICK(10); solve_pgs(counters); }
               B2_TICK(11);
             }
             else if (tl == 0) p_misc()[MISC_ITERS] = 0;
-            if (wl == 0) qfrc_constraint(dim(DD_solver) == 2);
+            if (wl == 0) qfrc_constraint(newton());
           } else {
             if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
           }

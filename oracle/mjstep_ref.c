@@ -582,6 +582,7 @@ static int capsule_cylinder(RawCon *c, const real *pos1, const real *mat1, const
   real ax[3] = {mat1[2], mat1[5], mat1[8]}, dif[3] = {pos1[0]-pos2[0], pos1[1]-pos2[1], pos1[2]-pos2[2]}, c0[3], a[3];
   to_local(c0, mat2, dif); to_local(a, mat2, ax);
   real l = size1[1], fb = 0; int ib = 0;
+  if (capcyl_f(c0, a, 0, size2) - l - size1[0] > margin) return 0;   /* the distance is 1-Lipschitz along the segment */
   for (int i = 0; i <= 8; i++) { real f = capcyl_f(c0, a, -l + 0.25*l*i, size2); if (i == 0 || f < fb) { fb = f; ib = i; } }
   real lo = -l + 0.25*l*(ib > 0 ? ib - 1 : 0), hi = -l + 0.25*l*(ib < 8 ? ib + 1 : 8);
   for (int it = 0; it < 24; it++) {

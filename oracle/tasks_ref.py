@@ -917,6 +917,7 @@ class HumanoidMartialArtsRef:
         self.left_foot = t.name2id("body", "left_ankle")
         self.dummy1 = t.name2id("body", "dummy1"); self.dummy2 = t.name2id("body", "dummy2")
         self.ctrl_hi = np.asarray(t.act_ctrlrange, np.float64).reshape(-1, 2)[:, 1].copy()
+        self.action_low = np.full(28, -1.0); self.action_high = np.full(28, 1.0)
         self.combo_len = 0; self.stance_stability_time = 0.0; self.technique_accuracy = 0.0; self.active_dummy_idx = 0
         self.episode_stats = dict(techniques_performed=0, falls=0)
         self.np_random = np.random.default_rng(seed)
