@@ -20,7 +20,7 @@ typedef struct B2Model B2Model;
 typedef struct B2Batch B2Batch;
 
 enum { B2_OK = 0, B2_ERR_ARG = -1, B2_ERR_CUDA = -2, B2_ERR_LAYOUT = -3, B2_ERR_UNSUPPORTED = -4 };
-enum { B2_TASK_NONE = 0, B2_TASK_QUADRUPED_PARKOUR = 1, B2_TASK_HUMANOID_DANCING = 2, B2_TASK_HUMANOID_SOCCER = 3, B2_TASK_BIPEDAL_RESCUE = 4, B2_TASK_HUMANOID_CONSTRUCTION = 5, B2_TASK_HUMANOID_MARTIAL_ARTS = 6 };
+enum { B2_TASK_NONE = 0, B2_TASK_QUADRUPED_PARKOUR = 1, B2_TASK_HUMANOID_DANCING = 2, B2_TASK_HUMANOID_SOCCER = 3, B2_TASK_BIPEDAL_RESCUE = 4, B2_TASK_HUMANOID_CONSTRUCTION = 5, B2_TASK_HUMANOID_MARTIAL_ARTS = 6, B2_TASK_ROBOTIC_ARM_ASSEMBLY = 7 };
 
 /* Replaces mujoco.MjModel.from_xml_string(...) (quadruped_parkour_env/parkour_env.py:100 and the six sibling call
  * sites): takes the packed device tables produced by the Python-side compiler (device_pack.pack_device_model) and
@@ -33,6 +33,8 @@ typedef struct B2TaskDesc {
   int task;            /* B2_TASK_* */
   int ids[16];
   float act_lo[40], act_hi[40];
+  int aux_i[64];       /* task-specific integer table (arm: per-geom component index from the reference's geom-name matching) */
+  float aux_f[32];     /* task-specific float table (arm: component targets, assembly_env.py:65-75, and the ee_site offset) */
 } B2TaskDesc;
 
 /* Fixed capacities of the per-env on-chip buffers; 0 = library default.  Contacts / rows beyond a capacity are

@@ -21,12 +21,12 @@ SYMBOLS = ["b2_model_create", "b2_model_destroy", "b2_batch_create", "b2_batch_d
            "b2_get_task_state", "b2_set_task_state", "b2_get_contacts", "b2_get_xpos", "b2_debug_forward", "b2_stats",
            "b2_launch_count", "b2_last_error"]
 
-TASK_NONE, TASK_QUADRUPED_PARKOUR, TASK_HUMANOID_DANCING, TASK_HUMANOID_SOCCER, TASK_BIPEDAL_RESCUE, TASK_HUMANOID_CONSTRUCTION, TASK_HUMANOID_MARTIAL_ARTS = 0, 1, 2, 3, 4, 5, 6
+TASK_NONE, TASK_QUADRUPED_PARKOUR, TASK_HUMANOID_DANCING, TASK_HUMANOID_SOCCER, TASK_BIPEDAL_RESCUE, TASK_HUMANOID_CONSTRUCTION, TASK_HUMANOID_MARTIAL_ARTS, TASK_ROBOTIC_ARM_ASSEMBLY = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 class B2TaskDesc(ctypes.Structure):
     _fields_ = [("task", ctypes.c_int), ("ids", ctypes.c_int * 16), ("act_lo", ctypes.c_float * 40),
-                ("act_hi", ctypes.c_float * 40)]
+                ("act_hi", ctypes.c_float * 40), ("aux_i", ctypes.c_int * 64), ("aux_f", ctypes.c_float * 32)]
 
 
 class B2BatchOpts(ctypes.Structure):

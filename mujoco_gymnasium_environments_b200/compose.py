@@ -181,5 +181,7 @@ COMPOSERS = {
     "bipedal_rescue": lambda root: inline_mjcf("rescue", root),
     "humanoid_construction": lambda root: inline_mjcf("construction", root),
     "humanoid_martial_arts": lambda root: inline_mjcf("martial_arts", root),
+    # the arm loads a file (assembly_env.py:53-61); complete_model.xml has no <include>, so the file is the model
+    "robotic_arm_assembly": lambda root: open(os.path.join(root, "robotic_arm_assembly_env", "assets", "complete_model.xml")).read(),
 }
 

@@ -20,6 +20,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct B2Model {
   int device; DevModel dm; int* d_ints; float* d_flts;
   std::vector<int> h_ints;
+  bool condim6 = false;     // some contact pair has condim 6 (needs a kernel built with 10-row pyramids)
 };
 struct B2Batch {
   B2Model* m; int n_envs, W; TaskParams tp; BatchView v; size_t smem;
@@ -45,7 +46,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -154,7 +155,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0;
   static constexpr int SOLVER = -1;
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -212,6 +213,7 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
     case TASK_BIPEDAL_RESCUE: return launch_task<RescueTask>(b, mode, inject, s);
     case TASK_HUMANOID_CONSTRUCTION: return launch_task<ConstructionTask>(b, mode, inject, s);
     case TASK_HUMANOID_MARTIAL_ARTS: return launch_task<MartialArtsTask>(b, mode, inject, s);
+    case TASK_ROBOTIC_ARM_ASSEMBLY: return launch_task<ArmTask>(b, mode, inject, s);
   }
   return fail(B2_ERR_UNSUPPORTED, "unknown task id");
 }
@@ -248,6 +250,11 @@ int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_f
   if (dm.dim[DD_integrator] != 0 && dm.dim[DD_integrator] != 1) { delete m; return fail(B2_ERR_UNSUPPORTED, "integrator must be Euler or RK4"); }
   if (dm.dim[DD_solver] != 0 && dm.dim[DD_solver] != 2) { delete m; return fail(B2_ERR_UNSUPPORTED, "solver must be PGS or Newton"); }
   if (dm.dim[DD_ntree] > B2_MAX_ISLANDS) { delete m; return fail(B2_ERR_UNSUPPORTED, "more than 16 kinematic trees"); }
+  for (int r = 0; r < dm.dim[DD_nprm]; r++) {
+    double cd = flts[dm.foff[DF_prm] + B2DEV_PRM_STRIDE * r + 14];
+    if (cd == 6.0) m->condim6 = true;
+    else if (cd != 3.0 && dm.dim[DD_npair] > 0) { delete m; return fail(B2_ERR_UNSUPPORTED, "contact pairs must be condim 3 or 6"); }
+  }
   std::vector<float> f32(n_flts);
   for (int i = 0; i < n_flts; i++) f32[i] = (float)flts[i];
   CK(cudaMalloc(&m->d_ints, sizeof(int) * n_ints)); CK(cudaMalloc(&m->d_flts, sizeof(float) * n_flts));
@@ -266,20 +273,22 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
   memset(&b->tp, 0, sizeof(b->tp));
-  int task_solver = -1, keep_frames = 0, xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
-  if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); }
+  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
+  if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); memcpy(b->tp.aux_i, task->aux_i, sizeof(task->aux_i)); memcpy(b->tp.aux_f, task->aux_f, sizeof(task->aux_f)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) task_solver = T::SOLVER; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
     case TASK_BIPEDAL_RESCUE: B2_TASK_DIMS(RescueTask); break;
     case TASK_HUMANOID_CONSTRUCTION: B2_TASK_DIMS(ConstructionTask); break;
     case TASK_HUMANOID_MARTIAL_ARTS: B2_TASK_DIMS(MartialArtsTask); break;
+    case TASK_ROBOTIC_ARM_ASSEMBLY: B2_TASK_DIMS(ArmTask); break;
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
+  if (m->condim6 && !task_c6) { delete b; return fail(B2_ERR_UNSUPPORTED, "the model has condim-6 pairs but the task kernel is built for 4-row pyramids"); }
   if (task_solver >= 0 && task_solver != dim[DD_solver]) { delete b; return fail(B2_ERR_UNSUPPORTED, "the task kernel is compiled for a different <option solver> than the model's"); }
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);

@@ -232,7 +232,8 @@ __device__ __noinline__ int c_cylinder_cylinder(float* dst, V3 p1, const float* 
   }
   if (side) {
     V3 q1 = p1 + a1 * x1, d = (p2 + a2 * x2) - q1; float dd = norm(d);
-    if (dd > 1e-9f) { best = dd - s1[0] - s2[0]; bn = d * (1.0f / dd); bpos = q1 + bn * (s1[0] + 0.5f * best); }
+    // (nearly) intersecting axes have no side-against-side direction
+    if (dd > 1e-6f) { best = dd - s1[0] - s2[0]; bn = d * (1.0f / dd); bpos = q1 + bn * (s1[0] + 0.5f * best); }
   }
   for (int g = 0; g < 2; g++) {
     V3 pa = g ? p2 : p1, pb = g ? p1 : p2; const float* ma = g ? m2 : m1; const float* mb = g ? m1 : m2;
@@ -242,7 +243,7 @@ __device__ __noinline__ int c_cylinder_cylinder(float* dst, V3 p1, const float* 
       if (dd < best - 1e-6f) { best = dd; bpos = mulmat(mb, cp + n * (dd * 0.5f)) + pb; bn = mulmat(mb, n) * (g ? 1.f : -1.f); }
     }
   }
-  if (best > margin) return 0;
+  if (best > margin + 1e-6f) return 0;    // stacked coaxial cylinders touch exactly (arm base / shoulder): the tie is a contact in both precisions
   raw_put(dst, best, bpos, bn, v3(0, 0, 0));
   return 1;
 }

@@ -145,7 +145,9 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // otherwise they are the model's static islands, set up once per launch.
 // SOLVER: 0 the task's model uses PGS, 2 Newton (the other solver is not compiled into that kernel), -1 decided at run time
 // from the model (physics-only batches).
-template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1>
+// C6: the model has condim-6 pairs (10-row pyramids: two tangential, one torsional, two rolling directions); otherwise every
+// contact is a 4-row pyramid and the row bookkeeping uses the cheaper fixed-size arithmetic.
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1, bool C6 = false>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -680,6 +682,12 @@ struct Engine {
     sync();
   }
 
+  // rows of contact c: 2 (condim - 1)
+  __device__ __forceinline__ int contact_rows(int c) const {
+    if (!C6) return 4;
+    int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]);
+    return F(DF_prm)[B2DEV_PRM_STRIDE * PI(DI_pair_prm)[p] + 14] == 6.0f ? 10 : 4;
+  }
   // ---- B.5 rows: joint limits then pyramidal contacts, stably partitioned by island
   __device__ void make_rows(unsigned long long* counters) {
     const int* limj = I(DI_lim_jnt); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
@@ -689,7 +697,7 @@ struct Engine {
     int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON];
     if (lane < B2_MAX_ISLANDS) p_isl_n()[lane] = 0;
     sync();
-    const int maxrows = B2_ISLAND_ROWS;
+    const int maxrows = newton() ? rowCap() : B2_ISLAND_ROWS;       // the 128-row island limit is the PGS register layout's
     int dropped = 0;
     unsigned lt = (1u << lane) - 1u;
     for (int c0 = 0; c0 < nlim; c0 += 32) {
@@ -722,11 +730,19 @@ struct Engine {
       unsigned peers = __match_any_sync(B2_FULL, isl);
       int before = 4 * __popc(peers & lt), total = 4 * __popc(peers);
       int base = valid ? p_isl_n()[isl] : 0;
+      const int nr = valid ? contact_rows(c) : 0;
+      int fit_total = 0;
+      if (C6) {        // pyramids of 4 or 10 rows: weighted prefix over the lanes of the same island
+        before = 0;
+        for (int src = 0; src < 32; src++) { int w = __shfl_sync(B2_FULL, nr, src); if (((peers >> src) & 1) && src < lane) before += w; }
+        const int mine = (valid && base + before + nr <= maxrows) ? nr : 0;
+        for (int src = 0; src < 32; src++) { int w = __shfl_sync(B2_FULL, mine, src); if ((peers >> src) & 1) fit_total += w; }
+      }
       sync();
       if (valid) {
         int r0 = base + before;
-        if (r0 + 4 <= maxrows) p_con_row()[c] = r0; else { p_con_row()[c] = -1; dropped++; }
-        if ((peers & lt) == 0) p_isl_n()[isl] = base + min(total, base < maxrows ? ((maxrows - base) / 4) * 4 : 0);
+        if (r0 + nr <= maxrows) p_con_row()[c] = r0; else { p_con_row()[c] = -1; dropped++; }
+        if ((peers & lt) == 0) p_isl_n()[isl] = C6 ? base + fit_total : base + min(total, base < maxrows ? ((maxrows - base) / 4) * 4 : 0);
       }
       sync();
     }
@@ -749,7 +765,15 @@ struct Engine {
           while (nf > 0 && r4(nf * ldj) + (newton ? newton_floats(nf, ndk) : a_floats(nf)) > avail) nf--;
           n = min(n, nf); ovf++;
         }
-        { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
+        if (!C6) { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
+        else if (n < min(p_isl_n()[k], maxrows) && n > p_isl_nl()[k]) {
+          int nb = p_isl_nl()[k];
+          for (int c = 0; c < ncon; c++) {
+            int r = p_con_row()[c];
+            if (r >= 0 && contact_island(c) == k) { int e = r + contact_rows(c); if (e <= n && e > nb) nb = e; }
+          }
+          n = nb;
+        }
         cut += min(p_isl_n()[k], maxrows) - n;
         int needJ = r4(n * ldj), needA = newton ? newton_floats(n, ndk) : a_floats(n);
         int aoff = used + needJ;
@@ -802,18 +826,19 @@ struct Engine {
     const float* dinvw = F(DF_dof_invweight0); const float* binvw = F(DF_body_invweight0); const float* prm = F(DF_prm);
     int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON], nmw = dim(DD_nmaskw);
     float timestep = P.opt[DO_timestep], impratio = P.opt[DO_impratio];
-    // row_info: limits  -> (joint << 2) | side ; contacts -> 0x40000000 | (contact << 2) | dir
+    // row_info: limits  -> (joint << 4) | side ; contacts -> 0x40000000 | (contact << 4) | row of the pyramid
     for (int k = tl; k < 2 * nlim; k += TEAM) {
       int r = p_lim_row()[k]; if (r < 0) continue;
       int j = limj[k >> 1], isl = p_tree_isl()[dtree[jd[j]]];
       if (r >= p_isl_n()[isl]) continue;
-      p_row_info()[p_isl_adr()[isl] + r] = (j << 2) | (k & 1);
+      p_row_info()[p_isl_adr()[isl] + r] = (j << 4) | (k & 1);
     }
     for (int c = tl; c < ncon; c += TEAM) {
       int r = p_con_row()[c]; if (r < 0) continue;
       int isl = contact_island(c);
-      if (r + 4 > p_isl_n()[isl]) { p_con_row()[c] = -1; continue; }
-      for (int d = 0; d < 4; d++) p_row_info()[p_isl_adr()[isl] + r + d] = 0x40000000 | (c << 2) | d;
+      const int nr = contact_rows(c);
+      if (r + nr > p_isl_n()[isl]) { p_con_row()[c] = -1; continue; }
+      for (int d = 0; d < nr; d++) p_row_info()[p_isl_adr()[isl] + r + d] = 0x40000000 | (c << 4) | d;
     }
     team_sync();
     // J entries
@@ -825,7 +850,7 @@ struct Engine {
         int i = item / nd, c = item - i * nd, d = cols.dof(c);
         int info = p_row_info()[e0 + i]; float val = 0.f;
         if (info & 0x40000000) {
-          int ci = (info >> 2) & 0x0fffffff, dir = info & 3;
+          int ci = (info >> 4) & 0x03ffffff, dir = info & 15;
           const float* con = p_con() + B2_CON_STRIDE * ci;
           int p = __float_as_int(con[13]);
           int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
@@ -833,15 +858,17 @@ struct Engine {
           int sgn = in2 - in1;
           if (sgn) {
             const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
-            float mu = pr[2 + (dir >> 1)];
-            V3 nrm = ld3(con + 4), tv = ld3(con + 7 + 3 * (dir >> 1));
-            V3 dv = nrm + tv * ((dir & 1) ? -mu : mu);
+            const int kd = dir >> 1;       // 0, 1: translation along t1, t2; 2, 3, 4 (condim 6): rotation about n, t1, t2
+            float mu = pr[2 + kd]; mu = (dir & 1) ? -mu : mu;
+            V3 nrm = ld3(con + 4);
             S6 cd = ld6(p_cdof() + 6 * d);
             V3 off = ld3(con + 1) - ld3(p_rootcom() + 3 * ridx[dbody[d]]);
-            val = (float)sgn * dot(dv, cd.l + cross(cd.a, off));
+            V3 lin = cd.l + cross(cd.a, off);
+            if (!C6 || kd < 2) val = (float)sgn * dot(nrm + ld3(con + 7 + 3 * kd) * mu, lin);
+            else val = (float)sgn * (dot(nrm, lin) + mu * dot(kd == 2 ? nrm : ld3(con + 7 + 3 * (kd - 3)), cd.a));
           }
         } else {
-          int j = info >> 2;
+          int j = info >> 4;
           if (jd[j] == d) val = (info & 1) ? -1.f : 1.f;
         }
         J[i * ldj + c] = val;
@@ -854,7 +881,7 @@ struct Engine {
       int info = p_row_info()[e];
       float pos, margin, da, solref0, solref1; const float* simp; int isl; float mu0 = 0.f; bool iscon = info & 0x40000000;
       if (iscon) {
-        int ci = (info >> 2) & 0x0fffffff;
+        int ci = (info >> 4) & 0x03ffffff;
         const float* con = p_con() + B2_CON_STRIDE * ci; int p = __float_as_int(con[13]);
         const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
         int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
@@ -864,7 +891,7 @@ struct Engine {
         da = tran + mu0 * mu0 * tran;   // first row of the pyramid sets R for all of its rows
         solref0 = pr[7]; solref1 = pr[8]; simp = pr + 9;
       } else {
-        int j = info >> 2, side = info & 1; float q = p_qpos()[jq[j]];
+        int j = info >> 4, side = info & 1; float q = p_qpos()[jq[j]];
         isl = p_tree_isl()[dtree[jd[j]]];
         pos = side ? jrange[2 * j + 1] - q : q - jrange[2 * j]; margin = jmargin[j]; da = dinvw[jd[j]];
         solref0 = jsol[8 * j]; solref1 = jsol[8 * j + 1]; simp = jsol + 8 * j + 2;

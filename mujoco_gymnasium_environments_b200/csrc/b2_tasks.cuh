@@ -6,7 +6,7 @@
 
 namespace b2 {
 
-enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4, TASK_HUMANOID_CONSTRUCTION = 5, TASK_HUMANOID_MARTIAL_ARTS = 6 };
+enum { TASK_NONE = 0, TASK_QUADRUPED_PARKOUR = 1, TASK_HUMANOID_DANCING = 2, TASK_HUMANOID_SOCCER = 3, TASK_BIPEDAL_RESCUE = 4, TASK_HUMANOID_CONSTRUCTION = 5, TASK_HUMANOID_MARTIAL_ARTS = 6, TASK_ROBOTIC_ARM_ASSEMBLY = 7 };
 
 // counter-based RNG (splitmix64 finaliser over (seed, env, episode, draw)); documented stream layout in DESIGN.md
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
@@ -21,6 +21,7 @@ struct TaskParams {
   int task;
   int ids[16];      // body / joint / actuator ids resolved by the host from names (mj_name2id stand-in)
   float act_lo[40], act_hi[40];
+  int aux_i[64]; float aux_f[32];   // task-specific tables (see B2TaskDesc)
 };
 
 // ------------------------------------------------------------------------------------------------ quadruped
@@ -33,7 +34,7 @@ struct TaskParams {
 struct QuadrupedTask {
   static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32, ARENA_SPAN = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -174,7 +175,7 @@ struct QuadrupedTask {
 struct DancingTask {
   static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -358,7 +359,7 @@ struct DancingTask {
 struct SoccerTask {
   static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -531,7 +532,7 @@ struct SoccerTask {
 struct RescueTask {
   static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -687,7 +688,7 @@ struct RescueTask {
 struct ConstructionTask {
   static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 64, ARENA_SPAN = 40;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -768,7 +769,7 @@ struct ConstructionTask {
 struct MartialArtsTask {
   static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 47;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -831,6 +832,140 @@ struct MartialArtsTask {
     int term = 0;
     if (xp[3 * torso + 2] < 0.5f) { ti[3] += 1; term = 1; }
     else if (fabsf(xp[3 * torso]) > 5.5f || fabsf(xp[3 * torso + 1]) > 5.5f) term = 1;
+    *terminated = term; *truncated = ti[0] >= MAX_STEPS;
+    tf[0] += reward;
+    return reward;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ robotic arm assembly
+// robotic_arm_assembly_env/assembly_env.py: reset :162-192 (+ _reset_components :194-218, 10 settle steps), step :220-250,
+// _apply_action :252-265, _update_task_state :267-297, _get_gripper_contacts :299-322, _calculate_reward :331-387,
+// _get_max_contact_force :389-397, _check_termination :399-417, _get_observation :419-472.
+// Ten Euler sub-steps of 2 ms, Newton-50/1e-10, 18 condim-6 pad pairs (CONDIM6).  The reference matches geom *names* by
+// substring per contact; the host resolves that once into aux_i[geom] (0..8 component, 100 gripper pad, -1 neither).
+// `list(set(contacts))[0]` is hash-order dependent in the reference; the first component in contact order is taken.
+// ti: [0] step_count [1] assembly_progress bits [2] episode id [3] held component (-1 none) [4] task phase (0 idle 1 pickup
+//     2 transport 4 insert) [5..13] component status (0 in_bin 1 held 2 assembled 3 dropped)
+// tf: [0] cumulative_reward
+// ids: [0..8] component bodies in assembly order, [9] body of ee_site    aux_f: [3k..3k+2] target of component k, [27..29] ee_site offset
+struct ArmTask {
+  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9;
+  static constexpr int SOLVER = 2;
+  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+
+  template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
+    for (int i = E.lane; i < ACT; i += 32) {
+      float a = clampf(act[i], tp.act_lo[i], tp.act_hi[i]);
+      act_clipped[i] = a;
+      if (i < 7) E.p_ctrl()[i] = a;
+      else if (i == 7) { E.p_ctrl()[7] = a / 1000.0f; E.p_ctrl()[8] = a / 1000.0f; }      // opening in mm for both fingers; the force entry is unused (:261-265)
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
+  template <class EN> __device__ static void reset_state(EN& E, const TaskParams& tp, const BatchView&, int, int* ti, float* tf,
+                                     const float*) {
+    E.reset_data();
+    const int* jq = E.I(DI_jnt_qposadr); const int* bja = E.I(DI_body_jntadr);
+    if (E.lane == 0) {
+      float* q = E.p_qpos();
+      q[0] = 0.f; q[1] = -0.5f; q[2] = 0.5f; q[3] = 0.f; q[4] = 0.5f; q[5] = 0.f; q[6] = 0.f;             // home (:172)
+      const float ini[27] = {-0.6f, 0.3f, 0.76f, -0.6f, -0.3f, 0.76f, -0.58f, -0.3f, 0.76f, -0.62f, -0.3f, 0.76f, -0.6f, -0.28f, 0.76f,
+                             -0.6f, 0.f, 0.76f, 0.6f, 0.3f, 0.76f, 0.6f, -0.3f, 0.76f, 0.6f, 0.f, 0.76f};                      // :197-207 in assembly order
+      for (int k = 0; k < 9; k++) {
+        int a = jq[bja[tp.ids[k]]];
+        q[a] = ini[3 * k]; q[a + 1] = ini[3 * k + 1]; q[a + 2] = ini[3 * k + 2]; q[a + 3] = 1.f; q[a + 4] = 0.f; q[a + 5] = 0.f; q[a + 6] = 0.f;
+      }
+      int ep = ti[2];
+      for (int k = 0; k < NTI; k++) ti[k] = 0;
+      ti[2] = ep + 1; ti[3] = -1; tf[0] = 0.f;
+      *E.p_time() = 0.f;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static float max_contact_force(EN& E) {
+    float mx = 0.f; const int ncon = E.p_misc()[MISC_NCON];
+    for (int c = 0; c < ncon; c++) mx = fmaxf(mx, fabsf(E.p_con()[B2_CON_STRIDE * c]) * 1000.0f);
+    return mx;
+  }
+  // step_count += 1 (:222) and _update_task_state (:267-297)
+  template <class EN> __device__ static void post_physics(EN& E, const TaskParams& tp, int* ti, float*) {
+    if (E.lane == 0) {
+      ti[0] += 1;
+      const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
+      const int ncon = E.p_misc()[MISC_NCON];
+      int first = -1;
+      for (int c = 0; c < ncon && first < 0; c++) {
+        int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
+        int k1 = tp.aux_i[gid[pc1[p]]], k2 = tp.aux_i[gid[pc2[p]]];
+        if (k1 == 100) { if (k2 >= 0 && k2 < 9) first = k2; }
+        else if (k2 == 100) { if (k1 >= 0 && k1 < 9) first = k1; }
+      }
+      int held = ti[3];
+      if (first >= 0) {
+        if (held < 0) { ti[3] = first; ti[4] = 1; ti[5 + first] = 1; }
+        else ti[4] = 2;
+      } else if (held >= 0) {
+        const float* xp = E.p_xpos() + 3 * tp.ids[held]; const float* tg = tp.aux_f + 3 * held;
+        float dx = xp[0] - tg[0], dy = xp[1] - tg[1], dz = xp[2] - tg[2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) < 0.002f) { ti[1] |= 1 << held; ti[5 + held] = 2; ti[4] = 4; }
+        else { ti[5 + held] = 3; ti[4] = 0; }
+        ti[3] = -1;
+      } else ti[4] = 0;
+    }
+    E.sync();
+  }
+  template <class EN> __device__ static void observe(EN& E, const TaskParams& tp, float* obs) {
+    const int* ti = E.p_ti();
+    const float mf = max_contact_force(E);
+    const int eb = tp.ids[9]; const float* xm = E.p_xmat() + 9 * eb; const float* so = tp.aux_f + 27;
+    int nprog = __popc((unsigned)ti[1] & 0x1ffu);
+    for (int i = E.lane; i < OBS; i += 32) {
+      float v = 0.f;
+      if (i < 7) v = E.p_qpos()[i];
+      else if (i < 14) v = E.p_qvel()[i - 7];
+      else if (i == 14) v = (E.p_qpos()[7] + E.p_qpos()[8]) / 2.0f * 1000.0f;
+      else if (i == 15) v = mf;
+      else if (i < 19) { int k = i - 16; v = E.p_xpos()[3 * eb + k] + xm[3 * k] * so[0] + xm[3 * k + 1] * so[1] + xm[3 * k + 2] * so[2]; }
+      else if (i < 23) v = i == 19 ? 1.f : 0.f;
+      else if (i < 79) { int k = (i - 23) / 7, f = (i - 23) % 7; v = f < 3 ? E.p_xpos()[3 * tp.ids[k] + f] : (f == 3 ? 1.f : 0.f); }   // components 0..7 (component 8 is overwritten below)
+      else if (i < 87) v = (float)((ti[1] >> (i - 79)) & 1);
+      else if (i == 87) v = ti[3] >= 0 ? 1.f : 0.f;
+      else if (i == 88) v = (float)ti[3];
+      else if (i < 104) v = 0.5f;
+      else if (i == 108) v = (float)nprog / 9.0f * 100.0f;
+      else if (i == 109) v = (float)ti[4];
+      obs[i] = v;
+    }
+  }
+  template <class EN> __device__ static float reward_and_done(EN& E, const TaskParams& tp, const float*, int* ti, float* tf,
+                                          int* terminated, int* truncated) {
+    float reward = -10.0f;
+    const int held = ti[3];
+    if (ti[4] == 1 && held >= 0) reward += 1000.f;
+    int ndropped = 0;
+    for (int k = 0; k < 9; k++) {
+      if (((ti[1] >> k) & 1) && ti[5 + k] == 2) reward += (k == 0 || k == 5) ? 2000.f : (k >= 1 && k <= 4 ? 500.f : 1000.f);
+      if (ti[5 + k] == 3) ndropped++;
+    }
+    if (held >= 0) {
+      const float* xp = E.p_xpos() + 3 * tp.ids[held]; const float* tg = tp.aux_f + 3 * held;
+      float dx = xp[0] - tg[0], dy = xp[1] - tg[1], dz = xp[2] - tg[2], dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (dist < 0.05f) reward += 300.f * (1.f - dist / 0.05f);
+    }
+    const float mf = max_contact_force(E);
+    if (mf > 50.0f) reward -= 5000.f; else if (mf < 10.0f) reward += 200.f;
+    float s = 0.f;
+    for (int i = 0; i < 7; i++) s += fabsf(E.p_qvel()[i]);
+    reward += -s * 10.f;
+    reward -= 2000.f * (float)ndropped;
+    const bool all = (ti[1] & 0x1ff) == 0x1ff;
+    if (all) reward += 10000.f;
+    const float lo[7] = {-3.14f, -2.36f, -2.97f, -3.14f, -2.09f, -3.14f, -3.14f}, hi[7] = {3.14f, 0.78f, 2.97f, 3.14f, 2.09f, 3.14f, 3.14f};
+    int term = all ? 1 : 0;
+    for (int i = 0; i < 7; i++) { float q = E.p_qpos()[i]; if (q < lo[i] * 0.95f || q > hi[i] * 0.95f) term = 1; }
     *terminated = term; *truncated = ti[0] >= MAX_STEPS;
     tf[0] += reward;
     return reward;

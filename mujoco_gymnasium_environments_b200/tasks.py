@@ -179,6 +179,44 @@ def _martial_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- robotic arm assembly
+ARM_SEQUENCE = ["pcb", "screw1", "screw2", "screw3", "screw4", "cpu", "battery", "cable", "cover"]       # assembly_env.py:46-49
+ARM_TARGETS = {"pcb": [0, 0, 0.74], "cpu": [0, 0, 0.76], "screw1": [-0.08, -0.06, 0.735], "screw2": [0.08, -0.06, 0.735],
+               "screw3": [-0.08, 0.06, 0.735], "screw4": [0.08, 0.06, 0.735], "battery": [0.05, 0, 0.77],
+               "cable": [-0.05, 0, 0.77], "cover": [0, 0, 0.79]}                                           # :65-75
+
+
+def arm_geom_component(name: str) -> int:
+    """The reference's per-contact geom-name matching (assembly_env.py:299-322) resolved once per geom: 100 for a gripper
+    pad, the index of the first component (assembly order) whose name is a substring, else -1."""
+    if name and "gripper" in name and "pad" in name:
+        return 100
+    for i, comp in enumerate(ARM_SEQUENCE):
+        if name and comp in name:
+            return i
+    return -1
+
+
+def _arm_desc(t: ModelTables) -> capi.B2TaskDesc:
+    d = capi.B2TaskDesc()
+    d.task = capi.TASK_ROBOTIC_ARM_ASSEMBLY
+    for k, comp in enumerate(ARM_SEQUENCE):
+        d.ids[k] = t.name2id("body", comp)
+        for a in range(3):
+            d.aux_f[3 * k + a] = float(ARM_TARGETS[comp][a])
+    site = t.name2id("site", "ee_site")                        # :436
+    d.ids[9] = int(t.site_bodyid[site])
+    for a in range(3):
+        d.aux_f[27 + a] = float(np.asarray(t.site_pos).reshape(-1, 3)[site][a])
+    assert int(t.ngeom) <= 64
+    for g in range(64):
+        d.aux_i[g] = arm_geom_component(t.id2name("geom", g)) if g < int(t.ngeom) else -1
+    lo = [-2.0] * 7 + [0.0, 0.0]; hi = [2.0] * 7 + [100.0, 50.0]    # :150-152
+    for k in range(9):
+        d.act_lo[k] = lo[k]; d.act_hi[k] = hi[k]
+    return d
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -222,4 +260,10 @@ TASKS: Dict[str, TaskSpec] = {
         # the reference declares 85 entries but returns 113: the actual length is exposed
         observation_space=lambda t: Box(np.full(113, -np.inf, np.float32), np.full(113, np.inf, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "combo_chain", "stance_stability", "current_step"]),
+    "robotic_arm_assembly": TaskSpec(
+        name="robotic_arm_assembly", task_id=capi.TASK_ROBOTIC_ARM_ASSEMBLY, obs_dim=110, act_dim=9, max_episode_steps=150000,
+        frame_skip=10, render_fps=50, bytes_per_env_step=2266, describe=_arm_desc,
+        action_space=lambda t: Box(np.array([-2.0] * 7 + [0.0, 0.0], np.float32), np.array([2.0] * 7 + [100.0, 50.0], np.float32), dtype=np.float32),
+        observation_space=lambda t: Box(np.full(110, -np.inf, np.float32), np.full(110, np.inf, np.float32), dtype=np.float32),
+        info_keys=["step_count", "assembly_progress", "component_status", "task_phase", "held_component", "cumulative_reward", "success"]),
 }

@@ -676,7 +676,7 @@ static int cylinder_cylinder(RawCon *c, const real *pos1, const real *mat1, cons
     real q1[3], q2[3], d[3];
     for (int k = 0; k < 3; k++) { q1[k] = pos1[k] + a1[k]*x1; q2[k] = pos2[k] + a2[k]*x2; d[k] = q2[k] - q1[k]; }
     real dd = norm3(d);
-    if (dd > 1e-9) {
+    if (dd > 1e-6) {                               /* (nearly) intersecting axes have no side-against-side direction */
       best = dd - size1[0] - size2[0];
       for (int k = 0; k < 3; k++) { bn[k] = d[k]/dd; bpos[k] = q1[k] + bn[k]*(size1[0] + 0.5*best); }
     }
@@ -698,7 +698,7 @@ static int cylinder_cylinder(RawCon *c, const real *pos1, const real *mat1, cons
       }
     }
   }
-  if (best > margin) return 0;
+  if (best > margin + 1e-6) return 0;     /* stacked coaxial cylinders touch exactly (arm base / shoulder): the tie is a contact in both precisions */
   c->dist = best;
   for (int k = 0; k < 3; k++) { c->pos[k] = bpos[k]; c->frame[k] = bn[k]; c->frame[3+k] = 0; }
   return 1;

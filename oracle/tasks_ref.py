@@ -986,6 +986,167 @@ class HumanoidMartialArtsRef:
         return bool(abs(p[0]) > 5.5 or abs(p[1]) > 5.5)
 
 
+class RoboticArmAssemblyRef:
+    """robotic_arm_assembly_env/assembly_env.py restated: __init__ :28-95, reset :162-192, _reset_components :194-218,
+    step :220-250, _apply_action :252-265, _update_task_state :267-297, _get_gripper_contacts :299-322, _calculate_reward
+    :331-387, _get_max_contact_force :389-397, _check_termination :399-417, _get_observation :419-472.
+    Ten Euler sub-steps of 2 ms per env.step, Newton-50/1e-10, condim-6 pad pairs.  Geom names are matched by substring in
+    assembly order exactly as the reference does (so ``cpu_socket`` on the PCB counts as the CPU and ``pcb_bin_base`` as the
+    PCB).  ``list(set(contacts))[0]`` is hash-order dependent in the reference; here the first component in contact order
+    is taken.  The observation writes overlap (nine components in an eight-component layout) and are applied in the
+    reference's order."""
+
+    SEQ = ["pcb", "screw1", "screw2", "screw3", "screw4", "cpu", "battery", "cable", "cover"]
+    TARGETS = {"pcb": [0, 0, 0.74], "cpu": [0, 0, 0.76], "screw1": [-0.08, -0.06, 0.735], "screw2": [0.08, -0.06, 0.735],
+               "screw3": [-0.08, 0.06, 0.735], "screw4": [0.08, 0.06, 0.735], "battery": [0.05, 0, 0.77],
+               "cable": [-0.05, 0, 0.77], "cover": [0, 0, 0.79]}
+    INITIAL = {"pcb": [-0.6, 0.3, 0.76], "cpu": [-0.6, 0, 0.76], "screw1": [-0.6, -0.3, 0.76], "screw2": [-0.58, -0.3, 0.76],
+               "screw3": [-0.62, -0.3, 0.76], "screw4": [-0.6, -0.28, 0.76], "battery": [0.6, 0.3, 0.76],
+               "cable": [0.6, -0.3, 0.76], "cover": [0.6, 0, 0.76]}
+    PHASES = {"idle": 0, "pickup": 1, "transport": 2, "align": 3, "insert": 4}
+
+    def __init__(self, tables=None, seed=None):
+        self.tables = tables if tables is not None else _load("robotic_arm_assembly")
+        t = self.tables
+        self.model = ref.load_model(t)
+        self.data = ref.RefData(self.model)
+        self.max_episode_steps = 150000; self.skip_frames = 10
+        self.assembly_tolerance = 0.002; self.force_threshold = 50.0; self.gentle_force_threshold = 10.0
+        self.action_low = np.array([-2.0] * 7 + [0.0, 0.0]); self.action_high = np.array([2.0] * 7 + [100.0, 50.0])
+        self.comp_body = {c: t.name2id("body", c) for c in self.SEQ}
+        self.comp_qadr = {c: int(t.jnt_qposadr[int(t.body_jntadr[self.comp_body[c]])]) for c in self.SEQ}
+        self.ee_site = t.name2id("site", "ee_site")
+        self.geom_names = [t.id2name("geom", g) for g in range(int(t.ngeom))]
+        self.reset()
+
+    @classmethod
+    def geom_component(cls, name):
+        """-1: neither, 100: a gripper pad, else the index of the first component whose name is a substring (:306-320)."""
+        if name and "gripper" in name and "pad" in name:
+            return 100
+        for i, comp in enumerate(cls.SEQ):
+            if name and comp in name:
+                return i
+        return -1
+
+    def reset(self, seed=None, draws=None):
+        m, d = self.model, self.data
+        ref.mj_resetData(m, d)
+        d.qpos[0:7] = [0, -0.5, 0.5, 0, 0.5, 0, 0]
+        for c in self.SEQ:
+            a = self.comp_qadr[c]
+            d.qpos[a:a + 3] = self.INITIAL[c]; d.qpos[a + 3:a + 7] = [1, 0, 0, 0]
+        self.step_count = 0
+        self.assembly_progress = {c: False for c in self.SEQ}
+        self.component_status = {c: "in_bin" for c in self.SEQ}
+        self.task_phase = "idle"; self.held_component = None; self.cumulative_reward = 0.0
+        ref.mj_step(m, d, 10)
+        return self._get_observation(), dict(step_count=0)
+
+    def step(self, action):
+        d = self.data
+        self.step_count += 1
+        a = np.clip(np.asarray(action, np.float64), self.action_low, self.action_high)
+        d.ctrl[0:7] = a[0:7]
+        d.ctrl[7] = a[7] / 1000.0; d.ctrl[8] = a[7] / 1000.0
+        ref.mj_step(self.model, d, self.skip_frames)
+        self._update_task_state()
+        reward = self._calculate_reward()
+        self.cumulative_reward += reward
+        terminated = self._check_termination()
+        truncated = self.step_count >= self.max_episode_steps
+        return self._get_observation(), reward, terminated, truncated, dict(step_count=self.step_count, task_phase=self.task_phase)
+
+    def _gripper_contacts(self):
+        out = []
+        for c in self.data.contact:
+            k1 = self.geom_component(self.geom_names[c.geom1]); k2 = self.geom_component(self.geom_names[c.geom2])
+            if k1 == 100:
+                if 0 <= k2 < 9 and self.SEQ[k2] not in out: out.append(self.SEQ[k2])
+            elif k2 == 100:
+                if 0 <= k1 < 9 and self.SEQ[k1] not in out: out.append(self.SEQ[k1])
+        return out
+
+    def _update_task_state(self):
+        contacts = self._gripper_contacts()
+        if contacts:
+            if self.held_component is None:
+                self.held_component = contacts[0]; self.task_phase = "pickup"
+                self.component_status[self.held_component] = "held"
+            else:
+                self.task_phase = "transport"
+        elif self.held_component:
+            pos = self.data.xpos[self.comp_body[self.held_component]]
+            if np.linalg.norm(pos - np.array(self.TARGETS[self.held_component])) < self.assembly_tolerance:
+                self.assembly_progress[self.held_component] = True
+                self.component_status[self.held_component] = "assembled"; self.task_phase = "insert"
+            else:
+                self.component_status[self.held_component] = "dropped"; self.task_phase = "idle"
+            self.held_component = None
+        else:
+            self.task_phase = "idle"
+
+    def _max_contact_force(self):
+        mx = 0.0
+        for c in self.data.contact:
+            mx = max(mx, abs(c.dist) * 1000)
+        return mx
+
+    def _calculate_reward(self):
+        reward = -10.0
+        if self.task_phase == "pickup" and self.held_component:
+            reward += 1000
+        for comp, done in self.assembly_progress.items():
+            if done and self.component_status[comp] == "assembled":
+                reward += 2000 if comp in ("pcb", "cpu") else (500 if comp.startswith("screw") else 1000)
+        if self.held_component:
+            pos = self.data.xpos[self.comp_body[self.held_component]]
+            dist = float(np.linalg.norm(pos - np.array(self.TARGETS[self.held_component])))
+            if dist < 0.05:
+                reward += 300 * (1 - dist / 0.05)
+        mf = self._max_contact_force()
+        if mf > self.force_threshold:
+            reward -= 5000
+        elif mf < self.gentle_force_threshold:
+            reward += 200
+        reward += -float(np.sum(np.abs(self.data.qvel[0:7]))) * 10
+        for comp, st in self.component_status.items():
+            if st == "dropped":
+                reward -= 2000
+        if all(self.assembly_progress.values()):
+            reward += 10000
+        return float(reward)
+
+    def _check_termination(self):
+        if all(self.assembly_progress.values()):
+            return True
+        q = self.data.qpos[0:7]
+        lo = np.array([-3.14, -2.36, -2.97, -3.14, -2.09, -3.14, -3.14]); hi = np.array([3.14, 0.78, 2.97, 3.14, 2.09, 3.14, 3.14])
+        return bool(np.any(q < lo * 0.95) or np.any(q > hi * 0.95))
+
+    def _get_observation(self):
+        d = self.data
+        obs = np.zeros(110, dtype=np.float32)
+        obs[0:7] = d.qpos[0:7]; obs[7:14] = d.qvel[0:7]
+        obs[14] = (d.qpos[7] + d.qpos[8]) / 2.0 * 1000
+        obs[15] = self._max_contact_force()
+        obs[16:19] = d.site_xpos[self.ee_site]; obs[19:23] = [1, 0, 0, 0]
+        idx = 23
+        for comp in self.SEQ:
+            obs[idx:idx + 3] = d.xpos[self.comp_body[comp]]; obs[idx + 3:idx + 7] = [1, 0, 0, 0]
+            idx += 7
+        for i, comp in enumerate(self.SEQ):
+            obs[79 + i] = float(self.assembly_progress[comp])
+        obs[87] = float(self.held_component is not None)
+        obs[88] = self.SEQ.index(self.held_component) if self.held_component else -1
+        obs[89:114] = 0.5
+        obs[104:110] = 0
+        obs[108] = sum(self.assembly_progress.values()) / len(self.assembly_progress) * 100
+        obs[109] = self.PHASES.get(self.task_phase, 0)
+        return obs
+
+
 TASKS = {"quadruped_parkour": QuadrupedParkourRef, "humanoid_dancing": HumanoidDancingRef, "humanoid_soccer": HumanoidSoccerRef,
          "bipedal_rescue": BipedalRescueRef, "humanoid_construction": HumanoidConstructionRef,
-         "humanoid_martial_arts": HumanoidMartialArtsRef}
+         "humanoid_martial_arts": HumanoidMartialArtsRef,
+         "robotic_arm_assembly": RoboticArmAssemblyRef}

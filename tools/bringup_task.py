@@ -43,6 +43,8 @@ def make_inject(task, rng, n):
         return inj
     if task == "humanoid_martial_arts":
         return rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
+    if task == "robotic_arm_assembly":
+        return np.zeros((n, 1), np.float32)
     raise KeyError(task)
 
 
@@ -55,6 +57,8 @@ def ref_reset(task, env, inj):
         return env.reset(draws=[float(x) for x in inj])
     if task in ("humanoid_construction", "humanoid_martial_arts"):
         return env.reset(draws=tuple(float(x) for x in inj))
+    if task == "robotic_arm_assembly":
+        return env.reset()
 
 
 def main():
@@ -141,7 +145,7 @@ def main():
     print("stats", env.episode_stats())
     env.close()
     # ---------------- throughput
-    for N in ((2048,) if task in ("bipedal_rescue", "humanoid_construction") else (4096, 8192)):
+    for N in ((2048,) if task in ("bipedal_rescue", "humanoid_construction", "robotic_arm_assembly") else (4096, 8192)):
         for sc in (0.02, 1.0):
             env = B200VectorEnv(task, N, device=0, seed=1)
             env.reset()
