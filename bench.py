@@ -35,6 +35,9 @@ WORKLOADS = {
     "humanoid_martial_arts": (4096, 1500, "humanoid_martial_arts_env: {n} envs/GPU lockstep, 1 Euler step (dt 16.67 ms), Newton-50, 47 dofs in 4 trees "
                               "(free humanoid, two free cylinder dummies, hinged board), 294 candidate pairs, uniform random actions over action_space x {s}, "
                               "same-step auto-reset"),
+    "robotic_arm_assembly": (2048, 100, "robotic_arm_assembly_env: {n} envs/GPU lockstep, frame_skip 10 (dt 2 ms), Euler, Newton-50, 63 dofs in 10 trees "
+                             "(7-dof arm + gripper, nine free components), 785 candidate pairs incl. 18 condim-6, uniform random actions over "
+                             "action_space x {s}, same-step auto-reset"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the task's default size, from the
 # `ncu --set full` captures summarised under profiles/ (r01_e quadruped, r01_f dancing, r01_g soccer, r01_h rescue).

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(capi.B2TaskDesc) == 4 + 16 * 4 + 40 * 4 + 40 * 4
+    assert ctypes.sizeof(capi.B2TaskDesc) == 4 + 16 * 4 + 40 * 4 + 40 * 4 + 64 * 4 + 32 * 4
     assert ctypes.sizeof(capi.B2BatchOpts) == 8 * 4
 
 
