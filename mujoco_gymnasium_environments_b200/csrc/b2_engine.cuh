@@ -1322,15 +1322,53 @@ struct Engine {
         // H = M + J' diag(D active) J, lower triangle, then symmetric diagonal scaling H <- S H S with S = diag(H_ii^-1/2):
         // joint inertias span orders of magnitude (finger hinges vs the crane), which fp32 Cholesky does not survive
         // unscaled; the scaled matrix has a unit diagonal
-        for (int q = lane; q < nh; q += 32) {
-          int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-          while (r * (r + 1) / 2 > q) r--;
-          while ((r + 1) * (r + 2) / 2 <= q) r++;
-          int c = q - r * (r + 1) / 2; float h = 0.f;
-          for (int i = 0; i < n; i++) if (jar[i] < 0.f) h = fmaf(J[i * ldj + r] * Dr[i], J[i * ldj + c], h);
-          H[q] = h;
+        if (nd >= 16 && nd <= 64) {
+          // J rows are sparse (a contact touches the dof chains of its two bodies only): per group of rows that belong
+          // to one contact / one limit, list the columns any active row touches and accumulate only their pairs (pays
+          // from ~16 dofs; a free body's 6-dof island has dense rows and takes the plain loop below)
+          for (int q = lane; q < nh; q += 32) H[q] = 0.f;
+          sync();
+          const int* rinfo = p_row_info() + e0; int* clist = reinterpret_cast<int*>(y);
+          const unsigned lt = (1u << lane) - 1u;
+          for (int i0 = 0; i0 < n;) {
+            int g = 1; const int key = rinfo[i0] >> 4;
+            while (i0 + g < n && (rinfo[i0 + g] >> 4) == key) g++;
+            unsigned act = 0;
+            for (int r = 0; r < g; r++) if (jar[i0 + r] < 0.f) act |= 1u << r;
+            if (act) {
+              bool nz0 = false, nz1 = false;
+              for (int r = 0; r < g; r++) if ((act >> r) & 1) {
+                const float* Jr = J + (i0 + r) * ldj;
+                nz0 |= lane < nd && Jr[lane] != 0.f; nz1 |= lane + 32 < nd && Jr[lane + 32] != 0.f;
+              }
+              const unsigned m0 = __ballot_sync(B2_FULL, nz0), m1 = __ballot_sync(B2_FULL, nz1);
+              const int k0 = __popc(m0), kk = k0 + __popc(m1);
+              if (nz0) clist[__popc(m0 & lt)] = lane;
+              if (nz1) clist[k0 + __popc(m1 & lt)] = lane + 32;
+              sync();
+              for (int q = lane; q < kk * (kk + 1) / 2; q += 32) {
+                int a = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+                while (a * (a + 1) / 2 > q) a--;
+                while ((a + 1) * (a + 2) / 2 <= q) a++;
+                const int ca = clist[a], cb = clist[q - a * (a + 1) / 2]; float h = 0.f;
+                for (int r = 0; r < g; r++) if ((act >> r) & 1) { const float* Jr = J + (i0 + r) * ldj; h = fmaf(Jr[ca] * Dr[i0 + r], Jr[cb], h); }
+                H[ca * (ca + 1) / 2 + cb] += h;
+              }
+              sync();
+            }
+            i0 += g;
+          }
+        } else {
+          for (int q = lane; q < nh; q += 32) {
+            int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+            while (r * (r + 1) / 2 > q) r--;
+            while ((r + 1) * (r + 2) / 2 <= q) r++;
+            int c = q - r * (r + 1) / 2; float h = 0.f;
+            for (int i = 0; i < n; i++) if (jar[i] < 0.f) h = fmaf(J[i * ldj + r] * Dr[i], J[i * ldj + c], h);
+            H[q] = h;
+          }
+          sync();
         }
-        sync();
         for (int c = lane; c < nd; c += 32) {
           int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
           for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); H[r * (r + 1) / 2 + cc] += p_M()[m0 + u]; }
