@@ -1246,6 +1246,9 @@ struct Engine {
 #ifndef B2_NEWTON_NOISE
 #define B2_NEWTON_NOISE 5e-7f
 #endif
+#ifndef B2_NEWTON_GRADNOISE
+#define B2_NEWTON_GRADNOISE 1e-6f
+#endif
   __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
   // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
   // shared-memory atomics (one warp, <= a few hundred entries)
@@ -1311,14 +1314,18 @@ struct Engine {
           jar[i] = s - aref[i];
         }
         sync();
-        float g2 = 0.f;
+        float g2 = 0.f; bool resolved = false;
         for (int c = lane; c < nd; c += 32) {
-          float g = Ma[c] - fs[c];
-          for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) g = fmaf(J[i * ldj + c], Dr[i] * x, g); }
+          float g = Ma[c] - fs[c], sabs = fabsf(Ma[c]) + fabsf(fs[c]);
+          for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) { float t = J[i * ldj + c] * (Dr[i] * x); g += t; sabs += fabsf(t); } }
           grad[c] = g; g2 = fmaf(g, g, g2);
+          resolved |= fabsf(g) > B2_NEWTON_GRADNOISE * sabs;
         }
         g2 = warp_sum(g2);
         if (scale * sqrtf(g2) < tol) break;
+        // every gradient entry is below the rounding noise of its own terms: the Newton step it would produce is below the
+        // step-size criterion at the end of the loop, so the factorisation is skipped (typically the second one of a solve)
+        if (!__any_sync(B2_FULL, resolved)) break;
         // H = M + J' diag(D active) J, lower triangle, then symmetric diagonal scaling H <- S H S with S = diag(H_ii^-1/2):
         // joint inertias span orders of magnitude (finger hinges vs the crane), which fp32 Cholesky does not survive
         // unscaled; the scaled matrix has a unit diagonal
