@@ -40,10 +40,13 @@ WORKLOADS = {
                              "action_space x {s}, same-step auto-reset"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the task's default size, from the
-# `ncu --set full` captures summarised under profiles/ (r01_e quadruped, r01_f dancing, r01_g soccer, r01_h rescue).
+# `ncu --set full` captures summarised under profiles/ (r01_i quadruped, r01_f dancing, r01_g soccer, r01_h rescue,
+# r01_j construction, r01_k martial arts, r01_l arm).
 # Below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2.
-NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.139264e6 + 76.032e3), "humanoid_dancing": (8192, 9.365248e6 + 721.408e3),
-               "humanoid_soccer": (4096, 4.960768e6 + 33.024e3), "bipedal_rescue": (2048, 3.231744e6 + 72.96e3)}
+NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.233728e6 + 287.744e3), "humanoid_dancing": (8192, 9.365248e6 + 721.408e3),
+               "humanoid_soccer": (4096, 4.960768e6 + 33.024e3), "bipedal_rescue": (2048, 3.231744e6 + 72.96e3),
+               "humanoid_construction": (2048, 4.565248e6 + 58.88e3), "humanoid_martial_arts": (4096, 5.395456e6 + 12.032e3),
+               "robotic_arm_assembly": (2048, 3.196928e6 + 194.048e3)}
 TASK = "quadruped_parkour"
 WORKLOAD = WORKLOADS[TASK][2]
 
@@ -238,7 +241,7 @@ def main():
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=(NCU_TRAFFIC[TASK][1] if NCU_TRAFFIC.get(TASK, (0, 0))[0] == N else None), peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                           bytes_per_env_step=spec.bytes_per_env_step, kernel_ms=kern_ms,
-                          traffic_source="ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, profiles/r01_[e-h]_*.txt",
+                          traffic_source="ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, profiles/r01_[f-l]_*.txt",
                           note="fp32-latency bound physics: state stays on chip, HBM sees only state load/store"),
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
             episode_stats={k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped",
