@@ -125,3 +125,26 @@ def test_pickup_state_machine_and_class_api(gpu, gold):
     o, r, te, tr, info = e.step(np.zeros(9, np.float32))
     assert isinstance(r, float) and info["step_count"] == 1 and info["task_phase"] in ("idle", "pickup", "transport", "insert")
     e.close()
+
+
+def test_physics_only_batch_selects_newton_and_condim6_at_run_time(gpu, gold):
+    """b2_physics_step / b2_forward on a batch without a task (the kernel that picks the solver from the model and always
+    carries the 10-row pyramid path) must agree with the task kernel's compile-time choices."""
+    torch = gpu["torch"]
+    n = gold["qpos"].shape[0]
+    b = gpu["capi"].Batch(gpu["model"], None, n, 0, 0, con_cap=128, row_cap=512)
+    f = lambda k: torch.tensor(gold[k], dtype=torch.float32)
+    b.set_state(f("qpos"), f("qvel"), f("ctrl"), f("warm"), torch.zeros(n))
+    ncon, geom, dist = b.contacts(128)
+    dbg = b.debug_forward()
+    torch.cuda.synchronize()
+    for k in range(n):
+        m = int(gold["ncon"][k])
+        assert int(ncon[k]) == m and np.array_equal(geom[k, :m].cpu().numpy(), gold["pairs"][k][:m])
+        assert int(dbg["nefc"][k]) == int(gold["nefc"][k])
+        assert rel(dbg["qacc"][k].cpu(), gold["qacc"][k]) < (3e-3 if k < 2 else 3e-4)
+    b.physics_step(1)
+    st = b.get_state()
+    for k in range(n):
+        assert rel(st["qpos"][k].cpu(), gold["qpos1"][k]) < 1e-4 and rel(st["qvel"][k].cpu(), gold["qvel1"][k]) < 1e-4
+    b.close()
