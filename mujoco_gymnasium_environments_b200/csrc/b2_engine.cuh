@@ -1399,23 +1399,25 @@ struct Engine {
           }
           sync();
         }
-        // search = -H^-1 grad: L y = -grad, L' s = y (one pivot per step, dot products spread over the lanes)
+        // search = -H^-1 grad: L z = -S grad, L' x = z, both column-oriented (once an unknown is final every lane subtracts
+        // its multiple from the entries it owns): one warp barrier per pivot and no reductions.  z lives in srch, x in y.
+        for (int c = lane; c < nd; c += 32) y[c] = -grad[c] * Mv[c];
         for (int r = 0; r < nd; r++) {
-          const float* Hr = H + r * (r + 1) / 2; float sdot = 0.f;
-          for (int c = lane; c < r; c += 32) sdot = fmaf(Hr[c], y[c], sdot);
-          sdot = warp_sum(sdot);
-          if (lane == 0) y[r] = (-grad[r] * Mv[r] - sdot) / Hr[r];
           sync();
+          const float zr = y[r] / H[r * (r + 1) / 2 + r];
+          if (lane == 0) srch[r] = zr;
+          for (int i = r + 1 + lane; i < nd; i += 32) y[i] = fmaf(-H[i * (i + 1) / 2 + r], zr, y[i]);
         }
         for (int r = nd - 1; r >= 0; r--) {
-          float sdot = 0.f;
-          for (int c = r + 1 + lane; c < nd; c += 32) sdot = fmaf(H[c * (c + 1) / 2 + r], srch[c], sdot);
-          sdot = warp_sum(sdot);
-          if (lane == 0) srch[r] = (y[r] - sdot) / H[r * (r + 1) / 2 + r];
           sync();
+          const float* Hr = H + r * (r + 1) / 2;
+          const float xr = srch[r] / Hr[r];
+          if (lane == 0) y[r] = xr;
+          for (int i = lane; i < r; i += 32) srch[i] = fmaf(-Hr[i], xr, srch[i]);
         }
+        sync();
         // undo the scaling, s = S (S H S)^-1 S (-g); y <- fp32 noise floor of each acceleration, (|f_smooth| + |M a|) / H_cc
-        for (int c = lane; c < nd; c += 32) { float sc = Mv[c]; srch[c] *= sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); }
+        for (int c = lane; c < nd; c += 32) { float sc = Mv[c]; srch[c] = y[c] * sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); }
         sync();
         newton_mulM(cols, nd, srch, Mv);
         float q1 = 0.f, q2 = 0.f;
