@@ -1302,7 +1302,7 @@ struct Engine {
         if (ss < 0.f) cs += 0.5f * Dr[i] * ss * ss;
       }
       for (int c = lane; c < nd; c += 32) cw += 0.5f * Mv[c] * y[c];
-      cw = warp_sum(cw); cs = warp_sum(cs);
+      warp_sum2(cw, cs);
       for (int c = lane; c < nd; c += 32) a[c] = (cw < cs) ? wrm[c] : as[c];
       sync();
       newton_mulM(cols, nd, a, Ma);
@@ -1385,33 +1385,34 @@ struct Engine {
         sync();
         for (int r = 0; r < nd; r++) { float sr = Mv[r]; float* Hr = H + r * (r + 1) / 2; for (int c = lane; c <= r; c += 32) Hr[c] *= sr * Mv[c]; }
         sync();
-        // Cholesky H = L L' in place (right-looking; lanes over the rows below the pivot)
+        // Cholesky H = L L' in place (right-looking; lanes over the rows below the pivot).  The reciprocal pivots go to wrm
+        // (the warm start is not needed once the iteration has begun), so a pivot costs one rsqrt and two warp barriers and
+        // the triangular solves below multiply instead of dividing
         for (int p = 0; p < nd; p++) {
-          const int pp = p * (p + 1) / 2;
-          float dk = sqrtf(fmaxf(H[pp + p], 1e-7f)), inv = 1.0f / dk;
           sync();
+          const float inv = rsqrtf(fmaxf(H[p * (p + 1) / 2 + p], 1e-7f));
+          if (lane == 0) wrm[p] = inv;
           for (int i = p + 1 + lane; i < nd; i += 32) H[i * (i + 1) / 2 + p] *= inv;
-          if (lane == 0) H[pp + p] = dk;
           sync();
           for (int i = p + 1 + lane; i < nd; i += 32) {
             float* Hi = H + i * (i + 1) / 2; float lip = Hi[p];
+#pragma unroll 4
             for (int c = p + 1; c <= i; c++) Hi[c] = fmaf(-lip, H[c * (c + 1) / 2 + p], Hi[c]);
           }
-          sync();
         }
         // search = -H^-1 grad: L z = -S grad, L' x = z, both column-oriented (once an unknown is final every lane subtracts
         // its multiple from the entries it owns): one warp barrier per pivot and no reductions.  z lives in srch, x in y.
         for (int c = lane; c < nd; c += 32) y[c] = -grad[c] * Mv[c];
         for (int r = 0; r < nd; r++) {
           sync();
-          const float zr = y[r] / H[r * (r + 1) / 2 + r];
+          const float zr = y[r] * wrm[r];
           if (lane == 0) srch[r] = zr;
           for (int i = r + 1 + lane; i < nd; i += 32) y[i] = fmaf(-H[i * (i + 1) / 2 + r], zr, y[i]);
         }
         for (int r = nd - 1; r >= 0; r--) {
           sync();
           const float* Hr = H + r * (r + 1) / 2;
-          const float xr = srch[r] / Hr[r];
+          const float xr = srch[r] * wrm[r];
           if (lane == 0) y[r] = xr;
           for (int i = lane; i < r; i += 32) srch[i] = fmaf(-Hr[i], xr, srch[i]);
         }
@@ -1427,17 +1428,18 @@ struct Engine {
           for (int c = 0; c < nd; c++) sj = fmaf(Ji[c], srch[c], sj);
           jv[i] = sj;
         }
-        q1 = warp_sum(q1); q2 = warp_sum(q2);
+        warp_sum2(q1, q2);
         sync();
         // exact minimisation along the search direction
         float alpha = 0.f, lo = 0.f, hi = -1.f;
         for (int ls = 0; ls < 40; ls++) {
           float d1 = 0.f, d2 = 0.f, dn = 0.f;
           for (int i = lane; i < n; i += 32) { float x = fmaf(alpha, jv[i], jar[i]); if (x < 0.f) { float t = Dr[i] * jv[i]; d1 = fmaf(t, x, d1); d2 = fmaf(t, jv[i], d2); dn += fabsf(t * x); } }
-          d1 = warp_sum(d1) + q1 + alpha * q2; d2 = warp_sum(d2) + q2;
+          if (ls == 0) warp_sum3(d1, d2, dn); else warp_sum2(d1, d2);
+          d1 += q1 + alpha * q2; d2 += q2;
           // a slope at alpha = 0 that is below the rounding noise of its own terms carries no information: take the plain
           // Newton step (the direction is noise-sized too) instead of searching on noise
-          if (ls == 0) { dn = warp_sum(dn); if (fabsf(d1) <= 2.4e-7f * (dn + fabsf(q1))) { alpha = 1.0f; break; } }
+          if (ls == 0 && fabsf(d1) <= 2.4e-7f * (dn + fabsf(q1))) { alpha = 1.0f; break; }
           if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
           if (d1 < 0.f) lo = alpha; else hi = alpha;
           if (!(d2 > 0.f)) break;
