@@ -1238,16 +1238,16 @@ struct Engine {
   // exact line search on the piecewise-quadratic cost (safeguarded Newton on its derivative).  The optimum is unique, so
   // parity with the fp64 oracle is on the converged solution, not on the iteration path.  Leaves efc_force in row_f.
 #ifndef B2_NEWTON_RTOL
-#define B2_NEWTON_RTOL 1e-6f
+#define B2_NEWTON_RTOL 1e-5f
 #endif
 #ifndef B2_NEWTON_AFLOOR
 #define B2_NEWTON_AFLOOR 10.0f
 #endif
 #ifndef B2_NEWTON_NOISE
-#define B2_NEWTON_NOISE 5e-7f
+#define B2_NEWTON_NOISE 5e-6f
 #endif
 #ifndef B2_NEWTON_GRADNOISE
-#define B2_NEWTON_GRADNOISE 1e-6f
+#define B2_NEWTON_GRADNOISE 1e-5f
 #endif
   __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
   // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
@@ -1450,7 +1450,7 @@ struct Engine {
           alpha = na;
           if (done) break;
         }
-        // fp32 termination: no acceleration moves by more than 1e-6 of the island's largest one plus its own rounding
+        // fp32 termination: no acceleration moves by more than 1e-5 of the island's largest one plus its own rounding
         // floor (the gradient test above cannot fire once the stiff rows' rounding noise exceeds the tolerance)
         float amx = B2_NEWTON_AFLOOR;
         for (int c = lane; c < nd; c += 32) { a[c] = fmaf(alpha, srch[c], a[c]); Ma[c] = fmaf(alpha, Mv[c], Ma[c]); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
