@@ -245,7 +245,7 @@ def main():
                           note="fp32-latency bound physics: state stays on chip, HBM sees only state load/store"),
             cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
             episode_stats={k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped",
-                                              "rows_dropped", "arena_overflows", "solver_iters", "substeps")})
+                                              "rows_dropped", "arena_overflows", "solver_iters", "substeps", "wide_passes")})
         print(json.dumps(_finite(out)))
     env.close()
     if world > 1:

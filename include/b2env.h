@@ -37,15 +37,17 @@ typedef struct B2TaskDesc {
   float aux_f[32];     /* task-specific float table (arm: component targets, assembly_env.py:65-75, and the ee_site offset) */
 } B2TaskDesc;
 
-/* Fixed capacities of the per-env on-chip buffers; 0 = library default.  Contacts / rows beyond a capacity are
- * dropped and counted (b2_stats), never silently. */
+/* Fixed capacities of the per-env on-chip buffers; 0 = library default.  A forward pass whose contacts / rows exceed
+ * them runs in the wide tier (per-env global workspace, same arithmetic); only what exceeds the wide capacities too
+ * (256 contacts, 1024 rows) is dropped and counted (b2_stats), never silently. */
 typedef struct B2BatchOpts {
   int envs_per_block;  /* warps (= envs) per CTA sharing one staged model copy */
   int arena_floats;    /* per-env shared-memory arena holding J and the packed A of every island */
   int con_cap;         /* contact buffer capacity per env */
   int row_cap;         /* constraint-row capacity per env */
-  int warps_per_env;   /* 1 or 3: warps cooperating on one env (islands / contact chain in parallel) */
-  int reserved[3];
+  int warps_per_env;   /* 3: warps cooperating on one env (islands / contact chain in parallel); 0 = default */
+  int disable_wide;    /* non-zero: no global spill workspace; what exceeds the on-chip capacities is dropped and counted (A/B tests) */
+  int reserved[2];
 } B2BatchOpts;
 
 /* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global
@@ -97,7 +99,7 @@ int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream);
 
 /* Episode statistics and engine counters summed over this shard into out_dev[16] (fp64), ready for an NCCL
  * all-reduce: [episodes, return_sum, length_sum, nan_resets, contacts_dropped, rows_dropped, arena_overflows,
- * solver_iters, substeps, arena_spills, 0...]. */
+ * solver_iters, substeps, newton_iteration_caps, wide_passes (forward passes run in the wide tier), 0...]. */
 int b2_stats(B2Batch* b, double* out_dev16, void* stream);
 
 /* kernels launched by this library since load (the bench's gpu_launches claim) */

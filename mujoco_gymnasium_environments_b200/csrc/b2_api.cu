@@ -37,7 +37,7 @@ struct B2Batch {
 // grid = ceil(n_envs / E) CTAs of E teams of W warps; team t of CTA c steps env c*E + t.
 // Shared memory: [model | E workspaces | mbarrier].  The task hooks are warp-level code run by warp 0 of the team.
 template <class Task, int W>
-__global__ void __launch_bounds__(W == 1 ? 256 : 32 * W * 6, 1)
+__global__ void __launch_bounds__(32 * W * Task::MAX_EPB, 1)
 b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B, const __grid_constant__ TaskParams tp,
               int mode, float* epstat, const float* inject) {
   const int team = threadIdx.x / (32 * W);
@@ -46,7 +46,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   const int env = blockIdx.x * B.envs_per_block + team;
   if (env >= B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team, env);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
@@ -61,7 +61,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     for (int i = tl; i < nv; i += TEAM) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
     for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
     if (tl < 8) E.p_xfrc()[tl] = 0.f;
-    if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; }
+    if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; E.p_misc()[MISC_WIDE] = 0; }
     if (!Task::DYN_ISLANDS && w0) E.static_islands();
     for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
     for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
@@ -122,9 +122,9 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
     if (tl == 0) B.c_ncon[env] = ncon;
     for (int c = tl; c < ncon && c < B.c_cap; c += TEAM) {
-      int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
+      int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]);
       B.c_geom[((size_t)env * B.c_cap + c) * 2] = gid[pc1[p]]; B.c_geom[((size_t)env * B.c_cap + c) * 2 + 1] = gid[pc2[p]];
-      B.c_dist[(size_t)env * B.c_cap + c] = E.p_con()[B2_CON_STRIDE * c];
+      B.c_dist[(size_t)env * B.c_cap + c] = E.x_con()[B2_CON_STRIDE * c];
     }
   }
   if (B.xpos_out) { int n = 3 * P.dim[DD_nbody]; for (int i = tl; i < n; i += TEAM) B.xpos_out[(size_t)env * n + i] = E.p_xpos()[i]; }
@@ -133,9 +133,9 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     float* o = B.debug_out + (size_t)env * B.debug_n; int nM = P.dim[DD_nM], k = 0;
     auto put = [&](const float* src, int n) { for (int i = tl; i < n; i += TEAM) if (k + i < B.debug_n) o[k + i] = src[i]; k += n; };
     put(E.p_qfs(), nv); put(E.p_qas(), nv); put(E.p_qfc(), nv); put(E.p_qacc(), nv); put(E.p_M(), nM);
-    if (tl == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.p_misc()[MISC_NCON]; o[k + 1] = (float)E.p_misc()[MISC_NEFC]; o[k + 2] = (float)E.p_misc()[MISC_ITERS]; o[k + 3] = 0.f; }
+    if (tl == 0 && k + 4 <= B.debug_n) { o[k] = (float)E.p_misc()[MISC_NCON]; o[k + 1] = (float)E.p_misc()[MISC_NEFC]; o[k + 2] = (float)E.p_misc()[MISC_ITERS]; o[k + 3] = (float)E.p_misc()[MISC_WIDE]; }
     k += 4;
-    put(E.p_row_f(), B.row_cap); put(E.p_row_b(), B.row_cap); put(E.p_row_R(), B.row_cap); put(E.p_row_res(), B.row_cap);
+    put(E.x_row_f(), B.row_cap); put(E.x_row_b(), B.row_cap); put(E.x_row_R(), B.row_cap); put(E.x_row_res(), B.row_cap);
   }
   // ---- store state
   if (mode != MODE_FORWARD) {
@@ -153,7 +153,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6;
   static constexpr int SOLVER = -1;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
@@ -171,55 +171,61 @@ __global__ void b2_stats_kernel(const unsigned long long* counters, const float*
   __shared__ double acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
   __syncthreads();
-  double loc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double loc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     loc[0] += epstat[4 * e]; loc[1] += epstat[4 * e + 1]; loc[2] += epstat[4 * e + 2];
     const unsigned long long* c = counters + (size_t)e * CTR_COUNT;
     loc[3] += (double)c[CTR_NAN_RESET]; loc[4] += (double)c[CTR_CON_DROPPED]; loc[5] += (double)c[CTR_ROW_DROPPED];
-    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS]; loc[9] += (double)c[CTR_ARENA_SPILL];
+    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS]; loc[9] += (double)c[CTR_ARENA_SPILL]; loc[10] += (double)c[CTR_WIDE];
   }
-  for (int k = 0; k < 10; k++) atomicAdd(&acc[k], loc[k]);
+  for (int k = 0; k < 11; k++) atomicAdd(&acc[k], loc[k]);
   __syncthreads();
   if (threadIdx.x < 16) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <class Task, int W>
-static int launch_W(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  auto kern = b2_env_kernel<Task, W>;
-  static thread_local size_t configured = 0;
-  if (configured < b->smem) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem)); configured = b->smem; }
-  int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
-  kern<<<grid, 32 * W * E, b->smem, s>>>(b->dm, b->v, b->tp, mode, b->epstat, inject);
-  g_launches++;
-  CK(cudaGetLastError());
+// The dynamic shared-memory opt-in is a per-device function attribute: it is set when a batch is created (on the batch's
+// device), never on the launch path, so that b2_step can be captured into a CUDA graph.
+template <class Task>
+static int configure_task(B2Batch* b) {
+  CK(cudaFuncSetAttribute(b2_env_kernel<Task, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
   return B2_OK;
 }
 template <class Task>
 static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  switch (b->W) {
-    case 1: return launch_W<Task, 1>(b, mode, inject, s);
-    case 3: return launch_W<Task, 3>(b, mode, inject, s);
-  }
-  return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3");
+  int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
+  b2_env_kernel<Task, 3><<<grid, 32 * 3 * E, b->smem, s>>>(b->dm, b->v, b->tp, mode, b->epstat, inject);
+  g_launches++;
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+#define B2_FOR_TASK(b, CALL) \
+  switch ((b)->tp.task) { \
+    case TASK_NONE: return CALL(NoTask); \
+    case TASK_QUADRUPED_PARKOUR: return CALL(QuadrupedTask); \
+    case TASK_HUMANOID_DANCING: return CALL(DancingTask); \
+    case TASK_HUMANOID_SOCCER: return CALL(SoccerTask); \
+    case TASK_BIPEDAL_RESCUE: return CALL(RescueTask); \
+    case TASK_HUMANOID_CONSTRUCTION: return CALL(ConstructionTask); \
+    case TASK_HUMANOID_MARTIAL_ARTS: return CALL(MartialArtsTask); \
+    case TASK_ROBOTIC_ARM_ASSEMBLY: return CALL(ArmTask); \
+  } \
+  return fail(B2_ERR_UNSUPPORTED, "unknown task id")
+static int configure(B2Batch* b) {
+#define B2_CALL(T) configure_task<T>(b)
+  B2_FOR_TASK(b, B2_CALL);
+#undef B2_CALL
 }
 static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   CK(cudaSetDevice(b->m->device));
-  switch (b->tp.task) {
-    case TASK_NONE: return launch_task<NoTask>(b, mode, inject, s);
-    case TASK_QUADRUPED_PARKOUR: return launch_task<QuadrupedTask>(b, mode, inject, s);
-    case TASK_HUMANOID_DANCING: return launch_task<DancingTask>(b, mode, inject, s);
-    case TASK_HUMANOID_SOCCER: return launch_task<SoccerTask>(b, mode, inject, s);
-    case TASK_BIPEDAL_RESCUE: return launch_task<RescueTask>(b, mode, inject, s);
-    case TASK_HUMANOID_CONSTRUCTION: return launch_task<ConstructionTask>(b, mode, inject, s);
-    case TASK_HUMANOID_MARTIAL_ARTS: return launch_task<MartialArtsTask>(b, mode, inject, s);
-    case TASK_ROBOTIC_ARM_ASSEMBLY: return launch_task<ArmTask>(b, mode, inject, s);
-  }
-  return fail(B2_ERR_UNSUPPORTED, "unknown task id");
+#define B2_CALL(T) launch_task<T>(b, mode, inject, s)
+  B2_FOR_TASK(b, B2_CALL);
+#undef B2_CALL
 }
 
 extern "C" {
 
+void b2_batch_destroy(B2Batch* b);
 const char* b2_last_error(void) { return g_err.c_str(); }
 unsigned long long b2_launch_count(void) { return g_launches.load(); }
 /* bring-up hook (not in b2env.h): per-phase clock64 sums when the library is built with -DB2_PHASE_TIMING */
@@ -272,12 +278,13 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaSetDevice(m->device));
   B2Batch* b = new B2Batch(); memset(b, 0, sizeof(*b));
   b->m = m; b->n_envs = n_envs;
+  struct Guard { B2Batch* b; ~Guard() { if (b) b2_batch_destroy(b); } } guard{b};      // released on success
   memset(&b->tp, 0, sizeof(b->tp));
-  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0; bool cold = false; b->ninj = 1;
+  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); memcpy(b->tp.aux_i, task->aux_i, sizeof(task->aux_i)); memcpy(b->tp.aux_f, task->aux_f, sizeof(task->aux_f)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -288,8 +295,8 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     default: delete b; return fail(B2_ERR_UNSUPPORTED, "unknown task id");
   }
   const int* dim = m->dm.dim;
-  if (m->condim6 && !task_c6) { delete b; return fail(B2_ERR_UNSUPPORTED, "the model has condim-6 pairs but the task kernel is built for 4-row pyramids"); }
-  if (task_solver >= 0 && task_solver != dim[DD_solver]) { delete b; return fail(B2_ERR_UNSUPPORTED, "the task kernel is compiled for a different <option solver> than the model's"); }
+  if (m->condim6 && !task_c6) { return fail(B2_ERR_UNSUPPORTED, "the model has condim-6 pairs but the task kernel is built for 4-row pyramids"); }
+  if (task_solver >= 0 && task_solver != dim[DD_solver]) { return fail(B2_ERR_UNSUPPORTED, "the task kernel is compiled for a different <option solver> than the model's"); }
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
@@ -298,7 +305,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
   int o_con = opts ? opts->con_cap : 0, o_row = opts ? opts->row_cap : 0;
   b->W = (opts && opts->warps_per_env > 0) ? opts->warps_per_env : 3;
-  if (b->W != 1 && b->W != 3) { delete b; return fail(B2_ERR_ARG, "warps_per_env must be 1 or 3"); }
+  if (b->W != 3) { return fail(B2_ERR_ARG, "warps_per_env must be 3 (the one-warp-per-env kernels are no longer built)"); }
   v.con_cap = o_con > 0 ? o_con : (dim[DD_maxraw] < task_con_cap ? dim[DD_maxraw] : task_con_cap); if (v.con_cap < 1) v.con_cap = 1;
   v.row_cap = o_row > 0 ? o_row : 4 * v.con_cap + dim[DD_nlim]; if (v.row_cap > B2_ISLAND_ROWS * 4) v.row_cap = B2_ISLAND_ROWS * 4;
   v.row_cap = r4(v.row_cap < 4 ? 4 : v.row_cap);
@@ -322,9 +329,9 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   v.model_floats = model_smem_floats(b->dm.n_ints_staged, b->dm.n_flts);
   const int smem_max = 227 * 1024;
   int epb = (smem_max - v.model_floats * 4 - 16) / (v.ws_floats * 4);
-  if (epb > (b->W == 1 ? 8 : 6)) epb = (b->W == 1 ? 8 : 6);
+  if (epb > max_epb) epb = max_epb;          // the kernel's __launch_bounds__ (register budget) is sized for the task's MAX_EPB
   if (o_epb > 0 && o_epb < epb) epb = o_epb;
-  if (epb < 1) { delete b; return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
+  if (epb < 1) { return fail(B2_ERR_UNSUPPORTED, "model needs more than 227 KB of shared memory per env"); }
   v.envs_per_block = epb;
   if (o_arena <= 0) {
     // the CTA's shared memory is allocated anyway: hand what is left over to the arenas (more rows before truncation)
@@ -334,6 +341,24 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   }
   b->smem = ((size_t)v.model_floats + (size_t)epb * v.ws_floats) * 4 + 16;
   size_t N = n_envs;
+  // raw contact slots live in the arena during the narrow phase: use what the final arena holds
+  if (dim[DD_maxraw] > v.raw_cap) { int fit = (v.arena_floats - 3 * v.act_cap) / 10; v.raw_cap = dim[DD_maxraw] < fit ? dim[DD_maxraw] : fit; if (v.raw_cap > 1024) v.raw_cap = 1024; }
+  // wide tier: per-env global workspace for forward passes that exceed the on-chip capacities (nothing is dropped)
+  {
+    const bool pgs = dim[DD_solver] == 0; const int nvw = (dim[DD_maxspan] + 3) & ~3;
+    bool on = !(opts && opts->disable_wide) && dim[DD_npair] > 0 && !(pgs && nvw > 128);
+    // the on-chip part of the wide tier must fit the arena: one scratch set + the rings (PGS) / the largest island's H and vectors (Newton)
+    int fixed = pgs ? 32 * dim[DD_nv] + 3 * 4 * (8 * nvw + 24) + 64 : 0;
+    if (fixed + 256 > v.arena_floats) on = false;
+    if (on) {
+      v.w_con_cap = dim[DD_maxraw] < 256 ? dim[DD_maxraw] : 256; if (v.w_con_cap < v.con_cap) v.w_con_cap = v.con_cap;
+      int rows = (task_c6 ? 10 : 4) * v.w_con_cap + 2 * dim[DD_nlim]; if (rows > 1024) rows = 1024; if (rows < v.row_cap) rows = v.row_cap;
+      v.w_row_cap = r4(rows);
+      v.w_arena_floats = pgs ? (v.w_row_cap / 4 + B2_MAX_ISLANDS) * (8 * nvw + 24) + 16 : r4(v.w_row_cap * ((dim[DD_maxspan] | 1) + 1)) + 16 * B2_MAX_ISLANDS;
+      v.wide_stride = wide_layout(v.w_con_cap, v.w_row_cap, v.w_arena_floats, &v.woff);
+      CK(cudaMalloc(&v.wide, N * (size_t)v.wide_stride * 4));
+    }
+  }
   CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));
   CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
   CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
@@ -357,6 +382,8 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&b->d_act, N * ad * 4)); CK(cudaMalloc(&b->d_obs, N * od * 4)); CK(cudaMalloc(&b->d_rew, N * 4));
   CK(cudaMalloc(&b->d_term, N)); CK(cudaMalloc(&b->d_trunc, N)); CK(cudaMalloc(&b->d_inject, N * (size_t)b->ninj * 4));
   CK(cudaStreamCreate(&b->own_stream));
+  { int rc = configure(b); if (rc) return rc; }
+  guard.b = nullptr;
   *out = b;
   return B2_OK;
 }
@@ -364,11 +391,12 @@ void b2_batch_destroy(B2Batch* b) {
   if (!b) return;
   cudaSetDevice(b->m->device);
   BatchView& v = b->v;
+  cudaFree(v.wide);
   cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
   cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.phase_cycles); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
   cudaFreeHost(b->h_act); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_rew); cudaFreeHost(b->h_term); cudaFreeHost(b->h_trunc);
   cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term); cudaFree(b->d_trunc); cudaFree(b->d_inject);
-  cudaStreamDestroy(b->own_stream);
+  if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
 

@@ -43,7 +43,7 @@ struct DevModel {
 };
 
 enum { CTR_NAN_RESET = 0, CTR_CON_DROPPED = 1, CTR_ROW_DROPPED = 2, CTR_ARENA_OVERFLOW = 3, CTR_EPISODES = 4,
-       CTR_SOLVER_ITERS = 5, CTR_SUBSTEPS = 6, CTR_ARENA_SPILL = 7, CTR_COUNT = 8 };
+       CTR_SOLVER_ITERS = 5, CTR_SUBSTEPS = 6, CTR_ARENA_SPILL = 7, CTR_WIDE = 8, CTR_COUNT = 10 };
 
 // -------------------------------------------------------------------------------------------- workspace (per warp)
 // All per-env intermediates live in the warp's slice of dynamic shared memory.  The slice is addressed as
@@ -62,7 +62,18 @@ struct WsOff {
   B2_WS_FLOAT_FIELDS(X) B2_WS_INT_FIELDS(X)
 #undef X
 };
-enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_NISL = 6, MISC_COUNT = 8 };
+// offsets (floats) of the spillable fields inside one env's wide workspace
+struct WideOff { int con, con_row, row_info, row_R, row_b, row_f, row_res, arena; };
+__host__ inline long long wide_layout(int w_con_cap, int w_row_cap, int w_arena_floats, WideOff* o) {
+  long long off = 0;
+  auto take = [&](int n) { long long r = off; off += (n + 3) & ~3; return (int)r; };
+  WideOff t;
+  t.con = take(w_con_cap * 16); t.con_row = take(w_con_cap); t.row_info = take(w_row_cap); t.row_R = take(w_row_cap);
+  t.row_b = take(w_row_cap); t.row_f = take(w_row_cap); t.row_res = take(w_row_cap); t.arena = take(w_arena_floats);
+  if (o) *o = t;
+  return (off + 31) & ~31ll;
+}
+enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_NISL = 6, MISC_WIDE = 7, MISC_WSCR = 8, MISC_COUNT = 12 };
 
 __host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 // model tables occupy the first model_floats of shared memory (ints first, then floats), padded to 32 floats
@@ -121,6 +132,11 @@ struct BatchView {
   int keep_frames;                                   // the task reads xquat / subtree com of the last forward pass
   int inject_stride;                                 // floats per env of the injected reset draws
   int xfrc_body;                                     // body whose xfrc_applied the task drives (-1: none); value in ws.xfrc[0..5]
+  // wide tier: per-env spill workspace in global memory (L2-resident while in use).  A forward pass whose contacts / rows /
+  // J do not fit the on-chip capacities keeps its contact records, row arrays and J there instead of dropping anything.
+  float* wide; long long wide_stride;                // [n_envs][wide_stride] floats (nullptr: tier disabled)
+  int w_con_cap, w_row_cap, w_arena_floats;
+  WideOff woff;
   WsOff off;
 };
 
@@ -156,9 +172,12 @@ struct Engine {
   int wl;      // warp in team
   int tl;      // thread in team
   int barid;   // named barrier of the team (1..15)
+  int env;     // env this team steps (row of the wide workspace)
+  bool wide;   // this forward pass keeps its contacts / rows / J in the wide workspace (team-uniform, refreshed from MISC_WIDE)
   static constexpr int TEAM = 32 * W;
+  static constexpr int RING = 4;      // cp.async ring stages of the wide PGS sweep
 
-  __device__ Engine(const DevModel& p, const BatchView& b, int team_base, int team_in_block) : P(p), B(b), wb(team_base) {
+  __device__ Engine(const DevModel& p, const BatchView& b, int team_base, int team_in_block, int env_) : P(p), B(b), wb(team_base), env(env_), wide(false) {
     tl = threadIdx.x % TEAM; lane = tl & 31; wl = tl >> 5; barid = 1 + team_in_block;
   }
   __device__ __forceinline__ void team_sync() const {
@@ -179,9 +198,27 @@ struct Engine {
   __device__ __forceinline__ int dim(int k) const { return P.dim[k]; }
   __device__ __forceinline__ bool newton() const { return SOLVER < 0 ? P.dim[DD_solver] == 2 : SOLVER == 2; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
-  __device__ __forceinline__ int conCap() const { return B.con_cap; }
-  __device__ __forceinline__ int rowCap() const { return B.row_cap; }
+  __device__ __forceinline__ int conCap() const { return wide ? B.w_con_cap : B.con_cap; }
+  __device__ __forceinline__ int rowCap() const { return wide ? B.w_row_cap : B.row_cap; }
   __device__ __forceinline__ int arenaFloats() const { return B.arena_floats; }
+  // spillable fields: shared memory in the fast tier, the env's wide workspace otherwise.  x_*() select at run time (generic
+  // pointers; contact chain, task epilogues), xs_*<WD>() at compile time (row fill, solvers).
+  __device__ __forceinline__ float* wbase() const { return B.wide + (size_t)env * (size_t)B.wide_stride; }
+#define XF(n) __device__ __forceinline__ float* x_##n() const { return wide ? wbase() + B.woff.n : b2_smem + wb + B.off.n; } \
+  template <bool WD> __device__ __forceinline__ float* xs_##n() const { return WD ? wbase() + B.woff.n : b2_smem + wb + B.off.n; }
+#define XI(n) __device__ __forceinline__ int* x_##n() const { return (int*)(wide ? wbase() + B.woff.n : b2_smem + wb + B.off.n); } \
+  template <bool WD> __device__ __forceinline__ int* xs_##n() const { return (int*)(WD ? wbase() + B.woff.n : b2_smem + wb + B.off.n); }
+  XF(con) XF(row_R) XF(row_b) XF(row_f) XF(row_res) XI(con_row) XI(row_info)
+#undef XF
+#undef XI
+  __device__ __forceinline__ void refresh_wide() { wide = p_misc()[MISC_WIDE] != 0; }
+  // J of island k: fast tier / Newton: plain rows (blk = 4 ldj, row i at i * ldj); wide PGS: blocks of four rows
+  // [J rows | B = M^-1 J' rows | record], ldj = r4(nd), so one aligned copy brings everything a 4-row sweep step needs
+  __device__ __forceinline__ int jblk(int ldj) const { return (wide && !newton()) ? 8 * ldj + 24 : 4 * ldj; }
+  __device__ __forceinline__ float* x_J(int k) const { return (wide ? wbase() + B.woff.arena : p_arena()) + p_isl_J()[k]; }
+  template <bool WD> __device__ __forceinline__ float* xs_J(int k) const { return (WD ? wbase() + B.woff.arena : p_arena()) + p_isl_J()[k]; }
+  __device__ __forceinline__ static int jrow(int i, int blk, int ldj) { return (i >> 2) * blk + (i & 3) * ldj; }
+  template <bool WD> __device__ __forceinline__ static int jr(int i, int blk, int ldj) { return WD ? jrow(i, blk, ldj) : i * ldj; }
 
   // ---- B.1 kinematics: level-synchronous over bodies, lanes = bodies of one depth level
   __device__ void kinematics() {
@@ -559,6 +596,16 @@ struct Engine {
       rcount[k] = n;
     }
     sync();
+    // tier of this forward pass: more contacts than the on-chip buffer holds -> wide workspace (nothing is dropped)
+    {
+      int tot = 0;
+      for (int k = lane; k < nact; k += 32) tot += rcount[k];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(B2_FULL, tot, o);
+      wide = B.wide != nullptr && tot > B.con_cap;
+      if (lane == 0) { p_misc()[MISC_WIDE] = wide ? 1 : 0; if (wide && counters) atomicAdd(&counters[CTR_WIDE], 1ull); }
+    }
+    float* const conbuf = x_con();
     // ordered compaction (active list is in pair order == MuJoCo contact order)
     int base = 0;
     for (int k0 = 0; k0 < nact; k0 += 32) {
@@ -571,7 +618,7 @@ struct Engine {
         int c = start + q;
         if (c >= conCap()) { dropped++; continue; }
         const float* src = rdata + B2_RAW * (araw[k] + q);
-        float* dst = p_con() + B2_CON_STRIDE * c;
+        float* dst = conbuf + B2_CON_STRIDE * c;
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         // frame: normal, then orthogonalised tangent hint (mju_makeFrame)
         V3 nrm = normalized(ld3(src + 4)); V3 t = ld3(src + 7);
@@ -594,7 +641,7 @@ struct Engine {
   // island of contact c: the island of its moving body (geom 2's tree when it has one, else geom 1's)
   __device__ __forceinline__ int contact_island(int c) const {
     const int* btree = I(DI_body_tree); const int* cgbody = I(DI_cg_body);
-    int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]);
+    int p = __float_as_int(x_con()[B2_CON_STRIDE * c + 13]);
     int t2 = btree[cgbody[PI(DI_pair_cg2)[p]]], t1 = btree[cgbody[PI(DI_pair_cg1)[p]]];
     return p_tree_isl()[t2 >= 0 ? t2 : t1];
   }
@@ -643,7 +690,7 @@ struct Engine {
     // lanes look their contacts' trees up in parallel; only contacts between two moving bodies reach the serial union
     for (int c0 = 0; c0 < ncon; c0 += 32) {
       int c = c0 + lane; int a = -1, b = -1;
-      if (c < ncon) { int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]); a = btree[cgbody[pc1[p]]]; b = btree[cgbody[pc2[p]]]; }
+      if (c < ncon) { int p = __float_as_int(x_con()[B2_CON_STRIDE * c + 13]); a = btree[cgbody[pc1[p]]]; b = btree[cgbody[pc2[p]]]; }
       unsigned m = __ballot_sync(B2_FULL, a >= 0 && b >= 0 && a != b);
       while (m) {
         int src = __ffs(m) - 1; m &= m - 1;
@@ -685,10 +732,16 @@ struct Engine {
   // rows of contact c: 2 (condim - 1)
   __device__ __forceinline__ int contact_rows(int c) const {
     if (!C6) return 4;
-    int p = __float_as_int(p_con()[B2_CON_STRIDE * c + 13]);
+    int p = __float_as_int(x_con()[B2_CON_STRIDE * c + 13]);
     return F(DF_prm)[B2DEV_PRM_STRIDE * PI(DI_pair_prm)[p] + 14] == 6.0f ? 10 : 4;
   }
-  // ---- B.5 rows: joint limits then pyramidal contacts, stably partitioned by island
+  // ---- B.5 rows: joint limits then pyramidal contacts, stably partitioned by island.
+  // Rows are numbered without a cap first; the carve-up then picks the tier of this forward pass:
+  //   fast  every island's J and packed A (Newton: J, H and its vectors) fit the on-chip arena, <= 128 rows per PGS island;
+  //   wide  contact records, row arrays and J live in the env's global workspace (B.wide); PGS sweeps matrix-free over
+  //         [J | M^-1 J' | record] blocks streamed through a cp.async ring, Newton keeps H on chip and reads J from global.
+  // Only what exceeds the wide capacities as well is cut from an island's tail (whole pyramids, last contacts first) and counted.
+  __device__ __forceinline__ int wide_blkf_max() const { return 8 * r4(dim(DD_maxspan)) + 24; }
   __device__ void make_rows(unsigned long long* counters) {
     const int* limj = I(DI_lim_jnt); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
     const int* dtree = I(DI_dof_tree);
@@ -697,8 +750,6 @@ struct Engine {
     int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON];
     if (lane < B2_MAX_ISLANDS) p_isl_n()[lane] = 0;
     sync();
-    const int maxrows = newton() ? rowCap() : B2_ISLAND_ROWS;       // the 128-row island limit is the PGS register layout's
-    int dropped = 0;
     unsigned lt = (1u << lane) - 1u;
     for (int c0 = 0; c0 < nlim; c0 += 32) {
       int k = c0 + lane; bool valid = k < nlim;
@@ -715,15 +766,16 @@ struct Engine {
       int r0 = base + before;
       if (valid) {
         int rl = -1, rh = -1;
-        if (lo) { if (r0 < maxrows) rl = r0; else dropped++; r0++; }
-        if (hi) { if (r0 < maxrows) rh = r0; else dropped++; }
+        if (lo) { rl = r0; r0++; }
+        if (hi) rh = r0;
         p_lim_row()[2 * k] = rl; p_lim_row()[2 * k + 1] = rh;
-        if ((peers & lt) == 0 && total) p_isl_n()[isl] = min(base + total, maxrows);
+        if ((peers & lt) == 0 && total) p_isl_n()[isl] = base + total;
       }
       sync();
     }
     if (lane < B2_MAX_ISLANDS) p_isl_nl()[lane] = p_isl_n()[lane];      // limit rows come first in every island
     sync();
+    int* const conrow = x_con_row();
     for (int c0 = 0; c0 < ncon; c0 += 32) {
       int c = c0 + lane; bool valid = c < ncon;
       int isl = valid ? contact_island(c) : -1 - lane;
@@ -731,56 +783,73 @@ struct Engine {
       int before = 4 * __popc(peers & lt), total = 4 * __popc(peers);
       int base = valid ? p_isl_n()[isl] : 0;
       const int nr = valid ? contact_rows(c) : 0;
-      int fit_total = 0;
       if (C6) {        // pyramids of 4 or 10 rows: weighted prefix over the lanes of the same island
-        before = 0;
-        for (int src = 0; src < 32; src++) { int w = __shfl_sync(B2_FULL, nr, src); if (((peers >> src) & 1) && src < lane) before += w; }
-        const int mine = (valid && base + before + nr <= maxrows) ? nr : 0;
-        for (int src = 0; src < 32; src++) { int w = __shfl_sync(B2_FULL, mine, src); if ((peers >> src) & 1) fit_total += w; }
+        before = 0; total = 0;
+        for (int src = 0; src < 32; src++) { int w = __shfl_sync(B2_FULL, nr, src); if ((peers >> src) & 1) { total += w; if (src < lane) before += w; } }
       }
       sync();
       if (valid) {
-        int r0 = base + before;
-        if (r0 + nr <= maxrows) p_con_row()[c] = r0; else { p_con_row()[c] = -1; dropped++; }
-        if ((peers & lt) == 0) p_isl_n()[isl] = C6 ? base + fit_total : base + min(total, base < maxrows ? ((maxrows - base) / 4) * 4 : 0);
+        conrow[c] = base + before;
+        if ((peers & lt) == 0) p_isl_n()[isl] = base + total;
       }
       sync();
     }
-    // island bases and arena carve-up: J (n x ldj) then packed A (n(n+1)/2); one island may spill its A to HBM
+    // tier, island bases and arena carve-up
     if (lane == 0) {
-      int adr = 0, used = 0, ovf = 0, cut = 0;
-      int scratch = scratch_in_arena();
+      const bool nw = newton(); const int scratch = scratch_in_arena(); const int nv = dim(DD_nv);
+      bool wd = wide;
+      if (!wd && B.wide) {
+        int adr = 0, used = 0; bool ok = true;
+        for (int k = 0; k < nisl; k++) {
+          int n = p_isl_n()[k], ndk = p_isl_nd()[k], ldj = ndk | 1;
+          if (n > (nw ? B.row_cap : B2_ISLAND_ROWS)) ok = false;
+          adr += n; used += r4(n * ldj) + (nw ? newton_floats(n, ndk) : a_floats(n));
+        }
+        if (adr > B.row_cap || used > arenaFloats() - scratch - 8) ok = false;
+        if (!ok) { wd = true; if (counters) atomicAdd(&counters[CTR_WIDE], 1ull); }
+      }
+      const int rcap = wd ? B.w_row_cap : B.row_cap;
+      const int gavail = wd ? B.w_arena_floats - 8 : arenaFloats() - scratch - 8;     // where J goes
+      int savail = arenaFloats() - 8, sbase = 0, nscr = W;                            // on-chip part of the wide tier
+      if (wd && !nw) {
+        const int ringf = W * RING * wide_blkf_max();
+        int fv = 0;
+        for (int k = 0; k < nisl; k++) fv += r4(p_isl_n()[k]) + 4 + r4(p_isl_nd()[k]);
+        if (nscr * 32 * nv + ringf + fv > savail) nscr = 1;
+        sbase = nscr * 32 * nv + ringf; savail -= sbase;
+      }
+      int adr = 0, used = 0, sused = 0, ovf = 0, cut = 0;
       for (int k = 0; k < nisl; k++) {
-        int n = min(p_isl_n()[k], maxrows);
-        int ldj = p_isl_nd()[k] | 1;
-        // rows that do not fit (row buffer, or J + packed A in what is left of the arena) are cut from the island's tail:
-        // the last contacts go first, the joint limits last; every cut is counted
-        int avail = arenaFloats() - scratch - used - 8;
-        const bool newton = this->newton(); const int ndk = p_isl_nd()[k];
-        if (adr + n > rowCap()) { n = max(rowCap() - adr, 0); ovf++; }
-        if (r4(n * ldj) + (newton ? newton_floats(n, ndk) : a_floats(n)) > avail) {
-          float hb = (float)ldj + 2.0f;
-          int nf = avail > 0 ? (newton ? (avail - newton_floats(0, ndk)) / (ldj + 1) : (int)(-hb + sqrtf(hb * hb + 2.0f * (float)avail)) + 4) : 0;
-          if (nf < 0) nf = 0;
-          while (nf > 0 && r4(nf * ldj) + (newton ? newton_floats(nf, ndk) : a_floats(nf)) > avail) nf--;
-          n = min(n, nf); ovf++;
-        }
-        if (!C6) { int nl = p_isl_nl()[k]; if (n > nl) n = nl + ((n - nl) >> 2) * 4; }     // keep whole contact pyramids only
-        else if (n < min(p_isl_n()[k], maxrows) && n > p_isl_nl()[k]) {
-          int nb = p_isl_nl()[k];
-          for (int c = 0; c < ncon; c++) {
-            int r = p_con_row()[c];
-            if (r >= 0 && contact_island(c) == k) { int e = r + contact_rows(c); if (e <= n && e > nb) nb = e; }
+        const int n0 = p_isl_n()[k], ndk = p_isl_nd()[k], nl = p_isl_nl()[k];
+        const int maxrows = (wd || nw) ? rcap : B2_ISLAND_ROWS;       // the 128-row island limit is the fast PGS register layout's
+        const int ldj = (wd && !nw) ? r4(ndk) : (ndk | 1);
+        auto needJ = [&](int n) { return (wd && !nw) ? ((n + 3) >> 2) * (8 * ldj + 24) : (wd ? r4(n * ldj) + r4(n) : r4(n * ldj)); };
+        auto needS = [&](int n) { return !wd ? (nw ? newton_floats(n, ndk) : a_floats(n)) : (nw ? newton_floats(0, ndk) : r4(n) + 4 + r4(ndk)); };
+        auto fits = [&](int n) { return wd ? (used + needJ(n) <= gavail && sused + needS(n) <= savail) : (used + needJ(n) + needS(n) <= gavail); };
+        int n = min(n0, maxrows);
+        if (adr + n > rcap) n = max(rcap - adr, 0);
+        while (n > 0 && !fits(n)) n--;
+        if (n < n0) {
+          // rows that do not fit are cut from the island's tail: the last contacts go first, the joint limits last; whole pyramids only
+          ovf++;
+          if (!C6) { if (n > nl) n = nl + ((n - nl) >> 2) * 4; }
+          else if (n > nl) {
+            int nb = nl;
+            for (int c = 0; c < ncon; c++) {
+              int r = conrow[c];
+              if (contact_island(c) == k) { int e = r + contact_rows(c); if (e <= n && e > nb) nb = e; }
+            }
+            n = nb;
           }
-          n = nb;
+          cut += n0 - n;
         }
-        cut += min(p_isl_n()[k], maxrows) - n;
-        int needJ = r4(n * ldj), needA = newton ? newton_floats(n, ndk) : a_floats(n);
-        int aoff = used + needJ;
-        p_isl_n()[k] = n; p_isl_adr()[k] = adr; p_isl_ldj()[k] = ldj; p_isl_J()[k] = used; p_isl_A()[k] = aoff;
-        adr += n; used += needJ + (aoff >= 0 ? needA : 0);
+        p_isl_n()[k] = n; p_isl_adr()[k] = adr; p_isl_ldj()[k] = ldj; p_isl_J()[k] = used;
+        if (!wd) { p_isl_A()[k] = used + needJ(n); used += needJ(n) + needS(n); }
+        else { p_isl_A()[k] = sbase + sused; used += needJ(n); sused += needS(n); }
+        adr += n;
       }
       p_isl_adr()[nisl] = adr; p_misc()[MISC_NEFC] = adr; p_misc()[MISC_ARENA_USED] = used;
+      p_misc()[MISC_WIDE] = wd ? 1 : 0; p_misc()[MISC_WSCR] = nscr;
       // islands -> warps of the team, greedily by sweep length (4-row blocks), so the A build and the PGS sweeps of
       // one env finish together
       int load[W > 1 ? W : 1];
@@ -799,9 +868,15 @@ struct Engine {
         if (cut) atomicAdd(&counters[CTR_ROW_DROPPED], (unsigned long long)cut);
       }
     }
-    dropped = (int)warp_sum((float)dropped);
-    if (lane == 0 && dropped && counters) atomicAdd(&counters[CTR_ROW_DROPPED], (unsigned long long)dropped);
     sync();
+    if (!wide && p_misc()[MISC_WIDE]) {      // upgraded by the carve-up: move the contact records and their row numbers over
+      const float* sc = b2_smem + wb + B.off.con; const int* sr = (const int*)(b2_smem + wb + B.off.con_row);
+      float* gc = wbase() + B.woff.con; int* gr = (int*)(wbase() + B.woff.con_row);
+      for (int i = lane; i < ncon * B2_CON_STRIDE; i += 32) gc[i] = sc[i];
+      for (int i = lane; i < ncon; i += 32) gr[i] = sr[i];
+      wide = true;
+      sync();
+    }
   }
   // column scratch for the A build: 32 * max island dof span floats; lives in the dead block when it fits
   __device__ __forceinline__ int max_span() const { return dim(DD_maxspan); }
@@ -816,7 +891,7 @@ struct Engine {
   __device__ __forceinline__ float* island_A(int k) const { return p_arena() + p_isl_A()[k]; }
 
   // ---- fill J (island-dense), per-row parameters, aref, b, warm-start force
-  __device__ void fill_rows() {
+  template <bool WD> __device__ void fill_rows() {
     const int* limj = I(DI_lim_jnt); const int* jd = I(DI_jnt_dofadr); const int* jq = I(DI_jnt_qposadr);
     const int* dtree = I(DI_dof_tree); const int* cgbody = I(DI_cg_body);
     const int* pc1 = PI(DI_pair_cg1); const int* pc2 = PI(DI_pair_cg2); const int* pprm = PI(DI_pair_prm);
@@ -826,32 +901,41 @@ struct Engine {
     const float* dinvw = F(DF_dof_invweight0); const float* binvw = F(DF_body_invweight0); const float* prm = F(DF_prm);
     int nlim = dim(DD_nlim), nisl = p_misc()[MISC_NISL], ncon = p_misc()[MISC_NCON], nmw = dim(DD_nmaskw);
     float timestep = P.opt[DO_timestep], impratio = P.opt[DO_impratio];
+    int* const rinfo = xs_row_info<WD>(); int* const conrow = xs_con_row<WD>(); const float* const conbuf = xs_con<WD>();
+    float* const rowR = xs_row_R<WD>(); float* const rowb = xs_row_b<WD>(); float* const rowf = xs_row_f<WD>(); float* const rowres = xs_row_res<WD>();
     // row_info: limits  -> (joint << 4) | side ; contacts -> 0x40000000 | (contact << 4) | row of the pyramid
     for (int k = tl; k < 2 * nlim; k += TEAM) {
       int r = p_lim_row()[k]; if (r < 0) continue;
       int j = limj[k >> 1], isl = p_tree_isl()[dtree[jd[j]]];
       if (r >= p_isl_n()[isl]) continue;
-      p_row_info()[p_isl_adr()[isl] + r] = (j << 4) | (k & 1);
+      rinfo[p_isl_adr()[isl] + r] = (j << 4) | (k & 1);
     }
     for (int c = tl; c < ncon; c += TEAM) {
-      int r = p_con_row()[c]; if (r < 0) continue;
+      int r = conrow[c]; if (r < 0) continue;
       int isl = contact_island(c);
       const int nr = contact_rows(c);
-      if (r + nr > p_isl_n()[isl]) { p_con_row()[c] = -1; continue; }
-      for (int d = 0; d < nr; d++) p_row_info()[p_isl_adr()[isl] + r + d] = 0x40000000 | (c << 4) | d;
+      if (r + nr > p_isl_n()[isl]) { conrow[c] = -1; continue; }
+      for (int d = 0; d < nr; d++) rinfo[p_isl_adr()[isl] + r + d] = 0x40000000 | (c << 4) | d;
+    }
+    if (WD && !newton()) {      // wide PGS blocks: padding columns, rows past n and the B / record parts start from zero
+      for (int k = 0; k < nisl; k++) {
+        int n = p_isl_n()[k]; if (!n) continue;
+        float4* z = reinterpret_cast<float4*>(xs_J<WD>(k)); const int nz = ((n + 3) >> 2) * (jblk(p_isl_ldj()[k]) >> 2);
+        for (int i = tl; i < nz; i += TEAM) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     team_sync();
     // J entries
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n) continue;
-      int nd = p_isl_nd()[k], ldj = p_isl_ldj()[k]; float* J = p_arena() + p_isl_J()[k];
+      int nd = p_isl_nd()[k], ldj = p_isl_ldj()[k]; float* J = xs_J<WD>(k); const int blk = jblk(ldj);
       int e0 = p_isl_adr()[k]; const Cols cols = island_cols(k);
       for (int item = tl; item < n * nd; item += TEAM) {
         int i = item / nd, c = item - i * nd, d = cols.dof(c);
-        int info = p_row_info()[e0 + i]; float val = 0.f;
+        int info = rinfo[e0 + i]; float val = 0.f;
         if (info & 0x40000000) {
           int ci = (info >> 4) & 0x03ffffff, dir = info & 15;
-          const float* con = p_con() + B2_CON_STRIDE * ci;
+          const float* con = conbuf + B2_CON_STRIDE * ci;
           int p = __float_as_int(con[13]);
           int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
           int in1 = (cmask[b1 * nmw + (d >> 5)] >> (d & 31)) & 1, in2 = (cmask[b2 * nmw + (d >> 5)] >> (d & 31)) & 1;
@@ -871,18 +955,18 @@ struct Engine {
           int j = info >> 4;
           if (jd[j] == d) val = (info & 1) ? -1.f : 1.f;
         }
-        J[i * ldj + c] = val;
+        J[jr<WD>(i, blk, ldj) + c] = val;
       }
     }
     team_sync();
     // per-row parameters
     int nefc = p_misc()[MISC_NEFC];
     for (int e = tl; e < nefc; e += TEAM) {
-      int info = p_row_info()[e];
+      int info = rinfo[e];
       float pos, margin, da, solref0, solref1; const float* simp; int isl; float mu0 = 0.f; bool iscon = info & 0x40000000;
       if (iscon) {
         int ci = (info >> 4) & 0x03ffffff;
-        const float* con = p_con() + B2_CON_STRIDE * ci; int p = __float_as_int(con[13]);
+        const float* con = conbuf + B2_CON_STRIDE * ci; int p = __float_as_int(con[13]);
         const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
         int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
         isl = contact_island(ci);
@@ -924,15 +1008,15 @@ struct Engine {
       } else { K = -solref0 / (dmax * dmax); B = -solref1 / dmax; }
       // J row products with qvel, qacc_smooth, qacc_warmstart
       int nd = p_isl_nd()[isl], ldj = p_isl_ldj()[isl]; const Cols cols = island_cols(isl);
-      const float* Jr = p_arena() + p_isl_J()[isl] + (e - p_isl_adr()[isl]) * ldj;
+      const float* Jr = xs_J<WD>(isl) + jr<WD>(e - p_isl_adr()[isl], jblk(ldj), ldj);
       float vel = 0.f, ja = 0.f, jw = 0.f;
       for (int c = 0; c < nd; c++) { float jv = Jr[c]; int d = cols.dof(c); vel = fmaf(jv, p_qvel()[d], vel); ja = fmaf(jv, p_qas()[d], ja); jw = fmaf(jv, p_warm()[d], jw); }
       float aref = -B * vel - K * imp * (pos - margin);
-      p_row_R()[e] = R;
-      p_row_b()[e] = ja - aref;
+      rowR[e] = R;
+      rowb[e] = ja - aref;
       float jar = jw - aref;
-      p_row_f()[e] = jar < 0.f ? -jar / R : 0.f;
-      p_row_res()[e] = pos;    // efc_pos until the solver overwrites it with the residual (debug export reads it)
+      rowf[e] = jar < 0.f ? -jar / R : 0.f;
+      rowres[e] = pos;    // efc_pos until the solver overwrites it with the residual (debug export reads it)
     }
     team_sync();
   }
@@ -975,15 +1059,15 @@ struct Engine {
   // phase 2 (two team barriers per column block); small islands are built by the warp they are assigned to.
   // the column scratch is indexed by dof (32 floats per dof of the model): islands own disjoint dofs, so warps building
   // different islands never collide and the sparse solves need no column translation
-  __device__ __forceinline__ void build_A_solve(int k, int j0, float* scratch) {
+  template <bool WD> __device__ __forceinline__ void build_A_solve(int k, int j0, float* scratch) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int* dadr = I(DI_dof_descadr); const int* dnum = I(DI_dof_descnum); const int* dpack = I(DI_desc_pack);
     const float* LDp = p_LD(); const Cols cols = island_cols(k);
     int n = p_isl_n()[k], nd = p_isl_nd()[k], ldj = p_isl_ldj()[k];
-    const float* J = p_arena() + p_isl_J()[k];
+    const float* J = xs_J<WD>(k) + jr<WD>(j0 + lane < n ? j0 + lane : 0, jblk(ldj), ldj);
     int j = j0 + lane; bool valid = j < n;
     float* x = scratch + lane;   // x[32 * dof]: lane-contiguous, conflict-free
-    for (int c = 0; c < nd; c++) x[32 * cols.dof(c)] = valid ? J[j * ldj + c] : 0.f;
+    for (int c = 0; c < nd; c++) x[32 * cols.dof(c)] = valid ? J[c] : 0.f;
     // x <- L^-T x (gather from descendants, highest dof first), then x <- L^-1 D^-1 x (gather from ancestors):
     // per-lane sequential sparse solves with uniform control flow; the loads inside a gather are independent.
     // Columns are the island's dofs (trees in order, dofs ascending), so descending columns visit descendants first.
@@ -1062,7 +1146,7 @@ struct Engine {
         float* scratch = scratch_base();
         int turn = p_isl_warp()[k];
         for (int j0 = 0; j0 < n; j0 += 32) {
-          if (wl == turn) build_A_solve(k, j0, scratch);
+          if (wl == turn) build_A_solve<false>(k, j0, scratch);
           team_sync();
           build_A_dots(k, j0, scratch, wl, W);
           team_sync();
@@ -1073,7 +1157,7 @@ struct Engine {
     for (int k = 0; k < nisl; k++) {
       int n = p_isl_n()[k]; if (!n || (W > 1 && n > COOPMIN) || p_isl_warp()[k] != wl) continue;
       float* scratch = scratch_base();
-      for (int j0 = 0; j0 < n; j0 += 32) { build_A_solve(k, j0, scratch); sync(); build_A_dots(k, j0, scratch, 0, 1); sync(); }
+      for (int j0 = 0; j0 < n; j0 += 32) { build_A_solve<false>(k, j0, scratch); sync(); build_A_dots(k, j0, scratch, 0, 1); sync(); }
     }
     team_sync();
   }
@@ -1232,6 +1316,196 @@ struct Engine {
     team_sync();
   }
 
+  // ---- wide PGS: the same scalar row updates as solve_pgs (mj_solPGS's order within each island, islands decoupled), but
+  // matrix-free.  With v = M^-1 J' f the residual of row i is J_i . v + R_i f_i + b_i and a force change d of row i moves v by
+  // (M^-1 J_i') d, so a sweep needs J and B = M^-1 J' (n x nd each) instead of A (n x n): memory O(n nd), no row limit.
+  // Rows are kept in blocks of four in the env's global workspace, [J rows | B rows | record] (8 ldw + 24 floats, ldw = r4(nd)),
+  // and streamed through a per-warp cp.async ring in shared memory, RING blocks deep.  Lanes own dofs: the four dots J_k . v
+  // are reduced by one interleaved butterfly, every lane then runs the 4-row chain on the same values
+  //     f_k' = max(0, c_k f_k - e_k - ainv_k (J_k . v) - sum_{j<k} (ainv_k G_kj) d_j),   G = J_blk B_blk',  ainv = 1 / (G_kk + R_k),
+  // (c_k = G_kk ainv_k, e_k = b_k ainv_k: the record), and folds the four force changes into its dofs of v.
+  __device__ __forceinline__ static void cp16(float* dst_smem, const float* src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ static void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  template <int N> __device__ __forceinline__ static void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+  template <int NC>
+  __device__ __forceinline__ void wide_sweep(const float* g, int nb, int blkf, int ldw, float* ring, float* f, float* vs, float& improvement) {
+    float v[NC];
+#pragma unroll
+    for (int q = 0; q < NC; q++) { int c = lane + 32 * q; v[q] = c < ldw ? vs[c] : 0.f; }
+    const int nv4 = blkf >> 2;
+#pragma unroll 1
+    for (int s = 0; s < RING - 1; s++) {
+      if (s < nb) for (int i = lane; i < nv4; i += 32) cp16(ring + s * blkf + 4 * i, g + (size_t)s * blkf + 4 * i);
+      cp_commit();
+    }
+#pragma unroll 1
+    for (int b = 0; b < nb; b++) {
+      cp_wait<RING - 2>(); __syncwarp();
+      {
+        const int nx = b + RING - 1;
+        if (nx < nb) { float* dst = ring + (nx % RING) * blkf; const float* src = g + (size_t)nx * blkf; for (int i = lane; i < nv4; i += 32) cp16(dst + 4 * i, src + 4 * i); }
+        cp_commit();
+      }
+      const float* blk = ring + (b % RING) * blkf; const float* Bb = blk + 4 * ldw;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NC; q++) {
+        int c = lane + 32 * q;
+        if (c < ldw) { float vq = v[q]; s0 = fmaf(blk[c], vq, s0); s1 = fmaf(blk[ldw + c], vq, s1); s2 = fmaf(blk[2 * ldw + c], vq, s2); s3 = fmaf(blk[3 * ldw + c], vq, s3); }
+      }
+      const float4* rec = reinterpret_cast<const float4*>(blk + 8 * ldw);
+      const float4 G0 = rec[0], G1 = rec[1], CC = rec[2], EE = rec[3], AI = rec[4], AD = rec[5];
+      const float4 fo = *reinterpret_cast<const float4*>(f + 4 * b);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        s0 += __shfl_xor_sync(B2_FULL, s0, o); s1 += __shfl_xor_sync(B2_FULL, s1, o);
+        s2 += __shfl_xor_sync(B2_FULL, s2, o); s3 += __shfl_xor_sync(B2_FULL, s3, o);
+      }
+      const float h0 = fmaf(-AI.x, s0, fmaf(CC.x, fo.x, -EE.x)); const float n0 = fmaxf(h0, 0.f), d0 = n0 - fo.x;
+      const float h1 = fmaf(-G0.x, d0, fmaf(-AI.y, s1, fmaf(CC.y, fo.y, -EE.y))); const float n1 = fmaxf(h1, 0.f), d1 = n1 - fo.y;
+      const float h2 = fmaf(-G0.z, d1, fmaf(-G0.y, d0, fmaf(-AI.z, s2, fmaf(CC.z, fo.z, -EE.z)))); const float n2 = fmaxf(h2, 0.f), d2 = n2 - fo.z;
+      const float h3 = fmaf(-G1.y, d2, fmaf(-G1.x, d1, fmaf(-G0.w, d0, fmaf(-AI.w, s3, fmaf(CC.w, fo.w, -EE.w))))); const float n3 = fmaxf(h3, 0.f), d3 = n3 - fo.w;
+      // cost change of a row update: d A_ii (1/2 d + f - unclamped)
+      improvement -= d0 * AD.x * fmaf(0.5f, d0, fo.x - h0) + d1 * AD.y * fmaf(0.5f, d1, fo.y - h1) +
+                     d2 * AD.z * fmaf(0.5f, d2, fo.z - h2) + d3 * AD.w * fmaf(0.5f, d3, fo.w - h3);
+      __syncwarp();                                  // every lane has read f[4b..] before lane 0 overwrites it
+      if (lane == 0) *reinterpret_cast<float4*>(f + 4 * b) = make_float4(n0, n1, n2, n3);
+#pragma unroll
+      for (int q = 0; q < NC; q++) {
+        int c = lane + 32 * q;
+        if (c < ldw) v[q] += fmaf(Bb[c], d0, Bb[ldw + c] * d1) + fmaf(Bb[2 * ldw + c], d2, Bb[3 * ldw + c] * d3);
+      }
+    }
+    cp_wait<0>(); __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NC; q++) { int c = lane + 32 * q; if (c < ldw) vs[c] = v[q]; }
+    __syncwarp();
+  }
+  __device__ void solve_pgs_wide(unsigned long long* counters) {
+    const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations), nv = dim(DD_nv), nscr = p_misc()[MISC_WSCR];
+    const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
+    float* red = p_red();
+    const float* rowR = xs_row_R<true>(); const float* rowb = xs_row_b<true>(); float* rowf = xs_row_f<true>();
+    // B rows and block records, 32 rows at a time; warps with a scratch set take the (island, row block) items in turn
+    if (wl < nscr) {
+      float* scratch = p_arena() + wl * 32 * nv; int item = 0;
+      for (int k = 0; k < nisl; k++) {
+        const int n = p_isl_n()[k]; if (!n) continue;
+        const int nd = p_isl_nd()[k], ldj = p_isl_ldj()[k], blk = jblk(ldj), e0 = p_isl_adr()[k];
+        float* Jg = xs_J<true>(k); const Cols cols = island_cols(k);
+        for (int j0 = 0; j0 < n; j0 += 32, item++) {
+          if (item % nscr != wl) continue;
+          build_A_solve<true>(k, j0, scratch);
+          sync();
+          const int j = j0 + lane;
+          if (j < n) {
+            const float* x = scratch + lane; float* blkp = Jg + (j >> 2) * blk; float* Bj = blkp + 4 * ldj + (j & 3) * ldj;
+            float G[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < nd; c++) {
+              const float xc = x[32 * cols.dof(c)]; Bj[c] = xc;
+              G[0] = fmaf(blkp[c], xc, G[0]); G[1] = fmaf(blkp[ldj + c], xc, G[1]); G[2] = fmaf(blkp[2 * ldj + c], xc, G[2]); G[3] = fmaf(blkp[3 * ldj + c], xc, G[3]);
+            }
+            const int q = j & 3; float* rec = blkp + 8 * ldj;
+            const float gd = q == 0 ? G[0] : q == 1 ? G[1] : q == 2 ? G[2] : G[3];
+            const float ad = gd + rowR[e0 + j], ainv = 1.0f / ad;
+            rec[8 + q] = gd * ainv; rec[12 + q] = rowb[e0 + j] * ainv; rec[16 + q] = ainv; rec[20 + q] = ad;
+            if (q == 1) rec[0] = ainv * G[0];
+            if (q == 2) { rec[1] = ainv * G[0]; rec[2] = ainv * G[1]; }
+            if (q == 3) { rec[3] = ainv * G[0]; rec[4] = ainv * G[1]; rec[5] = ainv * G[2]; }
+          }
+          sync();
+        }
+      }
+    }
+    __threadfence_block();
+    team_sync();
+    // f <- warm-start forces, v = B' f, cost(f) = sum_i f_i (1/2 (J_i . v + R_i f_i) + b_i); cost > 0 -> cold start
+    float cost = 0.f;
+    for (int k = 0; k < nisl; k++) {
+      const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+      const int ldw = p_isl_ldj()[k], blk = jblk(ldw), e0 = p_isl_adr()[k], nb = (n + 3) >> 2;
+      const float* Jg = xs_J<true>(k); float* f = p_arena() + p_isl_A()[k]; float* vs = f + 4 * nb;
+      for (int i = lane; i < 4 * nb; i += 32) f[i] = i < n ? rowf[e0 + i] : 0.f;
+      sync();
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        const float fi = f[i]; if (fi == 0.f) continue;
+        const float* Bi = Jg + jrow(i, blk, ldw) + 4 * ldw;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { int c = lane + 32 * q; if (c < ldw) acc[q] = fmaf(Bi[c], fi, acc[q]); }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) { int c = lane + 32 * q; if (c < ldw) vs[c] = acc[q]; }
+      sync();
+      for (int i = lane; i < n; i += 32) {
+        const float fi = f[i]; if (fi == 0.f) continue;
+        const float* Ji = Jg + jrow(i, blk, ldw); float dsum = 0.f;
+        for (int c = 0; c < ldw; c++) dsum = fmaf(Ji[c], vs[c], dsum);
+        cost += fi * (0.5f * fmaf(rowR[e0 + i], fi, dsum) + rowb[e0 + i]);
+      }
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) red[wl] = cost;
+    team_sync();
+    float total = 0.f;
+#pragma unroll
+    for (int q = 0; q < W; q++) total += red[q];
+    if (total > 0.f) {
+      for (int k = 0; k < nisl; k++) {
+        const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+        const int nb = (n + 3) >> 2; float* f = p_arena() + p_isl_A()[k];
+        for (int i = lane; i < 4 * nb + p_isl_ldj()[k]; i += 32) f[i] = 0.f;       // f and v
+      }
+    }
+    sync();
+    float* ring = p_arena() + nscr * 32 * nv + wl * RING * wide_blkf_max();
+    int it = 0;
+    for (; it < iters; it++) {
+      float improvement = 0.f;
+      for (int k = 0; k < nisl; k++) {
+        const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+        const int ldw = p_isl_ldj()[k], blkf = jblk(ldw), nb = (n + 3) >> 2;
+        const float* Jg = xs_J<true>(k); float* f = p_arena() + p_isl_A()[k]; float* vs = f + 4 * nb;
+        if (ldw <= 32) wide_sweep<1>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
+        else if (ldw <= 64) wide_sweep<2>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
+        else wide_sweep<4>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
+      }
+      if (W > 1) {
+        float* slot = red + 8 + (it & 1) * 4;      // double-buffered exchange (the sweeps leave `improvement` warp-uniform)
+        if (lane == 0) slot[wl] = improvement;
+        team_sync();
+        improvement = 0.f;
+#pragma unroll
+        for (int q = 0; q < W; q++) improvement += slot[q];
+      }
+      if (improvement * scale < tol) { it++; break; }
+    }
+    for (int k = 0; k < nisl; k++) {
+      const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
+      const int e0 = p_isl_adr()[k]; const float* f = p_arena() + p_isl_A()[k];
+      for (int i = lane; i < n; i += 32) rowf[e0 + i] = f[i];
+    }
+    if (tl == 0) { p_misc()[MISC_ITERS] = it; if (counters) atomicAdd(&counters[CTR_SOLVER_ITERS], (unsigned long long)it); }
+    __threadfence_block();
+    team_sync();
+  }
+  // pass 1 of a forward evaluation in the wide tier (cold: a few per cent of the passes; kept out of line)
+  __device__ __noinline__ void wide_pass(unsigned long long* counters) {
+    if (p_misc()[MISC_NEFC] > 0) {
+      fill_rows<true>();
+      __threadfence_block();
+      team_sync();
+      if (newton()) solve_newton<true>(counters);
+      else solve_pgs_wide(counters);
+    }
+    else if (tl == 0) p_misc()[MISC_ITERS] = 0;
+    if (wl == 0) qfrc_constraint<true>(newton());
+  }
+
   // ---- Newton solver (mj_solNewton restated for the one-sided quadratic rows of limits and pyramidal contacts), one warp
   // per island:  minimise  1/2 (a - a_s)' M (a - a_s) + sum_i 1/2 D_i min(0, J_i a - aref_i)^2  over the island's
   // accelerations with the exact Hessian H = M + J' diag(D active) J (dense Cholesky in shared memory, nd <= 64) and an
@@ -1267,7 +1541,7 @@ struct Engine {
     }
     sync();
   }
-  __device__ __noinline__ void solve_newton(unsigned long long* counters) {
+  template <bool WD> __device__ __noinline__ void solve_newton(unsigned long long* counters) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
     const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
@@ -1275,11 +1549,11 @@ struct Engine {
     for (int k = 0; k < nisl; k++) {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
-      const float* J = p_arena() + p_isl_J()[k]; const Cols cols = island_cols(k);
+      const float* J = xs_J<WD>(k); const Cols cols = island_cols(k);       // wide: J (plain rows) and jv in the global workspace, H on chip
       float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;   // H: packed lower triangle
       float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
-      float* wrm = y + ndp; float* jv = wrm + ndp;
-      float* Dr = p_row_R() + e0; float* aref = p_row_res() + e0; float* jar = p_row_f() + e0; const float* bb = p_row_b() + e0;
+      float* wrm = y + ndp; float* jv = WD ? xs_J<WD>(k) + r4(n * ldj) : wrm + ndp;
+      float* Dr = xs_row_R<WD>() + e0; float* aref = xs_row_res<WD>() + e0; float* jar = xs_row_f<WD>() + e0; const float* bb = xs_row_b<WD>() + e0;
       for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d]; }
       sync();
       // D = 1/R, capped at 1e8: MuJoCo floors R at 1e-15 (a body that cannot move along the row), and a penalty that
@@ -1335,7 +1609,7 @@ struct Engine {
           // from ~16 dofs; a free body's 6-dof island has dense rows and takes the plain loop below)
           for (int q = lane; q < nh; q += 32) H[q] = 0.f;
           sync();
-          const int* rinfo = p_row_info() + e0; int* clist = reinterpret_cast<int*>(y);
+          const int* rinfo = xs_row_info<WD>() + e0; int* clist = reinterpret_cast<int*>(y);
           const unsigned lt = (1u << lane) - 1u;
           for (int i0 = 0; i0 < n;) {
             int g = 1; const int key = rinfo[i0] >> 4;
@@ -1493,7 +1767,7 @@ struct Engine {
   }
 
   // ---- qfrc_constraint = J' f, also copied into qacc as the right-hand side of the pass-1 solve
-  __device__ void qfrc_constraint(bool newton) {
+  template <bool WD> __device__ __forceinline__ void qfrc_constraint(bool newton) {
     const int* dtree = I(DI_dof_tree);
     int nv = dim(DD_nv);
 #pragma unroll 1
@@ -1501,10 +1775,11 @@ struct Engine {
       int k = p_tree_isl()[dtree[d]]; int n = p_isl_n()[k]; float s0 = 0.f, s1 = 0.f;
       if (newton) { if (n && p_misc()[MISC_NEFC] > 0) continue; }
       else if (n && p_misc()[MISC_NEFC] > 0) {
-        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = p_dof_col()[d]; const float* J = p_arena() + p_isl_J()[k]; const float* f = p_row_f() + e0;
+        int ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], c = p_dof_col()[d]; const float* J = xs_J<WD>(k) + c; const float* f = xs_row_f<WD>() + e0;
+        const int blk = jblk(ldj);
         int i = 0;
-        for (; i + 2 <= n; i += 2) { s0 = fmaf(J[i * ldj + c], f[i], s0); s1 = fmaf(J[(i + 1) * ldj + c], f[i + 1], s1); }
-        if (i < n) s0 = fmaf(J[i * ldj + c], f[i], s0);
+        for (; i + 2 <= n; i += 2) { s0 = fmaf(J[jr<WD>(i, blk, ldj)], f[i], s0); s1 = fmaf(J[jr<WD>(i + 1, blk, ldj)], f[i + 1], s1); }
+        if (i < n) s0 = fmaf(J[jr<WD>(i, blk, ldj)], f[i], s0);
       }
       p_qfc()[d] = s0 + s1; p_qacc()[d] = s0 + s1;
     }
@@ -1589,14 +1864,17 @@ struct Engine {
               if (wl == 2) factor(h, true);
             }
           } else if (pass == 1) {
-            if (p_misc()[MISC_NEFC] > 0) {
-              fill_rows(); B2_TICK(9);
-              if (newton()) solve_newton(counters);
-              else { build_A(); B2_TICK(10); solve_pgs(counters); }
-              B2_TICK(11);
+            if (wide) wide_pass(counters);       // cold path, out of line
+            else {
+              if (p_misc()[MISC_NEFC] > 0) {
+                fill_rows<false>(); B2_TICK(9);
+                if (newton()) solve_newton<false>(counters);
+                else { build_A(); B2_TICK(10); solve_pgs(counters); }
+                B2_TICK(11);
+              }
+              else if (tl == 0) p_misc()[MISC_ITERS] = 0;
+              if (wl == 0) qfrc_constraint<false>(newton());
             }
-            else if (tl == 0) p_misc()[MISC_ITERS] = 0;
-            if (wl == 0) qfrc_constraint(newton());
           } else {
             if (wl == 0) { for (int d = lane; d < nv; d += 32) p_tmp()[d] = p_qfs()[d] + p_qfc()[d]; sync(); }
           }
@@ -1609,6 +1887,7 @@ struct Engine {
             if (pass == 1) { for (int d = lane; d < nv; d += 32) x[d] += p_qas()[d]; sync(); }
           }
           team_sync(); B2_TICK(1 + pass);
+          if (pass == 0) refresh_wide();
           if (pass == 1 && integrate && stage == 0 && attempt == 0) {      // mj_checkAcc
             if (wl == 0) { bool bad = bad_state(p_qacc(), nv); if (lane == 0) p_misc()[MISC_FLAG] = bad ? 1 : 0; }
             team_sync();

@@ -32,7 +32,7 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
 
@@ -83,7 +83,7 @@ struct QuadrupedTask {
         int fid = tp.ids[1 + i - 45]; int ncon = E.p_misc()[MISC_NCON];
         const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
+          int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]);
           if (gid[pc1[p]] == fid || gid[pc2[p]] == fid) { v = 1.f; break; }
         }
       } else if (i < 61) { int f = (i - 49) / 3, k = (i - 49) % 3; v = E.p_xpos()[3 * tp.ids[1 + f] + k] - E.p_xpos()[3 * torso + k]; }
@@ -124,7 +124,7 @@ struct QuadrupedTask {
       for (int f = 0; f < 4; f++) {
         int fid = tp.ids[1 + f];
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
+          int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]);
           if (gid[pc1[p]] == fid || gid[pc2[p]] == fid) { cc++; break; }
         }
       }
@@ -173,7 +173,7 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
@@ -260,7 +260,7 @@ struct DancingTask {
         int foot = tp.ids[1 + i - 71], ncon = E.p_misc()[MISC_NCON];
         const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+          int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
           if ((g1 == foot && (g2 == tp.ids[3] || g2 == tp.ids[4])) || (g2 == foot && (g1 == tp.ids[3] || g1 == tp.ids[4]))) v = 1.f;
         }
       } else if (i < 76) v = 0.f;
@@ -357,7 +357,7 @@ struct DancingTask {
 //      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
-  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0;
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 3;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
   static constexpr int NJOINT = 29, NOBSJ = 25;
@@ -453,10 +453,10 @@ struct SoccerTask {
         const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
         const int* pprm = E.PI(DI_pair_prm); const float* prm = E.F(DF_prm);
         for (int c = 0; c < ncon; c++) {
-          int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+          int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
           if ((g1 == foot && g2 == 0) || (g2 == foot && g1 == 0)) {
             const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
-            v = ((i - 69) & 1) ? sqrtf(pr[2] * pr[2] + pr[3] * pr[3]) : E.p_con()[B2_CON_STRIDE * c];
+            v = ((i - 69) & 1) ? sqrtf(pr[2] * pr[2] + pr[3] * pr[3]) : E.x_con()[B2_CON_STRIDE * c];
           }
         }
         v = clampf(v / 1000.0f, -1.f, 1.f);
@@ -485,7 +485,7 @@ struct SoccerTask {
       int ncon = E.p_misc()[MISC_NCON]; bool touch = false;
       const int* pc1 = E.PI(DI_pair_cg1); const int* pc2 = E.PI(DI_pair_cg2); const int* gid = E.I(DI_cg_geomid);
       for (int c = 0; c < ncon && !touch; c++) {
-        int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
+        int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]); int g1 = gid[pc1[p]], g2 = gid[pc2[p]];
         if (g1 == tp.ids[3] || g2 == tp.ids[3]) touch = robot_geom<EN>(tp, g1 == tp.ids[3] ? g2 : g1);
       }
       if (touch) { reward += 1000.0f; ti[3] += 1; }
@@ -530,7 +530,7 @@ struct SoccerTask {
 //      (26 consecutive) [4] victim1_x joint (victim joints are 6 apart, y = x + 1)
 // inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
 struct RescueTask {
-  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40;
+  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40, MAX_EPB = 2;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
@@ -613,7 +613,7 @@ struct RescueTask {
       else if (i < 55) v = xp[3 * torso + i - 52];
       else if (i < 59) v = E.p_xquat()[4 * torso + i - 55];
       else if (i < 65) v = E.p_qvel()[jd[tp.ids[2]] + i - 59];
-      else if (i == 65) { int n = min(E.p_misc()[MISC_NCON], 10); for (int c = 0; c < n; c++) v += fabsf(E.p_con()[B2_CON_STRIDE * c]); }
+      else if (i == 65) { int n = min(E.p_misc()[MISC_NCON], 10); for (int c = 0; c < n; c++) v += fabsf(E.x_con()[B2_CON_STRIDE * c]); }
       else if (i < 69) v = 0.f;
       else if (i < 89) {
         int k = (i - 69) >> 2, f = (i - 69) & 3;
@@ -659,7 +659,7 @@ struct RescueTask {
     { float dx = rx - 8.0f, dy = ry - 6.0f; if (sqrtf(dx * dx + dy * dy) < 1.2f) reward += -200.0f; }
     {
       int n = min(E.p_misc()[MISC_NCON], 20); bool hit = false;
-      for (int c = 0; c < n; c++) if (fabsf(E.p_con()[B2_CON_STRIDE * c]) > 0.1f) hit = true;
+      for (int c = 0; c < n; c++) if (fabsf(E.x_con()[B2_CON_STRIDE * c]) > 0.1f) hit = true;
       if (hit) { reward += -100.0f; ti[10] += 1; }
     }
     reward += -1.0f;
@@ -686,7 +686,7 @@ struct RescueTask {
 // tf: [0] total_reward [1] task_progress [2] wind_strength [3] rain_intensity [4] temperature
 // ids: [0] humanoid body      inject: task index, wind, rain, temperature
 struct ConstructionTask {
-  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 64, ARENA_SPAN = 40;
+  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 64, ARENA_SPAN = 40, MAX_EPB = 3;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
@@ -767,7 +767,7 @@ struct ConstructionTask {
 // tf: [0] total reward [1] stance_stability_time
 // ids: [0] torso [1] right_hand [2] left_hand [3] right_ankle [4] left_ankle [5] dummy1 [6] dummy2     inject: dx, dy
 struct MartialArtsTask {
-  static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 47;
+  static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 47, MAX_EPB = 3;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
 
@@ -850,7 +850,7 @@ struct MartialArtsTask {
 // tf: [0] cumulative_reward
 // ids: [0..8] component bodies in assembly order, [9] body of ee_site    aux_f: [3k..3k+2] target of component k, [27..29] ee_site offset
 struct ArmTask {
-  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9;
+  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 2;
   static constexpr int SOLVER = 2;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
@@ -887,7 +887,7 @@ struct ArmTask {
   }
   template <class EN> __device__ static float max_contact_force(EN& E) {
     float mx = 0.f; const int ncon = E.p_misc()[MISC_NCON];
-    for (int c = 0; c < ncon; c++) mx = fmaxf(mx, fabsf(E.p_con()[B2_CON_STRIDE * c]) * 1000.0f);
+    for (int c = 0; c < ncon; c++) mx = fmaxf(mx, fabsf(E.x_con()[B2_CON_STRIDE * c]) * 1000.0f);
     return mx;
   }
   // step_count += 1 (:222) and _update_task_state (:267-297)
@@ -898,7 +898,7 @@ struct ArmTask {
       const int ncon = E.p_misc()[MISC_NCON];
       int first = -1;
       for (int c = 0; c < ncon && first < 0; c++) {
-        int p = __float_as_int(E.p_con()[B2_CON_STRIDE * c + 13]);
+        int p = __float_as_int(E.x_con()[B2_CON_STRIDE * c + 13]);
         int k1 = tp.aux_i[gid[pc1[p]]], k2 = tp.aux_i[gid[pc2[p]]];
         if (k1 == 100) { if (k2 >= 0 && k2 < 9) first = k2; }
         else if (k2 == 100) { if (k1 >= 0 && k1 < 9) first = k1; }

@@ -75,10 +75,9 @@ class B200VectorEnv:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        keys = ["episodes", "return_sum", "length_sum", "nan_resets", "contacts_dropped", "rows_dropped",
-                "arena_overflows", "solver_iters", "substeps"]
+        from .sharding import STAT_KEYS
         v = s.cpu().numpy()
-        return {k: float(v[i]) for i, k in enumerate(keys)}
+        return {k: float(v[i]) for i, k in enumerate(STAT_KEYS)}
 
     def close(self):
         self.batch.close(); self.model.close()
