@@ -47,7 +47,9 @@ typedef struct B2BatchOpts {
   int row_cap;         /* constraint-row capacity per env */
   int warps_per_env;   /* 3: warps cooperating on one env (islands / contact chain in parallel); 0 = default */
   int disable_wide;    /* non-zero: no global spill workspace; what exceeds the on-chip capacities is dropped and counted (A/B tests) */
-  int reserved[2];
+  int warmstart_once_per_step; /* 0 (default): qacc_warmstart is saved at the end of every forward pass, as MuJoCo 3.x's mj_fwdConstraint does
+                                  (RK4 stages 2-4 start from the previous stage); non-zero: once per mj_step (the round-1 reading) */
+  int reserved[1];
 } B2BatchOpts;
 
 /* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global
@@ -76,7 +78,8 @@ int b2_step_host(B2Batch* b, const float* act, float* obs, float* rew, uint8_t* 
 
 /* nsub x mujoco.mj_step(model, data) on the raw state, no task logic (parkour_env.py:348,368). */
 int b2_physics_step(B2Batch* b, int nsub, void* stream);
-/* mujoco.mj_forward(model, data) (humanoid_martial_arts_env/martial_arts_env.py:481): refreshes contacts / xpos. */
+/* mujoco.mj_forward(model, data) (humanoid_martial_arts_env/martial_arts_env.py:481): refreshes contacts / xpos and,
+ * like mj_fwdConstraint, leaves qacc in qacc_warmstart (b2_get_contacts / b2_get_xpos / b2_debug_forward do not). */
 int b2_forward(B2Batch* b, void* stream);
 
 /* data.qpos / qvel / ctrl / qacc_warmstart / time access (dense row-major [n_envs][dim] fp32 device arrays; any

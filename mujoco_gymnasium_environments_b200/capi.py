@@ -32,7 +32,7 @@ class B2TaskDesc(ctypes.Structure):
 class B2BatchOpts(ctypes.Structure):
     _fields_ = [("envs_per_block", ctypes.c_int), ("arena_floats", ctypes.c_int), ("con_cap", ctypes.c_int),
                 ("row_cap", ctypes.c_int), ("warps_per_env", ctypes.c_int), ("disable_wide", ctypes.c_int),
-                ("reserved", ctypes.c_int * 2)]
+                ("warmstart_once_per_step", ctypes.c_int), ("reserved", ctypes.c_int * 1)]
 
 
 class B2Error(RuntimeError):
@@ -122,7 +122,7 @@ class Batch:
 
     def __init__(self, model: DeviceModel, task: Optional[B2TaskDesc], n_envs: int, seed: int = 0, env_offset: int = 0,
                  envs_per_block: int = 0, arena_floats: int = 0, con_cap: int = 0, row_cap: int = 0,
-                 warps_per_env: int = 0, disable_wide: bool = False):
+                 warps_per_env: int = 0, disable_wide: bool = False, warmstart_once_per_step: bool = False):
         import torch
         self.torch = torch
         self.model = model
@@ -133,6 +133,7 @@ class Batch:
         opts.con_cap = int(os.environ.get("B2_CON_CAP", con_cap)); opts.row_cap = int(os.environ.get("B2_ROW_CAP", row_cap))
         opts.warps_per_env = int(os.environ.get("B2_WPE", warps_per_env))
         opts.disable_wide = int(os.environ.get("B2_NO_WIDE", int(disable_wide)))
+        opts.warmstart_once_per_step = int(os.environ.get("B2_WARM_ONCE", int(warmstart_once_per_step)))
         _ck(lib().b2_batch_create(model.handle, ctypes.byref(task) if task is not None else None, n_envs,
                                   ctypes.c_uint64(seed & (2**64 - 1)), env_offset, ctypes.byref(opts), ctypes.byref(h)))
         self.handle = h

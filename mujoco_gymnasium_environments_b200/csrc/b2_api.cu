@@ -138,6 +138,10 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     put(E.x_row_f(), B.row_cap); put(E.x_row_b(), B.row_cap); put(E.x_row_R(), B.row_cap); put(E.x_row_res(), B.row_cap);
   }
   // ---- store state
+  if (mode == MODE_FORWARD && B.forward_saves_warm && !B.warm_once) {
+    float* gw = B.warm + (size_t)env * B.nvp;
+    for (int i = tl; i < nv; i += TEAM) gw[i] = E.p_warm()[i];
+  }
   if (mode != MODE_FORWARD) {
     float* gq = B.qpos + (size_t)env * B.nqp; float* gv = B.qvel + (size_t)env * B.nvp;
     float* gw = B.warm + (size_t)env * B.nvp; float* gc = B.ctrl + (size_t)env * B.nup;
@@ -300,6 +304,7 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;
+  v.warm_once = (opts && opts->warmstart_once_per_step) ? 1 : 0;
   v.seed = seed; v.env_offset = env_offset; v.keep_frames = keep_frames; v.inject_stride = b->ninj; v.xfrc_body = xfrc_body;
   // fixed-capacity buffers (SURVEY App. D suggests 32 contacts for the quadruped); rows: 4 per contact + limits
   int o_epb = opts ? opts->envs_per_block : 0, o_arena = opts ? opts->arena_floats : 0;
@@ -446,8 +451,10 @@ int b2_physics_step(B2Batch* b, int nsub, void* stream) {
 }
 int b2_forward(B2Batch* b, void* stream) {
   if (!b) return fail(B2_ERR_ARG, "null argument");
-  b->v.c_ncon = nullptr; b->v.xpos_out = nullptr;
-  return launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+  b->v.c_ncon = nullptr; b->v.xpos_out = nullptr; b->v.forward_saves_warm = 1;
+  int rc = launch(b, MODE_FORWARD, nullptr, (cudaStream_t)stream);
+  b->v.forward_saves_warm = 0;
+  return rc;
 }
 
 static int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t s) {

@@ -132,6 +132,8 @@ struct BatchView {
   int keep_frames;                                   // the task reads xquat / subtree com of the last forward pass
   int inject_stride;                                 // floats per env of the injected reset draws
   int xfrc_body;                                     // body whose xfrc_applied the task drives (-1: none); value in ws.xfrc[0..5]
+  int warm_once;                                     // 0 (default, MuJoCo 3.x): qacc_warmstart <- qacc at the end of every forward pass; 1: once per mj_step
+  int forward_saves_warm;                            // MODE_FORWARD writes the warm start back (b2_forward = mj_forward); the read-only exports do not
   // wide tier: per-env spill workspace in global memory (L2-resident while in use).  A forward pass whose contacts / rows /
   // J do not fit the on-chip capacities keeps its contact records, row arrays and J there instead of dropping anything.
   float* wide; long long wide_stride;                // [n_envs][wide_stride] floats (nullptr: tier disabled)
@@ -1898,6 +1900,13 @@ struct Engine {
           }
         }
         if (!restart) break;
+      }
+      // mj_fwdConstraint ends by saving qacc into qacc_warmstart (qacc_smooth when there are no rows: qacc equals it then), so
+      // RK4 stages 2-4 start from the previous stage's solution and mj_forward moves the warm start as well
+      if (!B.warm_once && wl == 0) {
+#pragma unroll 1
+        for (int d = lane; d < nv; d += 32) p_warm()[d] = p_qacc()[d];
+        sync();
       }
       if (nstage == 4) {
         if (wl == 0) {

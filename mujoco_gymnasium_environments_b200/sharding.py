@@ -32,7 +32,7 @@ def all_reduce_stats(stats_tensor, group=None):
 
 
 def stats_dict(values: Sequence[float]) -> Dict[str, float]:
-    out = {k: float(values[i]) for i, k in enumerate(STAT_KEYS)}
+    out = {k: (float(values[i]) if i < len(values) else 0.0) for i, k in enumerate(STAT_KEYS)}
     n = out["episodes"]
     out["mean_return"] = out["return_sum"] / n if n else float("nan")
     out["mean_length"] = out["length_sum"] / n if n else float("nan")

@@ -77,6 +77,7 @@ typedef struct {
   int solver_iter, nwarn_bad, ncon_dropped;
   real *scratch; /* >= 8*nv + nv*nv */
   int disable_eulerdamp, disable_warmstart;
+  int warmstart_once_per_step;   /* 0 (default): qacc_warmstart is saved at the end of every mj_fwdConstraint, as MuJoCo 3.x does; 1: once per mj_step */
 } RefData;
 
 /* ------------------------------------------------------------------ small vector helpers */
@@ -1262,7 +1263,15 @@ static void sol_pgs(const RefModel *m, RefData *d) {
 }
 int ref_sol_newton(const RefModel *m, RefData *d); /* defined below */
 
+/* mj_fwdConstraint (engine_forward.c, 3.x): every call ends by saving qacc into qacc_warmstart -- qacc_smooth when there are
+ * no constraint rows -- so under RK4 stages 2-4 are warm-started from the previous *stage* and mj_forward moves the warm
+ * start too.  warmstart_once_per_step = 1 restores the round-1 reading (saved once per mj_step, by the integrator). */
+static void fwd_constraint_inner(const RefModel *m, RefData *d);
 static void fwd_constraint(const RefModel *m, RefData *d) {
+  fwd_constraint_inner(m, d);
+  if (!d->warmstart_once_per_step) memcpy(d->qacc_warmstart, d->qacc, sizeof(real) * NV);
+}
+static void fwd_constraint_inner(const RefModel *m, RefData *d) {
   int nv = NV, ne = d->nefc;
   if (ne == 0) { memcpy(d->qacc, d->qacc_smooth, sizeof(real) * nv); memset(d->qfrc_constraint, 0, sizeof(real) * nv); d->solver_iter = 0; return; }
   for (int i = 0; i < ne; i++) {
@@ -1456,6 +1465,7 @@ int ref_ncon(const RefData *d) { return d->ncon; }
 int ref_nefc(const RefData *d) { return d->nefc; }
 int ref_solver_iter(const RefData *d) { return d->solver_iter; }
 int ref_nwarn(const RefData *d) { return d->nwarn_bad; }
+void ref_set_warmstart_mode(RefData *d, int once_per_step) { d->warmstart_once_per_step = once_per_step; }
 void ref_set_flags(RefData *d, int disable_eulerdamp, int disable_warmstart) { d->disable_eulerdamp = disable_eulerdamp; d->disable_warmstart = disable_warmstart; }
 /* contact k -> (geom1, geom2, dist, pos[3], frame[9], friction[5]) */
 void ref_contact(const RefData *d, int k, int *geoms, double *out) {

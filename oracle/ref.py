@@ -43,6 +43,7 @@ def lib():
         for f in ("ref_ncon", "ref_nefc", "ref_solver_iter", "ref_nwarn"):
             getattr(L, f).argtypes = [ctypes.c_void_p]; getattr(L, f).restype = ctypes.c_int
         L.ref_set_flags.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.ref_set_warmstart_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ref_contact.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L
     return _LIB
@@ -109,6 +110,10 @@ class RefData:
         if name == "time":
             return float(self._view("time")[0])
         raise AttributeError(name)
+
+    def set_warmstart_once_per_step(self, on: bool):
+        """False (default): qacc_warmstart saved by every mj_fwdConstraint (MuJoCo 3.x); True: once per mj_step."""
+        lib().ref_set_warmstart_mode(self.ptr, int(bool(on)))
 
     @property
     def ncon(self): return lib().ref_ncon(self.ptr)

@@ -35,6 +35,7 @@ def test_physics_golden(tables):
         assert d.ncon == gold["ncon"][k] and d.nefc == gold["nefc"][k]
         assert [c.dim for c in d.contact] == gold["dims"][k][:d.ncon].tolist()
         assert np.allclose(d.qacc, gold["qacc"][k], rtol=0, atol=1e-6 * (1 + np.abs(gold["qacc"][k]).max()))
+        d.qacc_warmstart[:] = gold["warm"][k]       # mj_forward left qacc there (MuJoCo 3.x mj_fwdConstraint); step from the stored warm start
         ref.mj_step(om, d)
         assert np.allclose(d.qpos, gold["qpos1"][k], rtol=0, atol=1e-9)
     assert (gold["dims"][2] == 6).sum() == 8          # the crafted grasp: eight condim-6 contacts = 80 rows

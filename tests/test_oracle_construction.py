@@ -32,6 +32,7 @@ def test_physics_golden(tables):
         ref.mj_forward(om, d)
         assert d.ncon == gold["ncon"][k] and d.nefc == gold["nefc"][k]
         assert np.allclose(d.qacc, gold["qacc"][k], rtol=0, atol=1e-7 * (1 + np.abs(gold["qacc"][k]).max()))
+        d.qacc_warmstart[:] = gold["warm"][k]       # mj_forward left qacc there (MuJoCo 3.x mj_fwdConstraint); step from the stored warm start
         ref.mj_step(om, d)
         assert np.allclose(d.qpos, gold["qpos1"][k], rtol=0, atol=1e-10)
 

@@ -38,6 +38,7 @@ def test_physics_golden(tables, gold):
         ref.mj_forward(om, d)
         assert d.ncon == gold["ncon"][k] and d.nefc == gold["nefc"][k]
         assert [(c.geom1, c.geom2) for c in d.contact] == [tuple(p) for p in gold["pairs"][k][:d.ncon].tolist()]
+        d.qacc_warmstart[:] = gold["warm"][k]       # mj_forward left qacc there (MuJoCo 3.x mj_fwdConstraint); step from the stored warm start
         ref.mj_step(om, d)
         assert np.allclose(d.qpos, gold["qpos1"][k], rtol=0, atol=1e-11)
         assert np.allclose(d.qvel, gold["qvel1"][k], rtol=0, atol=1e-9)

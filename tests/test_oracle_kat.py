@@ -193,3 +193,32 @@ def test_quadruped_two_coincident_planes_double_contacts(quad_tables):
     for g in feet:
         assert (0, g) in pairs and (1, g) in pairs
     assert pairs[0][0] == 0 and pairs[1][0] == 1 and pairs[0][1] == pairs[1][1]
+
+
+def test_warmstart_is_saved_by_every_forward_pass():
+    """MuJoCo 3.x mj_fwdConstraint ends with qacc_warmstart <- qacc (qacc_smooth when there are no rows), so mj_forward moves
+    the warm start and RK4 stages 2-4 start from the previous stage; the switch restores the once-per-step reading."""
+    xml = K.BOX_ON_PLANE.format(solver="PGS").replace('iterations="100"', 'iterations="3" integrator="RK4"')
+    t, m, d = make(xml)
+    ref.mj_step(m, d, 150)                                  # box and capsule resting on the plane: contact rows, PGS-3 unconverged
+    assert d.nefc > 0
+    q, v, w = d.qpos.copy(), d.qvel.copy(), d.qacc_warmstart.copy()
+    ref.mj_forward(m, d)
+    assert np.array_equal(d.qacc_warmstart, d.qacc) and not np.array_equal(d.qacc_warmstart, w)
+    out = []
+    for once in (False, True):
+        e = ref.RefData(m); e.set_warmstart_once_per_step(once)
+        e.qpos[:] = q; e.qvel[:] = v; e.qacc_warmstart[:] = w
+        ref.mj_step(m, e)
+        assert np.array_equal(e.qacc_warmstart, e.qacc)     # both readings leave the last stage's qacc behind
+        out.append(e.qvel.copy())
+    assert not np.allclose(out[0], out[1], rtol=0, atol=1e-9)   # the stages' warm starts differ, and PGS-3 does not forget it
+    e = ref.RefData(m); e.set_warmstart_once_per_step(True)
+    e.qpos[:] = q; e.qvel[:] = v; e.qacc_warmstart[:] = w
+    ref.mj_forward(m, e)
+    assert np.array_equal(e.qacc_warmstart, w)
+    # no constraint rows: the warm start becomes qacc_smooth
+    t2, m2, d2 = make(K.FREE_SPHERE.format(integ="Euler"))
+    d2.qacc_warmstart[:] = 7.0
+    ref.mj_forward(m2, d2)
+    assert d2.nefc == 0 and np.array_equal(d2.qacc_warmstart, d2.qacc_smooth)

@@ -51,6 +51,7 @@ def record(d):
     for i, cc in enumerate(con):
         pairs[i] = (cc.geom1, cc.geom2); dist[i] = cc.dist; dims[i] = cc.dim
     S["nefc"].append(e.nefc); S["qacc"].append(e.qacc.copy())
+    e.qacc_warmstart[:] = w                    # mj_forward left qacc there (MuJoCo 3.x); the fixture steps from the stored warm start
     ref.mj_step(om, e)
     S["qpos"].append(q); S["qvel"].append(v); S["ctrl"].append(c); S["warm"].append(w)
     S["qpos1"].append(e.qpos.copy()); S["qvel1"].append(e.qvel.copy())

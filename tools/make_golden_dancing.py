@@ -36,6 +36,7 @@ while len(S["qpos"]) < N:
     for i, cc in enumerate(con):
         pairs[i] = (cc.geom1, cc.geom2); dist[i] = cc.dist
     S["nefc"].append(e.nefc); S["iters"].append(e.solver_iter)
+    e.qacc_warmstart[:] = w                    # mj_forward left qacc there (MuJoCo 3.x); the fixture steps from the stored warm start
     ref.mj_step(om, e)
     S["qpos"].append(q); S["qvel"].append(v); S["ctrl"].append(c); S["warm"].append(w)
     S["qpos1"].append(e.qpos.copy()); S["qvel1"].append(e.qvel.copy()); S["warm1"].append(e.qacc_warmstart.copy())

@@ -41,6 +41,7 @@ while len(S["qpos"]) < N:
         pairs[i] = (cc.geom1, cc.geom2); dist[i] = cc.dist
     S["nefc"].append(e.nefc); S["iters"].append(e.solver_iter)
     ok = True
+    e.qacc_warmstart[:] = w                    # mj_forward left qacc there (MuJoCo 3.x); the fixture steps from the stored warm start
     ref.mj_step(om, e)
     q1, v1, w1 = e.qpos.copy(), e.qvel.copy(), e.qacc_warmstart.copy()
     S["qpos"].append(q); S["qvel"].append(v); S["ctrl"].append(c); S["warm"].append(w)
