@@ -51,13 +51,74 @@ TASK = "quadruped_parkour"
 WORKLOAD = WORKLOADS[TASK][2]
 
 
+# ---------------------------------------------------------------------------------------------- CPU arms
+# (module, class) of each reference env, for the arm that runs the UNMODIFIED reference under gymnasium's AsyncVectorEnv
+REF_CLASSES = {"quadruped_parkour": ("quadruped_parkour_env.parkour_env", "QuadrupedParkourEnv"),
+               "humanoid_dancing": ("humanoid_dancing_env.dancing_env", "HumanoidDancingEnv"),
+               "humanoid_soccer": ("humanoid_soccer_env.soccer_env", "HumanoidSoccerEnv"),
+               "bipedal_rescue": ("bipedal_rescue_env.rescue_env", "BipedalRescueEnv"),
+               "humanoid_construction": ("humanoid_construction_env.construction_env", "HumanoidConstructionEnv"),
+               "humanoid_martial_arts": ("humanoid_martial_arts_env.martial_arts_env", "HumanoidMartialArtsEnv"),
+               "robotic_arm_assembly": ("robotic_arm_assembly_env.assembly_env", "RoboticArmAssemblyEnv")}
+
+
+def _make_reference_env(root, mod, cls):
+    def thunk():
+        import importlib
+        if root not in sys.path:
+            sys.path.insert(0, root)
+        return getattr(importlib.import_module(mod), cls)()
+    return thunk
+
+
+def reference_arm_real(task, cores, n_steps, action_scale):
+    """The reference's own classes over mujoco, one process per host core (gymnasium.vector.AsyncVectorEnv; BASELINE.md section 3
+    harness B).  Returns (result, None) or (None, why-not): mujoco / gymnasium are absent from this image and the GPU box, so
+    this arm only runs where they are installed; nothing else in the file changes then."""
+    try:
+        import gymnasium  # noqa: F401
+        import mujoco  # noqa: F401
+        from gymnasium.vector import AsyncVectorEnv
+    except ImportError as e:
+        return None, f"{e}"
+    mod, cls = REF_CLASSES[task]
+    roots = [r for r in (os.environ.get("B2_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference")
+             if r and os.path.isdir(os.path.join(r, mod.split(".")[0]))]
+    if not roots:
+        return None, "no reference checkout (B2_REFERENCE_ROOT, baseline/_ref, /root/reference)"
+    try:
+        import numpy as np
+        # martial arts and construction return more observation entries than their declared spaces (SURVEY F11): no shared memory
+        venv = AsyncVectorEnv([_make_reference_env(roots[0], mod, cls)] * cores,
+                              shared_memory=task not in ("humanoid_martial_arts", "humanoid_construction"))
+        venv.reset(seed=1234)
+        lo = venv.single_action_space.low * action_scale; hi = venv.single_action_space.high * action_scale
+        rng = np.random.default_rng(1234)
+        for _ in range(3):
+            venv.step(rng.uniform(lo, hi, (cores,) + lo.shape).astype(np.float32))
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            venv.step(rng.uniform(lo, hi, (cores,) + lo.shape).astype(np.float32))
+        dt = time.perf_counter() - t0
+        venv.close()
+        return dict(value=cores * n_steps / dt, unit=UNIT, cores=cores, kind="reference",
+                    sample=f"{cores} AsyncVectorEnv workers x {n_steps} control steps of the unmodified {cls} over mujoco "
+                           f"{mujoco.__version__}, {dt:.1f} s", seconds=dt), None
+    except Exception as e:      # a reference env that fails to construct here (assets, version) must not take the bench down
+        return None, f"{type(e).__name__}: {e}"
+
+
 def cpu_arm(n_steps, action_scale):
-    from oracle import cpu_bench
     cores = len(os.sched_getaffinity(0))
+    real, why = reference_arm_real(TASK, cores, n_steps, action_scale)
+    if real is not None:
+        real.pop("seconds", None)
+        return real
+    from oracle import cpu_bench
     total, wall, inner = cpu_bench.run(TASK, cores, n_steps, action_scale)
     return dict(value=total / inner, unit=UNIT, cores=cores, kind="port",
                 sample=f"{cores} processes x {n_steps} control steps of the fp64 oracle port (oracle/mjstep_ref.c + "
-                       f"oracle/tasks_ref.py), {inner:.1f} s")
+                       f"oracle/tasks_ref.py), {inner:.1f} s; the reference itself was not runnable: {why}")
 
 
 class ClockSampler:
@@ -116,6 +177,111 @@ def _finite(x):
     return x
 
 
+# issue-slot utilisation of the step kernel (sm__inst_issued / cycle / 4 schedulers) from the committed `ncu --set full`
+# captures of one launch at the task's BASELINE size: the secondary bound of a path that is four orders of magnitude away from
+# its HBM roofline.  Static, like NCU_TRAFFIC: a bench run takes no profile.
+NCU_ISSUE_PCT = {"quadruped_parkour": (24.3, "profiles/r01_i_quadruped.txt"), "humanoid_dancing": (26.0, "profiles/r01_f_dancing_rk4.txt"),
+                 "humanoid_soccer": (21.0, "profiles/r01_g_soccer.txt"), "bipedal_rescue": (17.0, "profiles/r01_h_rescue_cold_pairs.txt"),
+                 "humanoid_construction": (9.3, "profiles/r01_j_construction_newton.txt"), "humanoid_martial_arts": (12.9, "profiles/r01_k_martial_arts_newton.txt"),
+                 "robotic_arm_assembly": (10.6, "profiles/r01_l_arm_condim6.txt")}
+PREROLL = 100     # un-timed control steps before the warm-up: the bench times the stationary regime, not the first seconds after reset
+
+
+def run_task(task, N, K, warmup, preroll, action_scale, rank, world, local, peaks, flush, e2e=True):
+    """One workload on this rank's GPU: pre-roll, warm-up, K device-timed steps, K steps through b2_step_host, one b2_rollout."""
+    import numpy as np
+    import torch
+    from mujoco_gymnasium_environments_b200 import capi, sharding
+    from mujoco_gymnasium_environments_b200.tasks import TASKS
+    from mujoco_gymnasium_environments_b200.vector_env import B200VectorEnv
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    spec = TASKS[task]
+    off, _ = sharding.shard_range(rank, world, N)
+    env = B200VectorEnv(task, N, device=local, seed=1234, env_offset=off)
+    env.reset()
+    hi = torch.tensor(env.single_action_space.high, device=dev) * action_scale
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    draw = lambda n: ((torch.rand((n, N, spec.act_dim), device=dev, generator=gen) * 2 - 1) * hi).contiguous()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(preroll):
+        env.step(draw(1)[0])
+    acts = draw(warmup + K)
+    for i in range(warmup):
+        flush.fill_(0.0); env.step(acts[i])
+    barrier()
+    s0 = env.batch.stats().clone()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = capi.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        flush.fill_(float(i))                     # L2 flush between timed iterations (inside the timed region)
+        ev[i][0].record(); env.batch.step(acts[warmup + i], env._obs, env._rew, env._term, env._trunc, env._final_obs); ev[i][1].record()
+    e1.record()
+    barrier()
+    launches = capi.launch_count() - launches0
+    s1 = env.batch.stats().clone()
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    per_launch = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = sum(per_launch) / K
+    value = world * N * K / (ms * 1e-3)
+    out = dict(task=task, envs_per_gpu=N, action_scale=action_scale, value=value, unit=UNIT, ms_per_step=ms / K, kernel_ms=kern_ms,
+               kernel_ms_min=min(per_launch), kernel_ms_max=max(per_launch), gpu_launches=int(launches),
+               envs_per_cta=env.batch.envs_per_block, smem_bytes_per_cta=env.batch.smem_bytes,
+               wide_workspace_kib_per_env=env.batch.wide_kib_per_env)
+    # counters of the timed region only (the statistics vector is cumulative): the one collective of the path
+    dstat = s1 - s0
+    sharding.all_reduce_stats(dstat)
+    st = sharding.stats_dict(dstat.cpu().numpy())
+    out["episode_stats"] = {k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped", "rows_dropped",
+                                               "arena_overflows", "solver_iters", "substeps", "wide_passes")}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = spec.bytes_per_env_step * N / (kern_ms * 1e-3) / 1e9
+    out["roofline"] = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                           traffic=(NCU_TRAFFIC[task][1] if NCU_TRAFFIC.get(task, (0, 0))[0] == N else None),
+                           traffic_source="static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, copied from profiles/ (not measured by this run)",
+                           peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                           bytes_per_env_step=spec.bytes_per_env_step, kernel_ms=kern_ms,
+                           fp32_issue=dict(issue_slots_busy_pct=NCU_ISSUE_PCT[task][0], source="static: " + NCU_ISSUE_PCT[task][1]),
+                           note="fp32-latency bound physics: state stays on chip, HBM sees only state load/store")
+    if e2e:
+        # end to end through the host-buffer C-ABI entry point with the caller's own (pageable) numpy arrays: one H2D copy of the
+        # actions, the launch, one D2H copy of the packed results and the staging memcpys are all inside the timed region
+        ha = acts[warmup:].cpu().numpy()
+        ho = np.zeros((N, spec.obs_dim), np.float32); hr = np.zeros(N, np.float32); ht = np.zeros(N, np.uint8); hu = np.zeros(N, np.uint8)
+        for i in range(3):
+            env.batch.step_host(ha[i % K], ho, hr, ht, hu)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            env.batch.step_host(ha[i], ho, hr, ht, hu)
+        torch.cuda.synchronize()
+        e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+        out["e2e"] = dict(value=world * N * K / e2e_s, unit=UNIT, h2d_bytes_per_step=N * spec.act_dim * 4,
+                          d2h_bytes_per_step=N * (spec.obs_dim * 4 + 4 + 2), host_buffers="pageable numpy arrays owned by the caller")
+        # the same K steps with the host out of the loop: b2_rollout = one CUDA graph of K launches (no L2 flush between them)
+        T = K
+        ro = dict(obs=torch.empty((T, N, spec.obs_dim), device=dev), rew=torch.empty((T, N), device=dev),
+                  term=torch.empty((T, N), dtype=torch.uint8, device=dev), trunc=torch.empty((T, N), dtype=torch.uint8, device=dev))
+        ra = draw(T)
+        env.batch.rollout(ra, ro["obs"], ro["rew"], ro["term"], ro["trunc"])          # capture + first replay
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record(); env.batch.rollout(ra, ro["obs"], ro["rew"], ro["term"], ro["trunc"]); g1.record()
+        barrier()
+        gms = sharding.max_over_ranks(g0.elapsed_time(g1), dev)
+        out["graph_rollout"] = dict(value=world * N * T / (gms * 1e-3), unit=UNIT, steps=T, note="b2_rollout: one CUDA-graph launch, no L2 flush between steps")
+    env.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,6 +293,8 @@ def main():
     ap.add_argument("--action-scale", type=float, default=1.0)
     ap.add_argument("--cpu-steps", type=int, default=0, help="control steps per CPU process (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preroll", type=int, default=PREROLL, help="un-timed control steps before the warm-up")
+    ap.add_argument("--no-per-task", action="store_true", help="only the headline workload, no per_task array")
     a = ap.parse_args()
     global TASK, WORKLOAD
     TASK = a.task; WORKLOAD = WORKLOADS[TASK][2]
@@ -139,19 +307,23 @@ def main():
             return
         # each "step" is a bounded sample: every host core steps its env `per` times
         per = a.cpu_steps or 40
-        from oracle import cpu_bench
         cores = len(os.sched_getaffinity(0))
-        cpu_bench.run(TASK, cores, max(3, min(per, 5 * warmup)), a.action_scale)
-        total, wall, inner = cpu_bench.run(TASK, cores, per * a.steps, a.action_scale)
-        v = total / inner
+        real, why = reference_arm_real(TASK, cores, per * a.steps, a.action_scale)
+        if real is not None:
+            v = real["value"]; inner = real.pop("seconds"); base = real
+        else:
+            from oracle import cpu_bench
+            cpu_bench.run(TASK, cores, max(3, min(per, 5 * warmup)), a.action_scale)
+            total, wall, inner = cpu_bench.run(TASK, cores, per * a.steps, a.action_scale)
+            v = total / inner
+            base = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                        sample=f"{cores} processes x {per * a.steps} control steps, one env per process (oracle port; the reference "
+                               f"itself was not runnable: {why})")
         print(json.dumps(dict(
             metric=METRIC, value=v, unit=UNIT, impl="reference", n_gpus=a.gpus, steps=a.steps, warmup=warmup,
             ms_per_step=inner / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
             data="synthetic", config=dict(workload=WORKLOAD.format(n=a.envs_per_gpu, s=a.action_scale), envs_per_step=cores * per),
-            cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                              sample=f"{cores} processes x {per * a.steps} control steps, one env per process (oracle port; "
-                                     f"mujoco/gymnasium are not installable here)"),
-            e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+            cpu_baseline=base, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
         return
 
     # ---- CPU baseline first (spawned processes; before CUDA is initialised in this one)
@@ -159,95 +331,46 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_arm(a.cpu_steps or WORKLOADS[TASK][1], a.action_scale)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from mujoco_gymnasium_environments_b200 import capi, sharding
-    from mujoco_gymnasium_environments_b200.tasks import TASKS
-    from mujoco_gymnasium_environments_b200.vector_env import B200VectorEnv
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    spec = TASKS[TASK]
-    N = a.envs_per_gpu
-    off, _ = sharding.shard_range(rank, world, N)
-    env = B200VectorEnv(TASK, N, device=local, seed=1234, env_offset=off)
-    env.reset()
-    hi = torch.tensor(env.single_action_space.high, device=dev) * a.action_scale
-    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    K = a.steps
-    acts = (torch.rand((warmup + K, N, spec.act_dim), device=dev, generator=gen) * 2 - 1) * hi
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(warmup):
-        flush.fill_(0.0); env.step(acts[i])
-    barrier()
+    K = a.steps
     sampler = ClockSampler(local); sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches0 = capi.launch_count()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        flush.fill_(float(i))                     # L2 flush between timed iterations (inside the timed region)
-        ev[i][0].record(); env.batch.step(acts[warmup + i], env._obs, env._rew, env._term, env._trunc, env._final_obs); ev[i][1].record()
-    e1.record()
-    barrier()
+    head = run_task(TASK, a.envs_per_gpu, K, warmup, a.preroll, a.action_scale, rank, world, local, peaks, flush)
     clocks = sampler.stop()
-    launches = capi.launch_count() - launches0
-    ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    kern_ms = sum(s.elapsed_time(e) for s, e in ev) / K
-    value = world * N * K / (ms * 1e-3)
-
-    # ---- end to end through the host-buffer C-ABI entry point (pinned staging, H2D + D2H inside the timed region)
-    ha = acts[warmup:].cpu().numpy()
-    ho = np.zeros((N, spec.obs_dim), np.float32); hr = np.zeros(N, np.float32); ht = np.zeros(N, np.uint8); hu = np.zeros(N, np.uint8)
-    for i in range(3):
-        env.batch.step_host(ha[i % K], ho, hr, ht, hu)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        env.batch.step_host(ha[i], ho, hr, ht, hu)
-    torch.cuda.synchronize()
-    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e = dict(value=world * N * K / e2e_s, unit=UNIT, h2d_bytes_per_step=N * spec.act_dim * 4,
-               d2h_bytes_per_step=N * (spec.obs_dim * 4 + 4 + 2))
-
-    stats = env.batch.stats()
-    sharding.all_reduce_stats(stats)                      # the one collective of the path (NCCL when world > 1)
-    st = sharding.stats_dict(stats.cpu().numpy())
+    # ---- every task at its BASELINE.json size (configs[2..4] and the two Newton tasks), plus the x0.1 action variant the
+    # reference's own demos use for soccer and rescue (full-range torques make those robots flail)
+    per_task = []
+    if not a.no_per_task:
+        for t in WORKLOADS:
+            for sc in ((1.0, 0.1) if t in ("humanoid_soccer", "bipedal_rescue") else (1.0,)):
+                if t == TASK and sc == a.action_scale and a.envs_per_gpu == WORKLOADS[t][0]:
+                    r = dict(head)
+                else:
+                    r = run_task(t, WORKLOADS[t][0], K, warmup, a.preroll, sc, rank, world, local, peaks, flush)
+                r["workload"] = WORKLOADS[t][2].format(n=WORKLOADS[t][0], s=sc)
+                per_task.append(r)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        bytes_launch = spec.bytes_per_env_step * N
-        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
         out = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=warmup, ms_per_step=ms / K,
+            metric=METRIC, value=head["value"], unit=UNIT, n_gpus=world, steps=K, warmup=warmup, ms_per_step=head["ms_per_step"],
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload=WORKLOAD.format(n=N, s=a.action_scale), envs_per_gpu=N, action_scale=a.action_scale,
+            config=dict(workload=WORKLOAD.format(n=a.envs_per_gpu, s=a.action_scale), envs_per_gpu=a.envs_per_gpu, action_scale=a.action_scale,
                         l2="256 MiB fill between timed steps, inside the timed region",
-                        envs_per_cta=env.batch.envs_per_block, smem_bytes_per_cta=env.batch.smem_bytes),
-            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=(NCU_TRAFFIC[TASK][1] if NCU_TRAFFIC.get(TASK, (0, 0))[0] == N else None), peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                          bytes_per_env_step=spec.bytes_per_env_step, kernel_ms=kern_ms,
-                          traffic_source="ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, profiles/r01_[f-l]_*.txt",
-                          note="fp32-latency bound physics: state stays on chip, HBM sees only state load/store"),
-            cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks,
-            episode_stats={k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped",
-                                              "rows_dropped", "arena_overflows", "solver_iters", "substeps", "wide_passes")})
+                        preroll=f"{a.preroll} un-timed control steps after reset, before the {warmup} warm-up steps (stationary regime)",
+                        envs_per_cta=head["envs_per_cta"], smem_bytes_per_cta=head["smem_bytes_per_cta"]),
+            roofline=head["roofline"], cpu_baseline=cpu, e2e=head["e2e"], graph_rollout=head.get("graph_rollout"),
+            gpu_launches=head["gpu_launches"], clocks=clocks, episode_stats=head["episode_stats"], per_task=per_task)
         print(json.dumps(_finite(out)))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -72,9 +72,35 @@ int b2_reset(B2Batch* b, const uint8_t* mask_dev, const float* inject_dev, float
 int b2_step(B2Batch* b, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* term_dev, uint8_t* trunc_dev,
             float* final_obs_dev, void* stream);
 
-/* Same call with HOST buffers (pageable or pinned): copies actions in, steps, copies results out, synchronises.
- * This is the end-to-end path a CPU-side caller of env.step would use. */
+/* Same call with HOST buffers (pageable or pinned): one H2D copy of the actions, one launch, one D2H copy of the packed
+ * [obs | rew | term | trunc] block, synchronises.  This is the end-to-end path a CPU-side caller of env.step would use
+ * (the host loop of quadruped_parkour_env/test_parkour.py:45-47). */
 int b2_step_host(B2Batch* b, const float* act, float* obs, float* rew, uint8_t* term, uint8_t* trunc);
+
+/* T consecutive Env.step calls with the host out of the loop (the caller of env.step: quadruped_parkour_env/test_parkour.py:45-47,
+ * humanoid_soccer_env/test_soccer.py:57-59, given T pre-computed actions): act_dev [T][n_envs][act_dim] in, obs_dev
+ * [T][n_envs][obs_dim], rew_dev / term_dev / trunc_dev [T][n_envs] (and final_obs_dev, nullable, like obs_dev) out.  The T
+ * launches are one CUDA graph, captured on first use and replayed while T and the buffers stay the same.  b2_step itself is
+ * capturable too (no attribute / device calls on its launch path), e.g. inside a torch.cuda.graph region with a policy. */
+int b2_rollout(B2Batch* b, int T, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* term_dev, uint8_t* trunc_dev,
+               float* final_obs_dev, void* stream);
+
+/* The library's own pinned staging buffers for b2_step_host ([n_envs][act_dim], [n_envs][obs_dim], [n_envs] ...): a caller
+ * that fills / reads these directly and passes them to b2_step_host pays no host-side staging copy.  Any pointer may be NULL. */
+int b2_host_buffers(B2Batch* b, float** act, float** obs, float** rew, uint8_t** term, uint8_t** trunc);
+
+/* Env.reset(seed=...) (parkour_env.py:314-322, super().reset(seed=seed) reseeds np_random): replaces the RNG seed and restarts
+ * the per-env episode counters, so b2_reseed(s) + b2_reset always produces the same initial states. */
+int b2_reseed(B2Batch* b, uint64_t seed, void* stream);
+
+/* caps (16 ints): [n_inject (floats per env of b2_reset's inject_dev), wide_con_cap, wide_row_cap, wide_arena_floats,
+ * wide_workspace_KiB_per_env, raw_cap, act_cap, wide_enabled, episode_slot, warmstart_once_per_step, 0...] */
+int b2_caps(const B2Batch* b, int* out16);
+
+/* Task state / data.xpos of the episode that ended in an env's last terminal step, snapshotted before the same-step
+ * auto-reset ([n_envs][nti], [n_envs][ntf], [n_envs][nbody][3]; rows of envs that never finished an episode are zero): what
+ * the reference's terminal-step `info` is built from (parkour_env.py:797-813).  Any pointer may be NULL. */
+int b2_get_final_state(B2Batch* b, int32_t* ti_dev, float* tf_dev, float* xpos_dev, void* stream);
 
 /* nsub x mujoco.mj_step(model, data) on the raw state, no task logic (parkour_env.py:348,368). */
 int b2_physics_step(B2Batch* b, int nsub, void* stream);

@@ -19,7 +19,7 @@ _LIB = None
 SYMBOLS = ["b2_model_create", "b2_model_destroy", "b2_batch_create", "b2_batch_destroy", "b2_dims", "b2_reset",
            "b2_step", "b2_step_host", "b2_physics_step", "b2_forward", "b2_get_state", "b2_set_state",
            "b2_get_task_state", "b2_set_task_state", "b2_get_contacts", "b2_get_xpos", "b2_debug_forward", "b2_stats",
-           "b2_launch_count", "b2_last_error"]
+           "b2_launch_count", "b2_last_error", "b2_rollout", "b2_host_buffers", "b2_reseed", "b2_caps", "b2_get_final_state"]
 
 TASK_NONE, TASK_QUADRUPED_PARKOUR, TASK_HUMANOID_DANCING, TASK_HUMANOID_SOCCER, TASK_BIPEDAL_RESCUE, TASK_HUMANOID_CONSTRUCTION, TASK_HUMANOID_MARTIAL_ARTS, TASK_ROBOTIC_ARM_ASSEMBLY = 0, 1, 2, 3, 4, 5, 6, 7
 
@@ -73,6 +73,11 @@ def lib():
         L.b2_get_xpos.argtypes = [vp, vp, vp]
         L.b2_debug_forward.argtypes = [vp, vp, ci, vp]
         L.b2_stats.argtypes = [vp, vp, vp]
+        L.b2_rollout.argtypes = [vp, ci] + [vp] * 7
+        L.b2_host_buffers.argtypes = [vp] + [ctypes.POINTER(vp)] * 5
+        L.b2_reseed.argtypes = [vp, ctypes.c_uint64, vp]
+        L.b2_caps.argtypes = [vp, vp]
+        L.b2_get_final_state.argtypes = [vp] * 5
         L.b2_launch_count.restype = ctypes.c_ulonglong
         L.b2_last_error.restype = ctypes.c_char_p
         _LIB = L
@@ -141,6 +146,23 @@ class Batch:
         _ck(lib().b2_dims(self.handle, d))
         (self.nq, self.nv, self.nu, self.nbody, self.obs_dim, self.act_dim, self.n_envs, self.nti, self.ntf, self.con_cap,
          self.smem_bytes, self.envs_per_block, self.row_cap, self.nM, self.arena_floats, self.ws_bytes) = [int(x) for x in d[:16]]
+        _ck(lib().b2_caps(self.handle, d))
+        (self.ninj, self.wide_con_cap, self.wide_row_cap, self.wide_arena_floats, self.wide_kib_per_env, self.raw_cap, self.act_cap,
+         self.wide_enabled, self.episode_slot, self.warm_once) = [int(x) for x in d[:10]]
+        self._host = None
+
+    # ---- argument checks: the kernel indexes these buffers by env without bounds checks (a wrong shape would read out of bounds)
+    def _check(self, name, t, shape, dtype=None):
+        if t is None:
+            return
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        if t.device != self.device:
+            raise ValueError(f"{name}: expected a tensor on {self.device}, got {t.device}")
+        if dtype is not None and t.dtype != dtype:
+            raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: must be contiguous")
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -150,13 +172,61 @@ class Batch:
 
     # ---- hot path
     def reset(self, obs, mask=None, inject=None):
+        t = self.torch
+        self._check("obs", obs, (self.n_envs, self.obs_dim), t.float32)
+        if mask is not None:
+            self._check("reset_mask", mask, (self.n_envs,), t.uint8)
+        if inject is not None:
+            self._check("inject", inject, (self.n_envs, self.ninj), t.float32)
         _ck(lib().b2_reset(self.handle, _ptr(mask), _ptr(inject), _ptr(obs), self._stream()))
 
+    def reseed(self, seed: int):
+        """``Env.reset(seed=...)``: new RNG seed, episode counters restart (same seed -> same initial states)."""
+        _ck(lib().b2_reseed(self.handle, ctypes.c_uint64(int(seed) & (2**64 - 1)), self._stream()))
+
     def step(self, act, obs, rew, term, trunc, final_obs=None):
+        t = self.torch
+        self._check("actions", act, (self.n_envs, self.act_dim), t.float32); self._check("obs", obs, (self.n_envs, self.obs_dim), t.float32)
+        self._check("reward", rew, (self.n_envs,), t.float32); self._check("terminated", term, (self.n_envs,), t.uint8)
+        self._check("truncated", trunc, (self.n_envs,), t.uint8); self._check("final_obs", final_obs, (self.n_envs, self.obs_dim), t.float32)
         _ck(lib().b2_step(self.handle, _ptr(act), _ptr(obs), _ptr(rew), _ptr(term), _ptr(trunc), _ptr(final_obs), self._stream()))
 
+    def rollout(self, act, obs, rew, term, trunc, final_obs=None):
+        """T env.steps with the host out of the loop (one CUDA graph): act [T, N, A] -> obs [T, N, D], rew/term/trunc [T, N]."""
+        t = self.torch; T = int(act.shape[0])
+        self._check("actions", act, (T, self.n_envs, self.act_dim), t.float32); self._check("obs", obs, (T, self.n_envs, self.obs_dim), t.float32)
+        self._check("reward", rew, (T, self.n_envs), t.float32); self._check("terminated", term, (T, self.n_envs), t.uint8)
+        self._check("truncated", trunc, (T, self.n_envs), t.uint8); self._check("final_obs", final_obs, (T, self.n_envs, self.obs_dim), t.float32)
+        _ck(lib().b2_rollout(self.handle, T, _ptr(act), _ptr(obs), _ptr(rew), _ptr(term), _ptr(trunc), _ptr(final_obs), self._stream()))
+
     def step_host(self, act: np.ndarray, obs: np.ndarray, rew: np.ndarray, term: np.ndarray, trunc: np.ndarray):
+        for name, a, shape, dt in (("actions", act, (self.n_envs, self.act_dim), np.float32), ("obs", obs, (self.n_envs, self.obs_dim), np.float32),
+                                   ("reward", rew, (self.n_envs,), np.float32), ("terminated", term, (self.n_envs,), np.uint8),
+                                   ("truncated", trunc, (self.n_envs,), np.uint8)):
+            if a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{name}: expected a C-contiguous {np.dtype(dt).name} array of shape {shape}, got {a.dtype} {a.shape}")
         _ck(lib().b2_step_host(self.handle, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data))
+
+    def host_buffers(self):
+        """numpy views of the library's pinned staging buffers (act, obs, rew, term, trunc): pass them to step_host for zero-copy."""
+        if self._host is None:
+            p = [ctypes.c_void_p() for _ in range(5)]
+            _ck(lib().b2_host_buffers(self.handle, *[ctypes.byref(x) for x in p]))
+            def view(ptr, shape, ctype, dt):
+                n = int(np.prod(shape)); buf = (ctype * n).from_address(ptr.value)
+                return np.frombuffer(buf, dtype=dt).reshape(shape)
+            N = self.n_envs
+            self._host = (view(p[0], (N, max(self.act_dim, 1)), ctypes.c_float, np.float32)[:, :self.act_dim] if self.act_dim else None,
+                          view(p[1], (N, max(self.obs_dim, 1)), ctypes.c_float, np.float32), view(p[2], (N,), ctypes.c_float, np.float32),
+                          view(p[3], (N,), ctypes.c_uint8, np.uint8), view(p[4], (N,), ctypes.c_uint8, np.uint8))
+        return self._host
+
+    def final_state(self):
+        """Task state / xpos of the episode that ended in each env's last terminal step (before the same-step auto-reset)."""
+        ti = self._new((self.n_envs, max(self.nti, 1)), self.torch.int32); tf = self._new((self.n_envs, max(self.ntf, 1)))
+        x = self._new((self.n_envs, self.nbody, 3))
+        _ck(lib().b2_get_final_state(self.handle, _ptr(ti), _ptr(tf), _ptr(x), self._stream()))
+        return ti, tf, x
 
     def physics_step(self, nsub: int = 1):
         _ck(lib().b2_physics_step(self.handle, nsub, self._stream()))

@@ -25,11 +25,17 @@ struct B2Model {
 struct B2Batch {
   B2Model* m; int n_envs, W; TaskParams tp; BatchView v; size_t smem;
   DevModel dm;        // the model as this batch's kernels see it (pair tables staged or cold)
-  float* epstat;      // [N][4] episodes, return_sum, length_sum, (spare)
+  double* epstat;     // [N][4] episodes, return_sum, length_sum, (spare)
   double* d_stats;
-  float *h_act, *h_obs, *h_rew; uint8_t *h_term, *h_trunc;   // pinned staging for b2_step_host
-  float *d_act, *d_obs, *d_rew, *d_inject; uint8_t *d_term, *d_trunc;
-  cudaStream_t own_stream;
+  // b2_step_host staging: ONE packed result block [obs | rew | term | trunc] on each side, so a step is one H2D copy, one
+  // launch and one D2H copy; the pinned host side is also handed out (b2_host_buffers) for zero-copy callers
+  float *h_act, *d_act; char *h_out, *d_out; size_t out_bytes, off_rew, off_term, off_trunc;
+  float *h_obs, *h_rew; uint8_t *h_term, *h_trunc;           // views into h_out
+  float *d_obs, *d_rew, *d_inject; uint8_t *d_term, *d_trunc; // views into d_out (d_inject separate)
+  cudaStream_t own_stream; cudaEvent_t ev_order; cudaStream_t last_stream; bool pending;   // caller-stream work not yet ordered before own_stream
+  int episode_slot;   // index of the episode id in ti (RNG stream key), -1 none
+  // b2_rollout: the T launches of a rollout as one instantiated CUDA graph, cached while T and the buffers stay the same
+  cudaGraphExec_t roll_exec; int roll_T; const void* roll_key[6];
   int obs_dim, act_dim, nti, ntf, ninj;
 };
 
@@ -39,12 +45,12 @@ struct B2Batch {
 template <class Task, int W>
 __global__ void __launch_bounds__(32 * W * Task::MAX_EPB, 1)
 b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B, const __grid_constant__ TaskParams tp,
-              int mode, float* epstat, const float* inject) {
+              int mode, double* epstat, const float* inject) {
   const int team = threadIdx.x / (32 * W);
   uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
   stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints_staged), bar);
-  const int env = blockIdx.x * B.envs_per_block + team;
-  if (env >= B.n_envs) return;
+  const int env = B.first_env + blockIdx.x * B.envs_per_block + team;
+  if (env >= B.first_env + B.n_envs) return;
   if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
   Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team, env);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
@@ -101,8 +107,16 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
       if (w0) {
         if (B.final_obs) for (int i = lane; i < Task::OBS; i += 32) B.final_obs[(size_t)env * B.obs_dim + i] = B.obs[(size_t)env * B.obs_dim + i];
         if (lane == 0) {
-          epstat[4 * env + 0] += 1.f; epstat[4 * env + 1] += s_tf[0]; epstat[4 * env + 2] += (float)s_ti[0];
+          epstat[4 * env + 0] += 1.0; epstat[4 * env + 1] += (double)s_tf[0]; epstat[4 * env + 2] += (double)s_ti[0];
           atomicAdd(&ctr[CTR_EPISODES], 1ull);
+        }
+        // the finished episode's task state and body positions, for the terminal step's info (the reference reports the
+        // totals of the episode that just ended, e.g. quadruped_parkour_env/parkour_env.py:797-813)
+        if (B.final_ti) {
+          for (int i = lane; i < Task::NTI; i += 32) B.final_ti[(size_t)env * B.nti + i] = s_ti[i];
+          for (int i = lane; i < Task::NTF; i += 32) B.final_tf[(size_t)env * B.ntf + i] = s_tf[i];
+          const int n3 = 3 * P.dim[DD_nbody];
+          for (int i = lane; i < n3; i += 32) B.final_xpos[(size_t)env * n3 + i] = E.p_xpos()[i];
         }
         E.sync();
         Task::reset_state(E, tp, B, env, s_ti, s_tf, nullptr);
@@ -157,7 +171,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1;
   static constexpr int SOLVER = -1;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
@@ -171,7 +185,7 @@ struct NoTask {
   template <class EN> __device__ static void post_physics(EN&, const TaskParams&, int*, float*) {}
 };
 
-__global__ void b2_stats_kernel(const unsigned long long* counters, const float* epstat, int n, double* out) {
+__global__ void b2_stats_kernel(const unsigned long long* counters, const double* epstat, int n, double* out) {
   __shared__ double acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
   __syncthreads();
@@ -197,7 +211,7 @@ static int configure_task(B2Batch* b) {
 }
 template <class Task>
 static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
-  int E = b->v.envs_per_block, grid = (b->n_envs + E - 1) / E;
+  int E = b->v.envs_per_block, grid = (b->v.n_envs + E - 1) / E;
   b2_env_kernel<Task, 3><<<grid, 32 * 3 * E, b->smem, s>>>(b->dm, b->v, b->tp, mode, b->epstat, inject);
   g_launches++;
   CK(cudaGetLastError());
@@ -220,8 +234,19 @@ static int configure(B2Batch* b) {
   B2_FOR_TASK(b, B2_CALL);
 #undef B2_CALL
 }
+// Work issued on a caller stream and work issued on own_stream (b2_step_host) touch the same state rows: whenever the stream
+// changes, the new one first waits for an event recorded on the previous one.
+static int order_after_last(B2Batch* b, cudaStream_t s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return B2_OK;    // inside a graph capture: the capturer orders
+  if (b->pending && b->last_stream != s) { CK(cudaEventRecord(b->ev_order, b->last_stream)); CK(cudaStreamWaitEvent(s, b->ev_order, 0)); }
+  b->last_stream = s; b->pending = true;
+  return B2_OK;
+}
 static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, s); if (rc) return rc; }
+  if (b->v.n_envs <= 0 || b->v.first_env + b->v.n_envs > b->n_envs) { b->v.first_env = 0; b->v.n_envs = b->n_envs; }
 #define B2_CALL(T) launch_task<T>(b, mode, inject, s)
   B2_FOR_TASK(b, B2_CALL);
 #undef B2_CALL
@@ -287,8 +312,8 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); memcpy(b->tp.aux_i, task->aux_i, sizeof(task->aux_i)); memcpy(b->tp.aux_f, task->aux_f, sizeof(task->aux_f)); }
   switch (b->tp.task) {
-    case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; break;
-#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+    case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; b->episode_slot = -1; break;
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; b->episode_slot = T::EPISODE_SLOT; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -368,10 +393,10 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
   CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
   CK(cudaMalloc(&v.phase_cycles, 16 * 8)); CK(cudaMemset(v.phase_cycles, 0, 16 * 8));
-  CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 4)); CK(cudaMalloc(&b->d_stats, 16 * 8));
+  CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 8)); CK(cudaMalloc(&b->d_stats, 16 * 8));
   CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));
   CK(cudaMemset(v.ctrl, 0, N * v.nup * 4)); CK(cudaMemset(v.time, 0, N * 4)); CK(cudaMemset(v.ti, 0, N * v.nti * 4));
-  CK(cudaMemset(v.tf, 0, N * v.ntf * 4)); CK(cudaMemset(v.counters, 0, N * CTR_COUNT * 8)); CK(cudaMemset(b->epstat, 0, N * 16));
+  CK(cudaMemset(v.tf, 0, N * v.ntf * 4)); CK(cudaMemset(v.counters, 0, N * CTR_COUNT * 8)); CK(cudaMemset(b->epstat, 0, N * 32));
   // qpos <- qpos0
   {
     std::vector<float> q((size_t)N * v.nqp, 0.f);
@@ -380,13 +405,17 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     for (size_t e = 0; e < N; e++) memcpy(&q[e * v.nqp], q0.data(), sizeof(float) * dim[DD_nq]);
     CK(cudaMemcpy(v.qpos, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
   }
-  // staging for the host-buffer entry point
+  // staging for the host-buffer entry point: one packed result block per side
   size_t od = b->obs_dim > 0 ? b->obs_dim : 1, ad = b->act_dim > 0 ? b->act_dim : 1;
-  CK(cudaMallocHost(&b->h_act, N * ad * 4)); CK(cudaMallocHost(&b->h_obs, N * od * 4)); CK(cudaMallocHost(&b->h_rew, N * 4));
-  CK(cudaMallocHost(&b->h_term, N)); CK(cudaMallocHost(&b->h_trunc, N));
-  CK(cudaMalloc(&b->d_act, N * ad * 4)); CK(cudaMalloc(&b->d_obs, N * od * 4)); CK(cudaMalloc(&b->d_rew, N * 4));
-  CK(cudaMalloc(&b->d_term, N)); CK(cudaMalloc(&b->d_trunc, N)); CK(cudaMalloc(&b->d_inject, N * (size_t)b->ninj * 4));
-  CK(cudaStreamCreate(&b->own_stream));
+  b->off_rew = (N * od * 4 + 15) & ~(size_t)15; b->off_term = (b->off_rew + N * 4 + 15) & ~(size_t)15;
+  b->off_trunc = (b->off_term + N + 15) & ~(size_t)15; b->out_bytes = (b->off_trunc + N + 15) & ~(size_t)15;
+  CK(cudaMallocHost(&b->h_act, N * ad * 4)); CK(cudaMallocHost(&b->h_out, b->out_bytes));
+  CK(cudaMalloc(&b->d_act, N * ad * 4)); CK(cudaMalloc(&b->d_out, b->out_bytes)); CK(cudaMalloc(&b->d_inject, N * (size_t)b->ninj * 4));
+  b->h_obs = (float*)b->h_out; b->h_rew = (float*)(b->h_out + b->off_rew); b->h_term = (uint8_t*)(b->h_out + b->off_term); b->h_trunc = (uint8_t*)(b->h_out + b->off_trunc);
+  b->d_obs = (float*)b->d_out; b->d_rew = (float*)(b->d_out + b->off_rew); b->d_term = (uint8_t*)(b->d_out + b->off_term); b->d_trunc = (uint8_t*)(b->d_out + b->off_trunc);
+  CK(cudaMalloc(&v.final_ti, N * v.nti * 4)); CK(cudaMalloc(&v.final_tf, N * v.ntf * 4)); CK(cudaMalloc(&v.final_xpos, N * (size_t)dim[DD_nbody] * 3 * 4));
+  CK(cudaMemset(v.final_ti, 0, N * v.nti * 4)); CK(cudaMemset(v.final_tf, 0, N * v.ntf * 4)); CK(cudaMemset(v.final_xpos, 0, N * (size_t)dim[DD_nbody] * 3 * 4));
+  CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&b->ev_order, cudaEventDisableTiming));
   { int rc = configure(b); if (rc) return rc; }
   guard.b = nullptr;
   *out = b;
@@ -399,8 +428,10 @@ void b2_batch_destroy(B2Batch* b) {
   cudaFree(v.wide);
   cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
   cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.phase_cycles); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
-  cudaFreeHost(b->h_act); cudaFreeHost(b->h_obs); cudaFreeHost(b->h_rew); cudaFreeHost(b->h_term); cudaFreeHost(b->h_trunc);
-  cudaFree(b->d_act); cudaFree(b->d_obs); cudaFree(b->d_rew); cudaFree(b->d_term); cudaFree(b->d_trunc); cudaFree(b->d_inject);
+  cudaFree(v.final_ti); cudaFree(v.final_tf); cudaFree(v.final_xpos);
+  cudaFreeHost(b->h_act); cudaFreeHost(b->h_out); cudaFree(b->d_act); cudaFree(b->d_out); cudaFree(b->d_inject);
+  if (b->roll_exec) cudaGraphExecDestroy(b->roll_exec);
+  if (b->ev_order) cudaEventDestroy(b->ev_order);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
@@ -432,16 +463,84 @@ int b2_step_host(B2Batch* b, const float* act, float* obs, float* rew, uint8_t* 
   if (!b || !act || !obs || !rew || !term || !trunc) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
   size_t N = b->n_envs; cudaStream_t s = b->own_stream;
-  memcpy(b->h_act, act, N * b->act_dim * 4);
+  if (act != b->h_act) memcpy(b->h_act, act, N * b->act_dim * 4);          // callers holding b2_host_buffers() skip the staging copies
   CK(cudaMemcpyAsync(b->d_act, b->h_act, N * b->act_dim * 4, cudaMemcpyHostToDevice, s));
   int rc = b2_step(b, b->d_act, b->d_obs, b->d_rew, b->d_term, b->d_trunc, nullptr, s);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(b->h_obs, b->d_obs, N * b->obs_dim * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(b->h_rew, b->d_rew, N * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(b->h_term, b->d_term, N, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(b->h_trunc, b->d_trunc, N, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(b->h_out, b->d_out, b->out_bytes, cudaMemcpyDeviceToHost, s));     // obs | rew | term | trunc in one copy
   CK(cudaStreamSynchronize(s));
-  memcpy(obs, b->h_obs, N * b->obs_dim * 4); memcpy(rew, b->h_rew, N * 4); memcpy(term, b->h_term, N); memcpy(trunc, b->h_trunc, N);
+  b->pending = false;
+  if (obs != b->h_obs) memcpy(obs, b->h_obs, N * b->obs_dim * 4);
+  if (rew != b->h_rew) memcpy(rew, b->h_rew, N * 4);
+  if (term != b->h_term) memcpy(term, b->h_term, N);
+  if (trunc != b->h_trunc) memcpy(trunc, b->h_trunc, N);
+  return B2_OK;
+}
+// T x env.step with the actions already on the device: the caller of env.step in test_parkour.py:45-47 / test_soccer.py:57-59 with
+// the host taken out of the loop.  The T launches are captured once into a CUDA graph (kernel parameters carry the per-step
+// slices of the caller's buffers) and replayed by one cudaGraphLaunch; the graph is re-captured when T or a buffer changes.
+int b2_rollout(B2Batch* b, int T, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* term_dev, uint8_t* trunc_dev,
+               float* final_obs_dev, void* stream) {
+  if (!b || T <= 0 || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(B2_ERR_ARG, "bad argument");
+  if (b->tp.task == TASK_NONE) return fail(B2_ERR_UNSUPPORTED, "batch has no task");
+  CK(cudaSetDevice(b->m->device));
+  cudaStream_t s = (cudaStream_t)stream; size_t N = b->n_envs;
+  { int rc = order_after_last(b, s); if (rc) return rc; }
+  const void* key[6] = {act_dev, obs_dev, rew_dev, term_dev, trunc_dev, final_obs_dev};
+  if (!b->roll_exec || b->roll_T != T || memcmp(key, b->roll_key, sizeof(key)) != 0) {
+    if (b->roll_exec) { cudaGraphExecDestroy(b->roll_exec); b->roll_exec = nullptr; }
+    cudaStream_t cap = s ? s : b->own_stream;            // the legacy default stream cannot be captured
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = B2_OK;
+    for (int t = 0; t < T && rc == B2_OK; t++)
+      rc = b2_step(b, act_dev + (size_t)t * N * b->act_dim, obs_dev + (size_t)t * N * b->obs_dim, rew_dev + (size_t)t * N, term_dev + (size_t)t * N,
+                   trunc_dev + (size_t)t * N, final_obs_dev ? final_obs_dev + (size_t)t * N * b->obs_dim : nullptr, cap);
+    cudaError_t e = cudaStreamEndCapture(cap, &g);
+    g_launches -= (unsigned long long)T;                 // counted per replay below, not per capture
+    if (rc != B2_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(B2_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&b->roll_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { b->roll_exec = nullptr; return fail(B2_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    b->roll_T = T; memcpy(b->roll_key, key, sizeof(key));
+  }
+  if (!s) { CK(cudaStreamSynchronize(0)); }             // a NULL stream means "after everything on the legacy stream"
+  CK(cudaGraphLaunch(b->roll_exec, s ? s : b->own_stream));
+  g_launches += (unsigned long long)T;
+  if (!s) { b->last_stream = b->own_stream; b->pending = true; }
+  return B2_OK;
+}
+int b2_host_buffers(B2Batch* b, float** act, float** obs, float** rew, uint8_t** term, uint8_t** trunc) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  if (act) *act = b->h_act; if (obs) *obs = b->h_obs; if (rew) *rew = b->h_rew; if (term) *term = b->h_term; if (trunc) *trunc = b->h_trunc;
+  return B2_OK;
+}
+int b2_reseed(B2Batch* b, uint64_t seed, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  b->v.seed = seed;
+  if (b->episode_slot >= 0) {      // episode counters restart, so reset(seed = s) always draws the same streams
+    { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
+    CK(cudaMemset2DAsync(b->v.ti + b->episode_slot, (size_t)b->v.nti * 4, 0, 4, (size_t)b->n_envs, (cudaStream_t)stream));
+  }
+  return B2_OK;
+}
+int b2_caps(const B2Batch* b, int* o) {  /* o has 16 entries */
+  if (!b || !o) return fail(B2_ERR_ARG, "null argument");
+  memset(o, 0, 16 * sizeof(int));
+  o[0] = b->ninj; o[1] = b->v.w_con_cap; o[2] = b->v.w_row_cap; o[3] = b->v.w_arena_floats; o[4] = (int)(b->v.wide_stride * 4 / 1024);
+  o[5] = b->v.raw_cap; o[6] = b->v.act_cap; o[7] = b->v.wide ? 1 : 0; o[8] = b->episode_slot; o[9] = b->v.warm_once;
+  return B2_OK;
+}
+int b2_get_final_state(B2Batch* b, int32_t* ti, float* tf, float* xpos, void* stream) {
+  if (!b) return fail(B2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->m->device));
+  size_t N = b->n_envs; cudaStream_t s = (cudaStream_t)stream;
+  { int rc = order_after_last(b, s); if (rc) return rc; }
+  if (ti && b->nti) CK(cudaMemcpyAsync(ti, b->v.final_ti, N * b->v.nti * 4, cudaMemcpyDeviceToDevice, s));
+  if (tf && b->ntf) CK(cudaMemcpyAsync(tf, b->v.final_tf, N * b->v.ntf * 4, cudaMemcpyDeviceToDevice, s));
+  if (xpos) CK(cudaMemcpyAsync(xpos, b->v.final_xpos, N * (size_t)b->m->dm.dim[DD_nbody] * 3 * 4, cudaMemcpyDeviceToDevice, s));
   return B2_OK;
 }
 int b2_physics_step(B2Batch* b, int nsub, void* stream) {
@@ -464,6 +563,7 @@ static int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size
 int b2_get_state(B2Batch* b, float* q, float* qv, float* c, float* wm, float* t, void* stream) {
   if (!b) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
   const int* d = b->m->dm.dim; BatchView& v = b->v; cudaStream_t s = (cudaStream_t)stream; size_t N = b->n_envs; int rc = 0;
   if (q) rc |= copy2d(q, d[DD_nq] * 4, v.qpos, v.nqp * 4, d[DD_nq] * 4, N, s);
   if (qv) rc |= copy2d(qv, d[DD_nv] * 4, v.qvel, v.nvp * 4, d[DD_nv] * 4, N, s);
@@ -475,6 +575,7 @@ int b2_get_state(B2Batch* b, float* q, float* qv, float* c, float* wm, float* t,
 int b2_set_state(B2Batch* b, const float* q, const float* qv, const float* c, const float* wm, const float* t, void* stream) {
   if (!b) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
   const int* d = b->m->dm.dim; BatchView& v = b->v; cudaStream_t s = (cudaStream_t)stream; size_t N = b->n_envs; int rc = 0;
   if (q) rc |= copy2d(v.qpos, v.nqp * 4, q, d[DD_nq] * 4, d[DD_nq] * 4, N, s);
   if (qv) rc |= copy2d(v.qvel, v.nvp * 4, qv, d[DD_nv] * 4, d[DD_nv] * 4, N, s);
@@ -486,6 +587,7 @@ int b2_set_state(B2Batch* b, const float* q, const float* qv, const float* c, co
 int b2_get_task_state(B2Batch* b, int32_t* ti, float* tf, void* stream) {
   if (!b) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
   size_t N = b->n_envs; cudaStream_t s = (cudaStream_t)stream;
   if (ti && b->nti) CK(cudaMemcpyAsync(ti, b->v.ti, N * b->v.nti * 4, cudaMemcpyDeviceToDevice, s));
   if (tf && b->ntf) CK(cudaMemcpyAsync(tf, b->v.tf, N * b->v.ntf * 4, cudaMemcpyDeviceToDevice, s));
@@ -494,6 +596,7 @@ int b2_get_task_state(B2Batch* b, int32_t* ti, float* tf, void* stream) {
 int b2_set_task_state(B2Batch* b, const int32_t* ti, const float* tf, void* stream) {
   if (!b) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
   size_t N = b->n_envs; cudaStream_t s = (cudaStream_t)stream;
   if (ti && b->nti) CK(cudaMemcpyAsync(b->v.ti, ti, N * b->v.nti * 4, cudaMemcpyDeviceToDevice, s));
   if (tf && b->ntf) CK(cudaMemcpyAsync(b->v.tf, tf, N * b->v.ntf * 4, cudaMemcpyDeviceToDevice, s));
@@ -523,6 +626,7 @@ int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream) {
 int b2_stats(B2Batch* b, double* out, void* stream) {
   if (!b || !out) return fail(B2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->m->device));
+  { int rc = order_after_last(b, (cudaStream_t)stream); if (rc) return rc; }
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaMemsetAsync(out, 0, 16 * 8, s));
   int blocks = (b->n_envs + 255) / 256; if (blocks > 148) blocks = 148;

@@ -111,11 +111,12 @@ __host__ inline int ws_layout(const int* dim, int con_cap, int row_cap, int aren
   return (off + 31) & ~31;
 }
 struct BatchView {
-  int n_envs;
+  int n_envs; int first_env;                         // this launch steps envs [first_env, first_env + n_envs)
   float *qpos, *qvel, *warm, *ctrl, *qfrc_applied, *time;
   int nqp, nvp, nup;               // row pitches (floats)
   int *ti; float *tf; int nti, ntf;  // per-env task state
   float *obs, *final_obs, *reward; uint8_t *term, *trunc; int obs_dim;
+  int* final_ti; float* final_tf; float* final_xpos; // task state / xpos of the episode that ended in this step (before the in-kernel reset)
   const float* action; int act_dim;
   const uint8_t* reset_mask;
   int *c_ncon, *c_geom; float* c_dist; int c_cap;   // optional contact export

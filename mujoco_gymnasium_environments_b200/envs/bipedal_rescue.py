@@ -56,7 +56,7 @@ class BipedalRescueEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._state(o)
 
     def _state(self, o) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         q = o[55:59]
         stats = {"victims_rescued": int(ti[11]), "distance_traveled": float(tf[6]), "energy_used": float(tf[7]),

@@ -45,7 +45,7 @@ class HumanoidConstructionEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
 
     def _info(self) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         return {"task": TASK_TYPES[int(ti[1])], "task_progress": float(tf[1]), "blocks_placed": 0, "safety_violations": 0,
                 "episode_stats": {"blocks_placed": 0, "materials_transported": 0, "crane_operations": 0, "safety_violations": 0,

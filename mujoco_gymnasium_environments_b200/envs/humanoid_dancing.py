@@ -75,7 +75,7 @@ class HumanoidDancingEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), info
 
     def _state(self) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         d = tf[2:8].view(np.float64)       # time_since_last_beat, combo_multiplier, move_start_time
         stats = {"total_score": float(tf[0]), "perfect_moves": 0, "good_moves": 0, "missed_beats": 0,

@@ -43,7 +43,7 @@ class HumanoidMartialArtsEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
 
     def _info(self) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         return {"episode_stats": {"techniques_performed": int(ti[1]), "successful_combos": 0, "balance_maintained": 0,
                                   "max_power_generated": 0.0, "total_distance_moved": 0.0, "falls": int(ti[3])},

@@ -57,7 +57,7 @@ class HumanoidSoccerEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._state()
 
     def _state(self) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         ball = tf[1:4].astype(np.float64); robot = tf[4:7].astype(np.float64)     # positions of the last forward pass
         quat_up = float(self._vec._obs[0, 50] ** 2 - self._vec._obs[0, 51] ** 2 - self._vec._obs[0, 52] ** 2 + self._vec._obs[0, 53] ** 2)

@@ -55,9 +55,9 @@ class QuadrupedParkourEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._info(prev_episode=done)
 
     def _info(self, prev_episode: bool = False) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf, xpos = self._vec.task_state(with_xpos=True)   # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
-        x = float(self._vec.batch.xpos()[0, self.model.name2id("body", "torso"), 0])
+        x = float(xpos[0, self.model.name2id("body", "torso"), 0])
         return {"step_count": int(ti[0]), "episode_reward": float(tf[0]), "max_forward_progress": float(tf[2]),
                 "checkpoints_reached": int(bin(int(ti[1])).count("1")), "fall_count": int(ti[2]),
                 "course_completion": min(1.0, max(0.0, (x - 2.0) / 96.0))}

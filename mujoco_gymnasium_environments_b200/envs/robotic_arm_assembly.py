@@ -45,7 +45,7 @@ class RoboticArmAssemblyEnv(_GymEnv):
         return o, float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
 
     def _info(self) -> Dict[str, Any]:
-        ti, tf = self._vec.batch.get_task_state()
+        ti, tf = self._vec.task_state()       # the finished episode's values on a terminal step
         ti = ti[0].cpu().numpy(); tf = tf[0].cpu().numpy()
         return {"step_count": int(ti[0]),
                 "assembly_progress": {c: bool((int(ti[1]) >> k) & 1) for k, c in enumerate(ARM_SEQUENCE)},

@@ -32,6 +32,7 @@ class TaskSpec:
     action_space: Callable[[ModelTables], Box]
     observation_space: Callable[[ModelTables], Box]
     info_keys: List[str]
+    vector_info: Callable = None     # (torch, ti[N, nti], tf[N, ntf], xpos[N, nbody, 3], tables) -> {reference info key: tensor[N] or dict of them}
 
 
 def load_tables(task: str, assets_root: str | None = None) -> ModelTables:
@@ -217,6 +218,60 @@ def _arm_desc(t: ModelTables) -> capi.B2TaskDesc:
     return d
 
 
+# ---------------------------------------------------------------------------------------------- per-env infos (vector API)
+# The numeric entries of each reference env's ``info`` dict as device tensors of shape [N], read from the task state rows
+# (layouts: the ``ti`` / ``tf`` comments above each task in csrc/b2_tasks.cuh).  String-valued entries (current_move, task,
+# task_phase ...) are given as their integer index.
+def _popcount(torch, x):
+    x = x.to(torch.int64); n = torch.zeros_like(x)
+    for k in range(32):
+        n += (x >> k) & 1
+    return n
+
+
+def _quad_info(torch, ti, tf, xpos, t):
+    x = xpos[:, t.name2id("body", "torso"), 0]
+    return {"step_count": ti[:, 0], "episode_reward": tf[:, 0], "max_forward_progress": tf[:, 2], "checkpoints_reached": _popcount(torch, ti[:, 1]),
+            "fall_count": ti[:, 2], "course_completion": ((x - 2.0) / 96.0).clamp(0.0, 1.0)}       # parkour_env.py:797-813
+
+
+def _dance_info(torch, ti, tf, xpos, t):
+    d = tf[:, 2:8].contiguous().view(torch.float64)       # time_since_last_beat, combo_multiplier, move_start_time (fp64 on the device)
+    return {"episode_stats": {"total_score": tf[:, 0], "longest_combo": ti[:, 6], "energy_used": tf[:, 11], "time_on_beat": tf[:, 12], "crowd_rating": tf[:, 1]},
+            "current_move": ti[:, 3] % 10, "beat_phase": d[:, 0] / 0.5, "combo_multiplier": d[:, 1], "crowd_excitement": tf[:, 1],
+            "performance_score": tf[:, 0]}                                                        # dancing_env.py:866-874
+
+
+def _soccer_info(torch, ti, tf, xpos, t):
+    goal = torch.tensor([24.5, 0.0, 0.0], device=tf.device)
+    return {"episode_stats": {"goals_scored": ti[:, 2], "ball_contacts": ti[:, 3], "distance_traveled": tf[:, 12], "time_upright": tf[:, 11],
+                              "max_ball_speed": tf[:, 13]},
+            "ball_position": tf[:, 1:4], "robot_position": tf[:, 4:7], "goal_distance": (tf[:, 4:7] - goal).norm(dim=1),
+            "goal_scored": ti[:, 1] != 0}                                                         # soccer_env.py:433-441
+
+
+def _rescue_info(torch, ti, tf, xpos, t):
+    return {"episode_stats": {"victims_rescued": ti[:, 11], "distance_traveled": tf[:, 6], "energy_used": tf[:, 7], "time_to_first_rescue": tf[:, 8],
+                              "falls": ti[:, 9], "collisions": ti[:, 10]},
+            "robot_position": xpos[:, t.name2id("body", "torso")], "victims_remaining": 5 - ti[:, 11], "victims_carried": _popcount(torch, ti[:, 2]),
+            "energy_remaining": tf[:, 1]}                                                         # rescue_env.py:454-461
+
+
+def _construction_info(torch, ti, tf, xpos, t):
+    return {"task": ti[:, 1], "task_progress": tf[:, 1], "blocks_placed": torch.zeros_like(ti[:, 0]), "safety_violations": torch.zeros_like(ti[:, 0]),
+            "episode_stats": {"tasks_completed": ti[:, 3], "total_reward": tf[:, 0]},
+            "weather": {"wind": tf[:, 2], "rain": tf[:, 3], "temperature": tf[:, 4]}}              # construction_env.py:613-620
+
+
+def _martial_info(torch, ti, tf, xpos, t):
+    return {"episode_stats": {"techniques_performed": ti[:, 1], "falls": ti[:, 3]}, "stance_stability": tf[:, 1], "current_step": ti[:, 0]}   # martial_arts_env.py:513-518
+
+
+def _arm_info(torch, ti, tf, xpos, t):
+    return {"step_count": ti[:, 0], "assembly_progress": ti[:, 1], "task_phase": ti[:, 4], "held_component": ti[:, 3], "cumulative_reward": tf[:, 0],
+            "success": (ti[:, 1] & 0x1ff) == 0x1ff}                                               # assembly_env.py:243-252
+
+
 TASKS: Dict[str, TaskSpec] = {
     "quadruped_parkour": TaskSpec(
         name="quadruped_parkour", task_id=capi.TASK_QUADRUPED_PARKOUR, obs_dim=95, act_dim=16, max_episode_steps=6000,
@@ -224,46 +279,46 @@ TASKS: Dict[str, TaskSpec] = {
         action_space=lambda t: Box(-_quad_limits(t), _quad_limits(t), dtype=np.float32),
         observation_space=_quad_obs_space,
         info_keys=["step_count", "episode_reward", "max_forward_progress", "checkpoints_reached", "fall_count",
-                   "course_completion"]),
+                   "course_completion"], vector_info=_quad_info),
     "humanoid_dancing": TaskSpec(
         name="humanoid_dancing", task_id=capi.TASK_HUMANOID_DANCING, obs_dim=94, act_dim=29, max_episode_steps=3600,
         frame_skip=1, render_fps=60, bytes_per_env_step=1954, describe=_dance_desc,
         action_space=lambda t: Box(np.full(29, -200.0, np.float32), np.full(29, 200.0, np.float32), dtype=np.float32),
         observation_space=lambda t: Box(np.full(94, -np.inf, np.float32), np.full(94, np.inf, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "current_move", "beat_phase", "combo_multiplier", "crowd_excitement",
-                   "performance_score"]),
+                   "performance_score"], vector_info=_dance_info),
     "humanoid_soccer": TaskSpec(
         name="humanoid_soccer", task_id=capi.TASK_HUMANOID_SOCCER, obs_dim=80, act_dim=33, max_episode_steps=5000,
         frame_skip=1, render_fps=50, bytes_per_env_step=1626, describe=_soccer_desc,
         action_space=lambda t: Box(np.full(33, -150.0, np.float32), np.full(33, 150.0, np.float32), dtype=np.float32),
         observation_space=lambda t: Box(np.full(80, -1.0, np.float32), np.full(80, 1.0, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "ball_position", "robot_position", "goal_distance", "ball_contact", "robot_upright",
-                   "goal_scored"]),
+                   "goal_scored"], vector_info=_soccer_info),
     "bipedal_rescue": TaskSpec(
         name="bipedal_rescue", task_id=capi.TASK_BIPEDAL_RESCUE, obs_dim=102, act_dim=26, max_episode_steps=10000,
         frame_skip=1, render_fps=50, bytes_per_env_step=2190, describe=_rescue_desc,
         action_space=lambda t: Box(np.full(26, -100.0, np.float32), np.full(26, 100.0, np.float32), dtype=np.float32),
         observation_space=lambda t: Box(np.full(102, -np.inf, np.float32), np.full(102, np.inf, np.float32), dtype=np.float32),
         info_keys=["episode_stats", "robot_position", "victims_remaining", "victims_carried", "energy_remaining",
-                   "robot_upright"]),
+                   "robot_upright"], vector_info=_rescue_info),
     "humanoid_construction": TaskSpec(
         name="humanoid_construction", task_id=capi.TASK_HUMANOID_CONSTRUCTION, obs_dim=135, act_dim=33, max_episode_steps=3000,
         frame_skip=1, render_fps=50, bytes_per_env_step=3222, describe=_construction_desc,
         action_space=lambda t: Box(np.full(33, -200.0, np.float32), np.full(33, 200.0, np.float32), dtype=np.float32),
         # the reference declares 125 entries but returns 135: the actual length is exposed
         observation_space=lambda t: Box(np.full(135, -np.inf, np.float32), np.full(135, np.inf, np.float32), dtype=np.float32),
-        info_keys=["task", "task_progress", "blocks_placed", "safety_violations", "episode_stats", "weather"]),
+        info_keys=["task", "task_progress", "blocks_placed", "safety_violations", "episode_stats", "weather"], vector_info=_construction_info),
     "humanoid_martial_arts": TaskSpec(
         name="humanoid_martial_arts", task_id=capi.TASK_HUMANOID_MARTIAL_ARTS, obs_dim=113, act_dim=28, max_episode_steps=6000,
         frame_skip=1, render_fps=60, bytes_per_env_step=1786, describe=_martial_desc,
         action_space=lambda t: Box(np.full(28, -1.0, np.float32), np.full(28, 1.0, np.float32), dtype=np.float32),
         # the reference declares 85 entries but returns 113: the actual length is exposed
         observation_space=lambda t: Box(np.full(113, -np.inf, np.float32), np.full(113, np.inf, np.float32), dtype=np.float32),
-        info_keys=["episode_stats", "combo_chain", "stance_stability", "current_step"]),
+        info_keys=["episode_stats", "combo_chain", "stance_stability", "current_step"], vector_info=_martial_info),
     "robotic_arm_assembly": TaskSpec(
         name="robotic_arm_assembly", task_id=capi.TASK_ROBOTIC_ARM_ASSEMBLY, obs_dim=110, act_dim=9, max_episode_steps=150000,
         frame_skip=10, render_fps=50, bytes_per_env_step=2266, describe=_arm_desc,
         action_space=lambda t: Box(np.array([-2.0] * 7 + [0.0, 0.0], np.float32), np.array([2.0] * 7 + [100.0, 50.0], np.float32), dtype=np.float32),
         observation_space=lambda t: Box(np.full(110, -np.inf, np.float32), np.full(110, np.inf, np.float32), dtype=np.float32),
-        info_keys=["step_count", "assembly_progress", "component_status", "task_phase", "held_component", "cumulative_reward", "success"]),
+        info_keys=["step_count", "assembly_progress", "component_status", "task_phase", "held_component", "cumulative_reward", "success"], vector_info=_arm_info),
 }

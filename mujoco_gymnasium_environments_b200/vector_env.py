@@ -15,17 +15,53 @@ from .spaces import batch_box
 from .tasks import TASKS, load_tables
 
 
+class LazyInfos(dict):
+    """``infos`` of a vector step.  ``final_obs`` / ``_final_obs`` are there from the start; the per-env counterparts of the
+    reference's ``info`` dict (e.g. quadruped_parkour_env/parkour_env.py:797-813: step_count, episode_reward, fall_count ...) are
+    device tensors of shape [N] built on first access from the task state -- rows of envs that finished an episode in this
+    step come from the snapshot taken before the same-step auto-reset -- so a training loop that never reads them pays nothing."""
+
+    def __init__(self, env, eager):
+        super().__init__(eager)
+        self._env = env; self._built = False
+
+    def _build(self):
+        if not self._built:
+            self._built = True
+            ti, tf, xpos = self._env.task_state(with_xpos=True)
+            for k, v in self._env.spec.vector_info(self._env.torch, ti, tf, xpos, self._env.tables).items():
+                dict.setdefault(self, k, v)
+            dict.setdefault(self, "task_ti", ti); dict.setdefault(self, "task_tf", tf)
+
+    def __missing__(self, key):
+        self._build()
+        if not dict.__contains__(self, key):
+            raise KeyError(key)
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        if dict.__contains__(self, key):
+            return True
+        self._build()
+        return dict.__contains__(self, key)
+
+    def keys(self):
+        self._build()
+        return dict.keys(self)
+
+
 class B200VectorEnv:
     metadata = {"autoreset_mode": "same_step", "render_modes": []}
 
     def __init__(self, task: str, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
-                 assets_root: Optional[str] = None, **batch_opts):
+                 assets_root: Optional[str] = None, tables=None, **batch_opts):
         import torch
         if not torch.cuda.is_available():
             raise capi.B2Error("B200VectorEnv needs a CUDA device; there is no CPU fallback")
         self.torch = torch
         self.spec = TASKS[task]
-        self.tables = load_tables(task, assets_root)
+        # tables: a ModelTables made elsewhere, e.g. from_mjmodel(mujoco.MjModel.from_xml_string(...)) where MuJoCo is importable
+        self.tables = tables if tables is not None else load_tables(task, assets_root)
         self.model = capi.DeviceModel(self.tables, device)
         self.batch = capi.Batch(self.model, self.spec.describe(self.tables), num_envs, seed, env_offset, **batch_opts)
         self.num_envs = num_envs
@@ -40,27 +76,57 @@ class B200VectorEnv:
         self._rew = torch.empty((num_envs,), dtype=f32, device=self.device)
         self._term = torch.empty((num_envs,), dtype=torch.uint8, device=self.device)
         self._trunc = torch.empty((num_envs,), dtype=torch.uint8, device=self.device)
+        self._done = torch.zeros((num_envs,), dtype=torch.bool, device=self.device)
 
     # ---- Gymnasium VectorEnv surface
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         mask = inject = None
+        if seed is not None:
+            # Env.reset(seed=...) reseeds np_random in the reference (parkour_env.py:314-322); here it replaces the device RNG seed and
+            # restarts the episode counters, so the same seed always yields the same initial states
+            self.batch.reseed(int(seed[0]) if isinstance(seed, (list, tuple)) else int(seed))
         if options:
             if options.get("reset_mask") is not None:
                 mask = self.torch.as_tensor(options["reset_mask"], device=self.device).to(self.torch.uint8).contiguous()
             if options.get("inject") is not None:
                 inject = self.torch.as_tensor(options["inject"], dtype=self.torch.float32, device=self.device).contiguous()
-        self.batch.reset(self._obs, mask, inject)
-        return self._obs, {}
+        if mask is not None and mask.numel() != self.num_envs:
+            raise ValueError(f"reset_mask: expected {self.num_envs} entries, got {mask.numel()}")
+        if inject is not None and tuple(inject.shape) != (self.num_envs, self.batch.ninj):
+            raise ValueError(f"inject: expected shape {(self.num_envs, self.batch.ninj)}, got {tuple(inject.shape)}")
+        self.batch.reset(self._obs, None if mask is None else mask.reshape(self.num_envs), inject)
+        if mask is None:
+            self._done.zero_()
+        else:
+            self._done &= ~mask.reshape(self.num_envs).bool()
+        return self._obs, LazyInfos(self, {})
 
     def step(self, actions):
         t = self.torch
         if not isinstance(actions, t.Tensor):
             actions = t.as_tensor(np.asarray(actions, np.float32))
+        if tuple(actions.shape) != (self.num_envs, self.spec.act_dim):
+            raise ValueError(f"actions: expected shape {(self.num_envs, self.spec.act_dim)}, got {tuple(actions.shape)}")
         actions = actions.to(self.device, t.float32).contiguous()
         self.batch.step(actions, self._obs, self._rew, self._term, self._trunc, self._final_obs)
         term = self._term.bool(); trunc = self._trunc.bool()
-        infos = {"final_obs": self._final_obs, "_final_obs": term | trunc}
+        self._done = term | trunc
+        infos = LazyInfos(self, {"final_obs": self._final_obs, "_final_obs": self._done})
         return self._obs, self._rew, term, trunc, infos
+
+    def task_state(self, with_xpos: bool = False):
+        """Per-env task state (ti, tf[, xpos]); rows of envs whose episode ended in the last step hold the finished episode's
+        values (snapshot taken in the kernel before the same-step auto-reset), as the reference's terminal ``info`` does."""
+        t = self.torch
+        ti, tf = self.batch.get_task_state()
+        x = self.batch.xpos() if with_xpos else None
+        if bool(self._done.any()):
+            fti, ftf, fx = self.batch.final_state()
+            d = self._done
+            ti = t.where(d[:, None], fti, ti); tf = t.where(d[:, None], ftf, tf)
+            if with_xpos:
+                x = t.where(d[:, None, None], fx, x)
+        return (ti, tf, x) if with_xpos else (ti, tf)
 
     def step_dlpack(self, actions_capsule):
         """Same as :meth:`step` for callers holding a DLPack capsule (JAX/CuPy); returns DLPack capsules."""
