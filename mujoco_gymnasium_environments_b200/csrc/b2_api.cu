@@ -37,24 +37,52 @@ struct B2Batch {
   // b2_rollout: the T launches of a rollout as one instantiated CUDA graph, cached while T and the buffers stay the same
   cudaGraphExec_t roll_exec; int roll_T; const void* roll_key[6];
   int obs_dim, act_dim, nti, ntf, ninj;
+  int num_sms;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-// grid = ceil(n_envs / E) CTAs of E teams of W warps; team t of CTA c steps env c*E + t.
+// Persistent CTAs: grid = min(#SMs, ceil(n_envs / E)) CTAs of E teams of W warps, one CTA per SM (shared-memory bound).  The
+// model tables are staged once per CTA; every team then pulls env indices from a global work queue (one atomicAdd per env)
+// until it is empty, so a team whose env is slow -- auto-reset with its settle steps, a wide-tier pass, a NaN retry -- holds
+// up nobody: its CTA-mates keep pulling work, and there is no wave tail (r01: 683 CTAs = 4.61 waves, retirement by CTA).
+// The last team to leave re-arms the queue for the next launch, so a launch is one kernel node (CUDA-graph friendly).
 // Shared memory: [model | E workspaces | mbarrier].  The task hooks are warp-level code run by warp 0 of the team.
+template <class Task, int W>
+__device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& B, const TaskParams& tp, int mode, double* epstat,
+                                            const float* inject, int team, int env);
+
 template <class Task, int W>
 __global__ void __launch_bounds__(32 * W * Task::MAX_EPB, 1)
 b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchView B, const __grid_constant__ TaskParams tp,
               int mode, double* epstat, const float* inject) {
-  const int team = threadIdx.x / (32 * W);
+  constexpr int TEAM = 32 * W;
+  const int team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
   stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints_staged), bar);
-  const int env = B.first_env + blockIdx.x * B.envs_per_block + team;
-  if (env >= B.first_env + B.n_envs) return;
-  if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) return;
+  volatile int* slot = (volatile int*)(b2_smem + B.model_floats + team * B.ws_floats + B.off.misc) + MISC_ENV;
+  for (;;) {
+    if (tl == 0) *slot = atomicAdd(B.queue, 1);
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TEAM) : "memory");
+    const int idx = *slot;
+    if (idx >= B.n_envs) break;
+    const int env = B.first_env + idx;
+    if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) continue;
+    b2_env_body<Task, W>(P, B, tp, mode, epstat, inject, team, env);
+  }
+  if (tl == 0) {      // last team out re-arms the queue
+    __threadfence();
+    const int total = (int)gridDim.x * B.envs_per_block;
+    if (atomicAdd(B.queue + 1, 1) == total - 1) { B.queue[1] = 0; __threadfence(); B.queue[0] = 0; }
+  }
+}
+
+template <class Task, int W>
+__device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& B, const TaskParams& tp, int mode, double* epstat,
+                                            const float* inject, int team, int env) {
   Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team, env);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
+  E.team_sync();      // the previous env's stores to this workspace are done
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
   unsigned long long* ctr = B.counters + (size_t)env * CTR_COUNT;
   int* s_ti = E.p_ti(); float* s_tf = E.p_tf(); float* s_act = E.p_act();
@@ -212,6 +240,7 @@ static int configure_task(B2Batch* b) {
 template <class Task>
 static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   int E = b->v.envs_per_block, grid = (b->v.n_envs + E - 1) / E;
+  if (grid > b->num_sms) grid = b->num_sms;            // persistent CTAs, one per SM; teams pull envs from the work queue
   b2_env_kernel<Task, 3><<<grid, 32 * 3 * E, b->smem, s>>>(b->dm, b->v, b->tp, mode, b->epstat, inject);
   g_launches++;
   CK(cudaGetLastError());
@@ -261,7 +290,7 @@ unsigned long long b2_launch_count(void) { return g_launches.load(); }
 int b2_phase_cycles(B2Batch* b, unsigned long long* out16) {
   if (!b || !out16) return B2_ERR_ARG;
   cudaSetDevice(b->m->device); cudaDeviceSynchronize();
-  return cudaMemcpy(out16, b->v.phase_cycles, 16 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? B2_OK : B2_ERR_CUDA;
+  return cudaMemcpy(out16, b->v.phase_cycles, 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? B2_OK : B2_ERR_CUDA;   /* 32 entries */
 }
 
 int b2_model_create(const int32_t* ints, int n_ints, const double* flts, int n_flts, int device, B2Model** out) {
@@ -392,7 +421,9 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&v.qpos, N * v.nqp * 4)); CK(cudaMalloc(&v.qvel, N * v.nvp * 4)); CK(cudaMalloc(&v.warm, N * v.nvp * 4));
   CK(cudaMalloc(&v.qfrc_applied, N * v.nvp * 4)); CK(cudaMalloc(&v.ctrl, N * v.nup * 4)); CK(cudaMalloc(&v.time, N * 4));
   CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
-  CK(cudaMalloc(&v.phase_cycles, 16 * 8)); CK(cudaMemset(v.phase_cycles, 0, 16 * 8));
+  CK(cudaMalloc(&v.phase_cycles, 32 * 8)); CK(cudaMemset(v.phase_cycles, 0, 32 * 8));
+  CK(cudaMalloc(&v.queue, 4 * 4)); CK(cudaMemset(v.queue, 0, 4 * 4));
+  CK(cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, m->device));
   CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 8)); CK(cudaMalloc(&b->d_stats, 16 * 8));
   CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));
   CK(cudaMemset(v.ctrl, 0, N * v.nup * 4)); CK(cudaMemset(v.time, 0, N * 4)); CK(cudaMemset(v.ti, 0, N * v.nti * 4));
@@ -425,7 +456,7 @@ void b2_batch_destroy(B2Batch* b) {
   if (!b) return;
   cudaSetDevice(b->m->device);
   BatchView& v = b->v;
-  cudaFree(v.wide);
+  cudaFree(v.wide); cudaFree(v.queue);
   cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
   cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.phase_cycles); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
   cudaFree(v.final_ti); cudaFree(v.final_tf); cudaFree(v.final_xpos);
@@ -505,10 +536,8 @@ int b2_rollout(B2Batch* b, int T, const float* act_dev, float* obs_dev, float* r
     if (e != cudaSuccess) { b->roll_exec = nullptr; return fail(B2_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
     b->roll_T = T; memcpy(b->roll_key, key, sizeof(key));
   }
-  if (!s) { CK(cudaStreamSynchronize(0)); }             // a NULL stream means "after everything on the legacy stream"
-  CK(cudaGraphLaunch(b->roll_exec, s ? s : b->own_stream));
+  CK(cudaGraphLaunch(b->roll_exec, s));                // launching into the legacy stream is fine; only capturing on it is not
   g_launches += (unsigned long long)T;
-  if (!s) { b->last_stream = b->own_stream; b->pending = true; }
   return B2_OK;
 }
 int b2_host_buffers(B2Batch* b, float** act, float** obs, float** rew, uint8_t** term, uint8_t** trunc) {

@@ -73,7 +73,7 @@ __host__ inline long long wide_layout(int w_con_cap, int w_row_cap, int w_arena_
   if (o) *o = t;
   return (off + 31) & ~31ll;
 }
-enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_NISL = 6, MISC_WIDE = 7, MISC_WSCR = 8, MISC_COUNT = 12 };
+enum { MISC_NCON = 0, MISC_NEFC = 1, MISC_FLAG = 2, MISC_ITERS = 3, MISC_ARENA_USED = 4, MISC_DONE = 5, MISC_NISL = 6, MISC_WIDE = 7, MISC_WSCR = 8, MISC_ENV = 9, MISC_WRING = 10, MISC_WRB = 11, MISC_COUNT = 12 };
 
 __host__ __device__ inline int r4(int n) { return (n + 3) & ~3; }
 // model tables occupy the first model_floats of shared memory (ints first, then floats), padded to 32 floats
@@ -123,6 +123,7 @@ struct BatchView {
   float* xpos_out;                                   // optional [N][nbody*3] export of the last forward pass
   float* debug_out; int debug_n;                     // optional [N][debug_n] dump of solver intermediates (bring-up / tests)
   unsigned long long* counters;                      // [N][CTR_COUNT]
+  int* queue;                                        // [0] next env of this launch, [1] teams that have left (work queue of the persistent CTAs)
   unsigned long long* phase_cycles;                  // [16] per-phase clock64 sums (only with -DB2_PHASE_TIMING)
   unsigned long long seed;
   int arena_floats, con_cap, row_cap;
@@ -178,7 +179,7 @@ struct Engine {
   int env;     // env this team steps (row of the wide workspace)
   bool wide;   // this forward pass keeps its contacts / rows / J in the wide workspace (team-uniform, refreshed from MISC_WIDE)
   static constexpr int TEAM = 32 * W;
-  static constexpr int RING = 4;      // cp.async ring stages of the wide PGS sweep
+  static constexpr int RING_MIN = 2, RING_MAX = 16;      // stages of the wide PGS sweep's bulk-copy ring (depth chosen per pass from the free arena)
 
   __device__ Engine(const DevModel& p, const BatchView& b, int team_base, int team_in_block, int env_) : P(p), B(b), wb(team_base), env(env_), wide(false) {
     tl = threadIdx.x % TEAM; lane = tl & 31; wl = tl >> 5; barid = 1 + team_in_block;
@@ -815,11 +816,13 @@ struct Engine {
       const int gavail = wd ? B.w_arena_floats - 8 : arenaFloats() - scratch - 8;     // where J goes
       int savail = arenaFloats() - 8, sbase = 0, nscr = W;                            // on-chip part of the wide tier
       if (wd && !nw) {
-        const int ringf = W * RING * wide_blkf_max();
+        // on chip: scratch columns for the B build, then every island's f and v, then the bulk-copy rings of the sweeping warps
+        // (at least RING_MIN stages each are reserved here; the depth actually used is whatever is left, below)
+        const int ringf = W * RING_MIN * (wide_blkf_max() + 4);
         int fv = 0;
         for (int k = 0; k < nisl; k++) fv += r4(p_isl_n()[k]) + 4 + r4(p_isl_nd()[k]);
         if (nscr * 32 * nv + ringf + fv > savail) nscr = 1;
-        sbase = nscr * 32 * nv + ringf; savail -= sbase;
+        sbase = nscr * 32 * nv; savail -= sbase + ringf;
       }
       int adr = 0, used = 0, sused = 0, ovf = 0, cut = 0;
       for (int k = 0; k < nisl; k++) {
@@ -865,6 +868,14 @@ struct Engine {
         p_isl_warp()[k] = best;
 #pragma unroll
         for (int q = 0; q < W; q++) if (q == best) load[q] += p_isl_n()[k] ? ((p_isl_n()[k] + 3) >> 2) + 2 : 0;
+      }
+      if (wd && !nw) {
+        int nsw = 0;
+#pragma unroll
+        for (int q = 0; q < W; q++) nsw += load[q] > 0 ? 1 : 0;
+        const int rb = sbase + sused, left = arenaFloats() - 8 - rb;
+        int depth = nsw ? left / (nsw * (wide_blkf_max() + 4)) : RING_MIN;
+        p_misc()[MISC_WRING] = max(RING_MIN, min(RING_MAX, depth)); p_misc()[MISC_WRB] = rb;
       }
       if (counters) {
         if (ovf) atomicAdd(&counters[CTR_ARENA_OVERFLOW], (unsigned long long)ovf);
@@ -1323,36 +1334,49 @@ struct Engine {
   // matrix-free.  With v = M^-1 J' f the residual of row i is J_i . v + R_i f_i + b_i and a force change d of row i moves v by
   // (M^-1 J_i') d, so a sweep needs J and B = M^-1 J' (n x nd each) instead of A (n x n): memory O(n nd), no row limit.
   // Rows are kept in blocks of four in the env's global workspace, [J rows | B rows | record] (8 ldw + 24 floats, ldw = r4(nd)),
-  // and streamed through a per-warp cp.async ring in shared memory, RING blocks deep.  Lanes own dofs: the four dots J_k . v
+  // and streamed through a per-warp ring in shared memory: one bulk async copy (cp.async.bulk, completion on an mbarrier) per
+  // block, as many stages deep as the free arena allows (L2 latency is ~3 block times, so two stages would stall).  Lanes own dofs: the four dots J_k . v
   // are reduced by one interleaved butterfly, every lane then runs the 4-row chain on the same values
   //     f_k' = max(0, c_k f_k - e_k - ainv_k (J_k . v) - sum_{j<k} (ainv_k G_kj) d_j),   G = J_blk B_blk',  ainv = 1 / (G_kk + R_k),
   // (c_k = G_kk ainv_k, e_k = b_k ainv_k: the record), and folds the four force changes into its dofs of v.
-  __device__ __forceinline__ static void cp16(float* dst_smem, const float* src) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  // one stage of the ring: an mbarrier (count 1) armed with the block's byte count, then ONE bulk copy global -> shared
+  __device__ __forceinline__ static void ring_issue(float* dst, const float* src, int bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
   }
-  __device__ __forceinline__ static void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-  template <int N> __device__ __forceinline__ static void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+  __device__ __forceinline__ static void ring_wait(uint64_t* bar, unsigned parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar); uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+  }
+  // `cnt` numbers the blocks this warp has streamed since its mbarriers were initialised: block c uses stage c % D, parity (c / D) & 1
   template <int NC>
-  __device__ __forceinline__ void wide_sweep(const float* g, int nb, int blkf, int ldw, float* ring, float* f, float* vs, float& improvement) {
+  __device__ __forceinline__ void wide_sweep(const float* g, int nb, int blkf, int ldw, float* ring, uint64_t* bars, int D, unsigned& cnt,
+                                              float* f, float* vs, float& improvement) {
     float v[NC];
 #pragma unroll
     for (int q = 0; q < NC; q++) { int c = lane + 32 * q; v[q] = c < ldw ? vs[c] : 0.f; }
-    const int nv4 = blkf >> 2;
+    const int bytes = blkf * 4; const unsigned c0 = cnt;
+    if (lane == 0) {
 #pragma unroll 1
-    for (int s = 0; s < RING - 1; s++) {
-      if (s < nb) for (int i = lane; i < nv4; i += 32) cp16(ring + s * blkf + 4 * i, g + (size_t)s * blkf + 4 * i);
-      cp_commit();
+      for (int s = 0; s < D - 1 && s < nb; s++) { const unsigned st = (c0 + s) % D; ring_issue(ring + st * blkf, g + (size_t)s * blkf, bytes, bars + st); }
     }
 #pragma unroll 1
     for (int b = 0; b < nb; b++) {
-      cp_wait<RING - 2>(); __syncwarp();
-      {
-        const int nx = b + RING - 1;
-        if (nx < nb) { float* dst = ring + (nx % RING) * blkf; const float* src = g + (size_t)nx * blkf; for (int i = lane; i < nv4; i += 32) cp16(dst + 4 * i, src + 4 * i); }
-        cp_commit();
-      }
-      const float* blk = ring + (b % RING) * blkf; const float* Bb = blk + 4 * ldw;
+      const unsigned c = c0 + b, st = c % D;
+#ifdef B2_PHASE_TIMING
+      long long tw0 = clock64();
+#endif
+      ring_wait(bars + st, (c / D) & 1u);
+#ifdef B2_PHASE_TIMING
+      if (lane == 0 && B.phase_cycles) { atomicAdd(&B.phase_cycles[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&B.phase_cycles[17], 1ull); }
+#endif
+      __syncwarp();                                  // every lane is done with the stage the next copy overwrites
+      if (lane == 0) { const int nx = b + D - 1; if (nx < nb) { const unsigned sn = (c0 + nx) % D; ring_issue(ring + sn * blkf, g + (size_t)nx * blkf, bytes, bars + sn); } }
+      const float* blk = ring + st * blkf; const float* Bb = blk + 4 * ldw;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int q = 0; q < NC; q++) {
@@ -1382,12 +1406,21 @@ struct Engine {
         if (c < ldw) v[q] += fmaf(Bb[c], d0, Bb[ldw + c] * d1) + fmaf(Bb[2 * ldw + c], d2, Bb[3 * ldw + c] * d3);
       }
     }
-    cp_wait<0>(); __syncwarp();
+    cnt = c0 + nb;
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < NC; q++) { int c = lane + 32 * q; if (c < ldw) vs[c] = v[q]; }
     __syncwarp();
   }
+#ifdef B2_PHASE_TIMING
+#define B2_WTICK(k) do { long long t_ = clock64(); if (tl == 0 && B.phase_cycles) atomicAdd(&B.phase_cycles[k], (unsigned long long)(t_ - wt0)); wt0 = t_; } while (0)
+#else
+#define B2_WTICK(k) do { } while (0)
+#endif
   __device__ void solve_pgs_wide(unsigned long long* counters) {
+#ifdef B2_PHASE_TIMING
+    long long wt0 = clock64();
+#endif
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations), nv = dim(DD_nv), nscr = p_misc()[MISC_WSCR];
     const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
     float* red = p_red();
@@ -1423,8 +1456,8 @@ struct Engine {
         }
       }
     }
-    __threadfence_block();
-    team_sync();
+    asm volatile("fence.proxy.async;" ::: "memory");      // the blocks were written through the generic proxy; the ring reads them through the async one
+    team_sync(); B2_WTICK(4);
     // f <- warm-start forces, v = B' f, cost(f) = sum_i f_i (1/2 (J_i . v + R_i f_i) + b_i); cost > 0 -> cold start
     float cost = 0.f;
     for (int k = 0; k < nisl; k++) {
@@ -1465,7 +1498,22 @@ struct Engine {
       }
     }
     sync();
-    float* ring = p_arena() + nscr * 32 * nv + wl * RING * wide_blkf_max();
+    // this warp's ring: D stages of one block each and their mbarriers, in the arena behind the islands' f / v
+    const int D = p_misc()[MISC_WRING]; int rank = 0, sweeps = 0;
+    for (int k = 0; k < nisl; k++) if (p_isl_n()[k]) { const int q = p_isl_warp()[k]; if (q == wl) sweeps = 1; }
+#pragma unroll
+    for (int q = 0; q < W; q++) { bool any = false; for (int k = 0; k < nisl; k++) any |= p_isl_n()[k] && p_isl_warp()[k] == q; if (q < wl && any) rank++; }
+    float* ring = p_arena() + p_misc()[MISC_WRB] + rank * D * (wide_blkf_max() + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + D * wide_blkf_max());
+    unsigned cnt = 0;
+    if (sweeps && lane == 0) {
+      for (int st = 0; st < D; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + st)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp(); B2_WTICK(5);
+#ifdef B2_PHASE_TIMING
+    if (tl == 0 && B.phase_cycles) { atomicAdd(&B.phase_cycles[14], (unsigned long long)D); atomicAdd(&B.phase_cycles[15], 1ull); atomicAdd(&B.phase_cycles[8], (unsigned long long)p_misc()[MISC_NEFC]); }
+#endif
     int it = 0;
     for (; it < iters; it++) {
       float improvement = 0.f;
@@ -1473,20 +1521,34 @@ struct Engine {
         const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
         const int ldw = p_isl_ldj()[k], blkf = jblk(ldw), nb = (n + 3) >> 2;
         const float* Jg = xs_J<true>(k); float* f = p_arena() + p_isl_A()[k]; float* vs = f + 4 * nb;
-        if (ldw <= 32) wide_sweep<1>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
-        else if (ldw <= 64) wide_sweep<2>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
-        else wide_sweep<4>(Jg, nb, blkf, ldw, ring, f, vs, improvement);
+        if (ldw <= 32) wide_sweep<1>(Jg, nb, blkf, ldw, ring, bars, D, cnt, f, vs, improvement);
+        else if (ldw <= 64) wide_sweep<2>(Jg, nb, blkf, ldw, ring, bars, D, cnt, f, vs, improvement);
+        else wide_sweep<4>(Jg, nb, blkf, ldw, ring, bars, D, cnt, f, vs, improvement);
       }
       if (W > 1) {
         float* slot = red + 8 + (it & 1) * 4;      // double-buffered exchange (the sweeps leave `improvement` warp-uniform)
         if (lane == 0) slot[wl] = improvement;
+#ifdef B2_PHASE_TIMING
+        long long tb0 = clock64();
+#endif
         team_sync();
+#ifdef B2_PHASE_TIMING
+        if (tl == 0 && B.phase_cycles) atomicAdd(&B.phase_cycles[18], (unsigned long long)(clock64() - tb0));
+#endif
         improvement = 0.f;
 #pragma unroll
         for (int q = 0; q < W; q++) improvement += slot[q];
       }
       if (improvement * scale < tol) { it++; break; }
     }
+    B2_WTICK(6);
+#ifdef B2_PHASE_TIMING
+    if (tl == 0 && B.phase_cycles) atomicAdd(&B.phase_cycles[7], (unsigned long long)it);
+#endif
+    if (sweeps && lane == 0) {      // the arena is re-carved every pass: retire the mbarriers before their words are reused
+      for (int st = 0; st < D; st++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bars + st)) : "memory");
+    }
+    __syncwarp();
     for (int k = 0; k < nisl; k++) {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       const int e0 = p_isl_adr()[k]; const float* f = p_arena() + p_isl_A()[k];
@@ -1497,10 +1559,10 @@ struct Engine {
     team_sync();
   }
   // pass 1 of a forward evaluation in the wide tier (cold: a few per cent of the passes; kept out of line)
-  __device__ __noinline__ void wide_pass(unsigned long long* counters) {
+  __device__ __forceinline__ void wide_pass(unsigned long long* counters) {
     if (p_misc()[MISC_NEFC] > 0) {
       fill_rows<true>();
-      __threadfence_block();
+      asm volatile("fence.proxy.async;" ::: "memory");
       team_sync();
       if (newton()) solve_newton<true>(counters);
       else solve_pgs_wide(counters);
@@ -1544,7 +1606,7 @@ struct Engine {
     }
     sync();
   }
-  template <bool WD> __device__ __noinline__ void solve_newton(unsigned long long* counters) {
+  template <bool WD> __device__ __forceinline__ void solve_newton(unsigned long long* counters) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
     const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
@@ -1867,7 +1929,7 @@ struct Engine {
               if (wl == 2) factor(h, true);
             }
           } else if (pass == 1) {
-            if (wide) wide_pass(counters);       // cold path, out of line
+            if (wide) { wide_pass(counters); B2_TICK(12); }      // cold path, out of line
             else {
               if (p_misc()[MISC_NEFC] > 0) {
                 fill_rows<false>(); B2_TICK(9);
