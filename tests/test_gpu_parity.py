@@ -146,6 +146,67 @@ def test_task_matches_live_oracle_with_full_range_actions(gpu):
     b.close()
 
 
+def test_full_range_rollout_step_by_step_with_contact_pairs(gpu):
+    """25 control steps = 250 `mj_step`s under FULL-range actions (x1.0 on every actuator, the bench's distribution: +-6400 N m on
+    the hips, joint speeds of 1e3 rad/s and more).  Such trajectories are chaotic -- a 1e-6 difference grows to O(1) within one
+    control step of ten sub-steps -- so the protocol is north_star's single-step one: six envs are driven by the task kernel,
+    and at every physics sub-step of every control step the state the GPU is in (fp32 qpos, qvel, ctrl, qacc_warmstart) is given
+    to the oracle; both take one mj_step.  Contact count, contact pairs (bit-exact, in order) and row count must agree, qacc and
+    the stepped velocity within the bounds below.  The robots go over, pile up 64-80 contacts (wide tier) and blow up to
+    |qvel| ~ 1e6 before mj_checkAcc resets them: all of it is compared, nothing may be dropped."""
+    torch = gpu["torch"]
+    from oracle import ref
+    n, T = 6, 25
+    b = gpu["capi"].Batch(gpu["model"], gpu["spec"].describe(gpu["tables"]), n, 5, 0)
+    b1 = gpu["capi"].Batch(gpu["model"], gpu["spec"].describe(gpu["tables"]), n, 5, 0)      # sub-step probe of the same states
+    obs = torch.zeros((n, 95), device="cuda"); rew = torch.zeros(n, device="cuda")
+    term = torch.zeros(n, dtype=torch.uint8, device="cuda"); trunc = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(23)
+    inj = np.zeros((n, 4), np.float32); inj[:, 0] = rng.uniform(-1.5, 1.5, n); inj[:, 1] = rng.uniform(-1, 1, n)
+    b.reset(obs, None, torch.tensor(inj, device="cuda"))
+    hi = np.asarray(gpu["spec"].action_space(gpu["tables"]).high)
+    om = ref.load_model(gpu["tables"])
+    compared = 0; worst_a = worst_v = 0.0; maxcon = 0; wild = 0
+    for s in range(T):
+        st = b.get_state()
+        a = (rng.uniform(-1, 1, (n, 16)) * hi).astype(np.float32)
+        b.step(torch.tensor(a, device="cuda"), obs, rew, term, trunc)
+        ctrl = b.get_state()["ctrl"]                                 # what apply_action wrote for this control step
+        done = (term | trunc).cpu().numpy().astype(bool)
+        b1.set_state(st["qpos"], st["qvel"], ctrl, st["qacc_warmstart"], torch.zeros(n))
+        for sub in range(10):
+            g = {k: v.cpu().numpy() for k, v in b1.get_state().items()}
+            ncon, geom, dist = b1.contacts(160)
+            dbg = b1.debug_forward()
+            b1.physics_step(1)
+            g1 = {k: v.cpu().numpy() for k, v in b1.get_state().items()}
+            for k in range(n):
+                if done[k] or not np.isfinite(g["qvel"][k]).all():
+                    continue                                        # auto-reset inside b.step: b1 has no task logic to follow it
+                d = ref.RefData(om)
+                d.qpos[:] = g["qpos"][k]; d.qvel[:] = g["qvel"][k]; d.ctrl[:] = g["ctrl"][k]; d.qacc_warmstart[:] = g["qacc_warmstart"][k]
+                ref.mj_forward(om, d)
+                nc = int(ncon[k]); maxcon = max(maxcon, nc)
+                assert nc == d.ncon and int(dbg["nefc"][k]) == d.nefc, (s, sub, k, nc, d.ncon, int(dbg["nefc"][k]), d.nefc)
+                assert np.array_equal(geom[k, :nc].cpu().numpy(), np.array([(c.geom1, c.geom2) for c in d.contact], np.int32).reshape(nc, 2))
+                vmax = float(np.max(np.abs(g["qvel"][k])))
+                ea = rel(dbg["qacc"][k].cpu().numpy(), d.qacc)
+                d.qacc_warmstart[:] = g["qacc_warmstart"][k]
+                ref.mj_step(om, d)
+                if d.nwarn:
+                    wild += 1; continue                             # mj_checkAcc reset on the oracle's side: compared through the counters below
+                ev = rel(g1["qvel"][k], d.qvel)
+                worst_a = max(worst_a, ea); worst_v = max(worst_v, ev); compared += 1
+                # sane states: the single-step bound; states already flying apart (|qvel| > 1e4 rad/s): one decade more
+                assert ea < (1e-3 if vmax < 1e4 else 1e-2) and ev < (1e-4 if vmax < 1e4 else 1e-3), (s, sub, k, vmax, ea, ev)
+    sdict = b.stats().cpu().numpy(); s1 = b1.stats().cpu().numpy()
+    print(f"full-range rollout: {compared} mj_steps compared, worst qacc {worst_a:.2e}, worst stepped qvel {worst_v:.2e}, most contacts {maxcon}, "
+          f"wide passes {sdict[10] + s1[10]:.0f}, checkAcc resets on the oracle side {wild}")
+    assert sdict[4] == 0 and sdict[5] == 0 and sdict[6] == 0 and s1[4] == 0 and s1[5] == 0 and s1[6] == 0
+    assert compared >= 1000 and maxcon > 32
+    b.close(); b1.close()
+
+
 def test_state_roundtrip_autoreset_and_determinism(gpu):
     torch = gpu["torch"]
     n = 64

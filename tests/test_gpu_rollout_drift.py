@@ -1,19 +1,23 @@
 """North_star: "the first 100 steps of a rollout must stay within a stated drift bound".  For every built task one env is
 reset with injected draws, both sides continue from the same fp32 post-reset state with the same small random actions
-(x0.02 of the action range, the scale the reference's own soccer / rescue demos use is x0.1), and the observation is
+(x0.02 of the action range; the scale the reference's own soccer / rescue demos use is x0.1), and the observation is
 compared over 100 control steps.  Stated bounds (max |obs_gpu - obs_oracle| / (1 + |obs_oracle|)): 1e-3 over the first 10
 steps, 5e-3 over all 100 (fp32 vs fp64 through an unconverged 50-iteration PGS; measured on B200: 2e-5 quadruped over 380
 `mj_step`s, 1.5e-4 dancing, 3e-4 soccer, 2e-4 rescue, 8e-6 construction (Newton), 7e-4 martial arts (Newton; the
-uncontrolled humanoid falls and terminates after ~73 steps, on both sides at the same step).  Termination flags must agree on every step.  The quadruped (10 physics sub-steps per control step) sinks onto
-its belly within ~40 control steps under these actions and then exceeds the engine's fixed row capacity (counted in
-`rows_dropped`); its window ends there and must be at least 30 control steps = 300 `mj_step`s long."""
+uncontrolled humanoid falls and terminates after ~73 steps, on both sides at the same step).  Termination flags must agree
+on every step, and nothing may be dropped anywhere in the window: the quadruped (10 physics sub-steps per control step) sinks
+onto its belly within ~40 control steps under these actions, and from there on its forward passes exceed the on-chip
+capacities and run in the wide tier -- all 100 control steps = 1000 `mj_step`s are compared.  The arm (mounted through its
+table and thrown around at > 10 rad/s after every reset) is chaotic from the first step: its stated bounds are
+2e-2 over 10 control steps (100 `mj_step`s) and 0.5 over 100 (measured 1.3e-2 / 0.23), i.e. the 100-step figure only says that both
+sides stay on the same branch of the pickup state machine, not that they agree to a tolerance."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 CASES = [("quadruped_parkour", 1e-3, 5e-3), ("humanoid_dancing", 1e-3, 5e-3), ("humanoid_soccer", 1e-3, 5e-3), ("bipedal_rescue", 1e-3, 5e-3),
-         ("humanoid_construction", 1e-3, 5e-3), ("humanoid_martial_arts", 1e-3, 5e-3)]
+         ("humanoid_construction", 1e-3, 5e-3), ("humanoid_martial_arts", 1e-3, 5e-3), ("robotic_arm_assembly", 2e-2, 5e-1)]
 
 
 def _draws(task, rng):
@@ -27,6 +31,8 @@ def _draws(task, rng):
         return np.array([0, 2.0, 0.1, 20.0], np.float32)        # stack_blocks: no scripted termination inside the window
     if task == "humanoid_martial_arts":
         return np.array([0.3, -0.2], np.float32)
+    if task == "robotic_arm_assembly":
+        return np.zeros(1, np.float32)
     x = np.zeros(12, np.float32); x[:2] = [1.5, -2.5]; x[2:] = rng.uniform(-1, 1, 10); return x
 
 
@@ -37,6 +43,8 @@ def _ref_reset(task, env, inj):
         return env.reset(sequence=[(int(inj[2 * k]), float(inj[2 * k + 1])) for k in range(20)])
     if task in ("humanoid_construction", "humanoid_martial_arts"):
         return env.reset(draws=tuple(float(v) for v in inj))
+    if task == "robotic_arm_assembly":
+        return env.reset()
     return env.reset(draws=[float(v) for v in inj])
 
 
@@ -65,8 +73,7 @@ def test_100_step_rollout_drift(task, tol10, tol100):
         o = (infos["final_obs"][0] if (bool(term[0]) or bool(trunc[0])) else obs[0]).cpu().numpy()     # same-step auto-reset
         err = float(np.max(np.abs(o - ro) / (1.0 + np.abs(ro))))
         stats = env.episode_stats()
-        if stats["contacts_dropped"] or stats["rows_dropped"]:
-            break                                  # beyond the fixed capacities: the comparison window ends here
+        assert stats["contacts_dropped"] == 0 and stats["rows_dropped"] == 0 and stats["arena_overflows"] == 0, (task, s, stats)
         if s < 10:
             worst10 = max(worst10, err)
         worst100 = max(worst100, err)
@@ -75,8 +82,8 @@ def test_100_step_rollout_drift(task, tol10, tol100):
         if rt or rtr:
             ended = True
             break
-    print(f"{task}: drift over 10 steps {worst10:.2e}, over {nvalid} steps {worst100:.2e}")
+    print(f"{task}: drift over 10 steps {worst10:.2e}, over {nvalid} steps {worst100:.2e}; wide-tier passes {stats['wide_passes']:.0f}")
     assert worst10 < tol10 and worst100 < tol100
     # the martial-arts humanoid has no controller and falls (terminates, on both sides at the same step) inside the window
-    assert nvalid >= (30 if task == "quadruped_parkour" else 100) or (ended and task == "humanoid_martial_arts" and nvalid >= 30)
+    assert nvalid >= 100 or (ended and task == "humanoid_martial_arts" and nvalid >= 30)
     env.close()
