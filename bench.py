@@ -241,7 +241,7 @@ def run_task(task, N, K, warmup, preroll, action_scale, rank, world, local, peak
     sharding.all_reduce_stats(dstat)
     st = sharding.stats_dict(dstat.cpu().numpy())
     out["episode_stats"] = {k: st[k] for k in ("episodes", "mean_return", "mean_length", "nan_resets", "contacts_dropped", "rows_dropped",
-                                               "arena_overflows", "solver_iters", "substeps", "wide_passes")}
+                                               "arena_overflows", "solver_iters", "substeps", "wide_passes", "wide_passes_rows")}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = spec.bytes_per_env_step * N / (kern_ms * 1e-3) / 1e9
     out["roofline"] = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

@@ -128,7 +128,8 @@ int b2_debug_forward(B2Batch* b, float* out_dev, int n_per_env, void* stream);
 
 /* Episode statistics and engine counters summed over this shard into out_dev[16] (fp64), ready for an NCCL
  * all-reduce: [episodes, return_sum, length_sum, nan_resets, contacts_dropped, rows_dropped, arena_overflows,
- * solver_iters, substeps, newton_iteration_caps, wide_passes (forward passes run in the wide tier), 0...]. */
+ * solver_iters, substeps, newton_iteration_caps, wide_passes (forward passes run in the wide tier), wide_passes_rows (of those: chosen because of rows /
+ * arena space rather than the contact count), 0...]. */
 int b2_stats(B2Batch* b, double* out_dev16, void* stream);
 
 /* kernels launched by this library since load (the bench's gpu_launches claim) */

@@ -86,19 +86,27 @@ __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& 
   const int nq = P.dim[DD_nq], nv = P.dim[DD_nv], nu = P.dim[DD_nu];
   unsigned long long* ctr = B.counters + (size_t)env * CTR_COUNT;
   int* s_ti = E.p_ti(); float* s_tf = E.p_tf(); float* s_act = E.p_act();
-  // ---- load the env's state rows (coalesced: consecutive threads read consecutive floats of one row)
+  // ---- load the env's state rows: 128-bit accesses, consecutive threads on consecutive 16-byte words of one row (rows are padded
+  // to 16 bytes in HBM and in the workspace, so the padding words simply travel along)
   {
-    const float* gq = B.qpos + (size_t)env * B.nqp; const float* gv = B.qvel + (size_t)env * B.nvp;
-    const float* gw = B.warm + (size_t)env * B.nvp; const float* gc = B.ctrl + (size_t)env * B.nup;
-    const float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = tl; i < nq; i += TEAM) E.p_qpos()[i] = gq[i];
-    for (int i = tl; i < nv; i += TEAM) { E.p_qvel()[i] = gv[i]; E.p_warm()[i] = gw[i]; E.p_qapp()[i] = ga[i]; }
-    for (int i = tl; i < nu; i += TEAM) E.p_ctrl()[i] = gc[i];
+    auto ld4 = [&](float* dst, const float* src, int nwords) {
+      const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int i = tl; i < (nwords >> 2); i += TEAM) d4[i] = s4[i];
+    };
+    ld4(E.p_qpos(), B.qpos + (size_t)env * B.nqp, B.nqp);
+    ld4(E.p_qvel(), B.qvel + (size_t)env * B.nvp, B.nvp); ld4(E.p_warm(), B.warm + (size_t)env * B.nvp, B.nvp);
+    ld4(E.p_qapp(), B.qfrc_applied + (size_t)env * B.nvp, B.nvp);
+    if (nu > 0) ld4(E.p_ctrl(), B.ctrl + (size_t)env * B.nup, B.nup);
     if (tl < 8) E.p_xfrc()[tl] = 0.f;
     if (tl == 0) { *E.p_time() = B.time[env]; E.p_misc()[MISC_NCON] = 0; E.p_misc()[MISC_NEFC] = 0; E.p_misc()[MISC_FLAG] = 0; E.p_misc()[MISC_DONE] = 0; E.p_misc()[MISC_WIDE] = 0; }
     if (!Task::DYN_ISLANDS && w0) E.static_islands();
-    for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
-    for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
+    if (Task::NTI % 4 == 0 && Task::NTF % 4 == 0) {
+      if (Task::NTI) ld4(reinterpret_cast<float*>(s_ti), reinterpret_cast<const float*>(B.ti + (size_t)env * B.nti), Task::NTI);
+      if (Task::NTF) ld4(s_tf, B.tf + (size_t)env * B.ntf, Task::NTF);
+    } else {
+      for (int i = tl; i < Task::NTI; i += TEAM) s_ti[i] = B.ti[(size_t)env * B.nti + i];
+      for (int i = tl; i < Task::NTF; i += TEAM) s_tf[i] = B.tf[(size_t)env * B.ntf + i];
+    }
   }
   E.team_sync();
 
@@ -179,21 +187,28 @@ __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& 
     k += 4;
     put(E.x_row_f(), B.row_cap); put(E.x_row_b(), B.row_cap); put(E.x_row_R(), B.row_cap); put(E.x_row_res(), B.row_cap);
   }
-  // ---- store state
+  // ---- store state (128-bit, like the load)
   if (mode == MODE_FORWARD && B.forward_saves_warm && !B.warm_once) {
     float* gw = B.warm + (size_t)env * B.nvp;
     for (int i = tl; i < nv; i += TEAM) gw[i] = E.p_warm()[i];
   }
   if (mode != MODE_FORWARD) {
-    float* gq = B.qpos + (size_t)env * B.nqp; float* gv = B.qvel + (size_t)env * B.nvp;
-    float* gw = B.warm + (size_t)env * B.nvp; float* gc = B.ctrl + (size_t)env * B.nup;
-    float* ga = B.qfrc_applied + (size_t)env * B.nvp;
-    for (int i = tl; i < nq; i += TEAM) gq[i] = E.p_qpos()[i];
-    for (int i = tl; i < nv; i += TEAM) { gv[i] = E.p_qvel()[i]; gw[i] = E.p_warm()[i]; ga[i] = E.p_qapp()[i]; }
-    for (int i = tl; i < nu; i += TEAM) gc[i] = E.p_ctrl()[i];
+    auto st4 = [&](float* dst, const float* src, int nwords) {
+      const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int i = tl; i < (nwords >> 2); i += TEAM) d4[i] = s4[i];
+    };
+    st4(B.qpos + (size_t)env * B.nqp, E.p_qpos(), B.nqp);
+    st4(B.qvel + (size_t)env * B.nvp, E.p_qvel(), B.nvp); st4(B.warm + (size_t)env * B.nvp, E.p_warm(), B.nvp);
+    st4(B.qfrc_applied + (size_t)env * B.nvp, E.p_qapp(), B.nvp);
+    if (nu > 0) st4(B.ctrl + (size_t)env * B.nup, E.p_ctrl(), B.nup);
     if (tl == 0) B.time[env] = *E.p_time();
-    for (int i = tl; i < Task::NTI; i += TEAM) B.ti[(size_t)env * B.nti + i] = s_ti[i];
-    for (int i = tl; i < Task::NTF; i += TEAM) B.tf[(size_t)env * B.ntf + i] = s_tf[i];
+    if (Task::NTI % 4 == 0 && Task::NTF % 4 == 0) {
+      if (Task::NTI) st4(reinterpret_cast<float*>(B.ti + (size_t)env * B.nti), reinterpret_cast<const float*>(s_ti), Task::NTI);
+      if (Task::NTF) st4(B.tf + (size_t)env * B.ntf, s_tf, Task::NTF);
+    } else {
+      for (int i = tl; i < Task::NTI; i += TEAM) B.ti[(size_t)env * B.nti + i] = s_ti[i];
+      for (int i = tl; i < Task::NTF; i += TEAM) B.tf[(size_t)env * B.ntf + i] = s_tf[i];
+    }
   }
 }
 
@@ -217,14 +232,14 @@ __global__ void b2_stats_kernel(const unsigned long long* counters, const double
   __shared__ double acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
   __syncthreads();
-  double loc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double loc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     loc[0] += epstat[4 * e]; loc[1] += epstat[4 * e + 1]; loc[2] += epstat[4 * e + 2];
     const unsigned long long* c = counters + (size_t)e * CTR_COUNT;
     loc[3] += (double)c[CTR_NAN_RESET]; loc[4] += (double)c[CTR_CON_DROPPED]; loc[5] += (double)c[CTR_ROW_DROPPED];
-    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS]; loc[9] += (double)c[CTR_ARENA_SPILL]; loc[10] += (double)c[CTR_WIDE];
+    loc[6] += (double)c[CTR_ARENA_OVERFLOW]; loc[7] += (double)c[CTR_SOLVER_ITERS]; loc[8] += (double)c[CTR_SUBSTEPS]; loc[9] += (double)c[CTR_ARENA_SPILL]; loc[10] += (double)c[CTR_WIDE]; loc[11] += (double)c[CTR_WIDE_ROWS];
   }
-  for (int k = 0; k < 11; k++) atomicAdd(&acc[k], loc[k]);
+  for (int k = 0; k < 12; k++) atomicAdd(&acc[k], loc[k]);
   __syncthreads();
   if (threadIdx.x < 16) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
@@ -234,7 +249,10 @@ __global__ void b2_stats_kernel(const unsigned long long* counters, const double
 // device), never on the launch path, so that b2_step can be captured into a CUDA graph.
 template <class Task>
 static int configure_task(B2Batch* b) {
-  CK(cudaFuncSetAttribute(b2_env_kernel<Task, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+  // the attribute belongs to the function (per device), not to the batch: always opt in to the full 227 KB, so that a later,
+  // smaller batch of the same task cannot lower the limit under an earlier one
+  (void)b;
+  CK(cudaFuncSetAttribute(b2_env_kernel<Task, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return B2_OK;
 }
 template <class Task>
@@ -407,13 +425,13 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
     const bool pgs = dim[DD_solver] == 0; const int nvw = (dim[DD_maxspan] + 3) & ~3;
     bool on = !(opts && opts->disable_wide) && dim[DD_npair] > 0 && !(pgs && nvw > 128);
     // the on-chip part of the wide tier must fit the arena: one scratch set + the rings (PGS) / the largest island's H and vectors (Newton)
-    int fixed = pgs ? 32 * dim[DD_nv] + 3 * 4 * (8 * nvw + 24) + 64 : 0;
+    int fixed = pgs ? 32 * dim[DD_nv] + 3 * 3 * (8 * nvw + B2_WREC + 4) + 64 : 0;
     if (fixed + 256 > v.arena_floats) on = false;
     if (on) {
       v.w_con_cap = dim[DD_maxraw] < 256 ? dim[DD_maxraw] : 256; if (v.w_con_cap < v.con_cap) v.w_con_cap = v.con_cap;
       int rows = (task_c6 ? 10 : 4) * v.w_con_cap + 2 * dim[DD_nlim]; if (rows > 1024) rows = 1024; if (rows < v.row_cap) rows = v.row_cap;
       v.w_row_cap = r4(rows);
-      v.w_arena_floats = pgs ? (v.w_row_cap / 4 + B2_MAX_ISLANDS) * (8 * nvw + 24) + 16 : r4(v.w_row_cap * ((dim[DD_maxspan] | 1) + 1)) + 16 * B2_MAX_ISLANDS;
+      v.w_arena_floats = pgs ? (v.w_row_cap / 4 + B2_MAX_ISLANDS) * (8 * nvw + B2_WREC) + 16 : r4(v.w_row_cap * ((dim[DD_maxspan] | 1) + 1)) + 16 * B2_MAX_ISLANDS;
       v.wide_stride = wide_layout(v.w_con_cap, v.w_row_cap, v.w_arena_floats, &v.woff);
       CK(cudaMalloc(&v.wide, N * (size_t)v.wide_stride * 4));
     }

@@ -31,6 +31,7 @@ namespace b2 {
 #define B2_CON_STRIDE 16   // floats per contact record
 #define B2_ISLAND_ROWS 128  // rows per island: each lane of the sweeping warp owns 4 consecutive rows in registers
 #define B2_FULL 0xffffffffu
+#define B2_WREC 40          // floats of a wide PGS block's record: 24 (chain coefficients) + 16 (look-ahead tile)
 
 struct DevModel {
   const int* ints; const float* flts;
@@ -43,7 +44,7 @@ struct DevModel {
 };
 
 enum { CTR_NAN_RESET = 0, CTR_CON_DROPPED = 1, CTR_ROW_DROPPED = 2, CTR_ARENA_OVERFLOW = 3, CTR_EPISODES = 4,
-       CTR_SOLVER_ITERS = 5, CTR_SUBSTEPS = 6, CTR_ARENA_SPILL = 7, CTR_WIDE = 8, CTR_COUNT = 10 };
+       CTR_SOLVER_ITERS = 5, CTR_SUBSTEPS = 6, CTR_ARENA_SPILL = 7, CTR_WIDE = 8, CTR_WIDE_ROWS = 9, CTR_COUNT = 10 };
 
 // -------------------------------------------------------------------------------------------- workspace (per warp)
 // All per-env intermediates live in the warp's slice of dynamic shared memory.  The slice is addressed as
@@ -179,7 +180,7 @@ struct Engine {
   int env;     // env this team steps (row of the wide workspace)
   bool wide;   // this forward pass keeps its contacts / rows / J in the wide workspace (team-uniform, refreshed from MISC_WIDE)
   static constexpr int TEAM = 32 * W;
-  static constexpr int RING_MIN = 2, RING_MAX = 16;      // stages of the wide PGS sweep's bulk-copy ring (depth chosen per pass from the free arena)
+  static constexpr int RING_MIN = 3, RING_MAX = 16;      // stages of the wide PGS sweep's bulk-copy ring (depth chosen per pass from the free arena)
 
   __device__ Engine(const DevModel& p, const BatchView& b, int team_base, int team_in_block, int env_) : P(p), B(b), wb(team_base), env(env_), wide(false) {
     tl = threadIdx.x % TEAM; lane = tl & 31; wl = tl >> 5; barid = 1 + team_in_block;
@@ -218,7 +219,7 @@ struct Engine {
   __device__ __forceinline__ void refresh_wide() { wide = p_misc()[MISC_WIDE] != 0; }
   // J of island k: fast tier / Newton: plain rows (blk = 4 ldj, row i at i * ldj); wide PGS: blocks of four rows
   // [J rows | B = M^-1 J' rows | record], ldj = r4(nd), so one aligned copy brings everything a 4-row sweep step needs
-  __device__ __forceinline__ int jblk(int ldj) const { return (wide && !newton()) ? 8 * ldj + 24 : 4 * ldj; }
+  __device__ __forceinline__ int jblk(int ldj) const { return (wide && !newton()) ? 8 * ldj + B2_WREC : 4 * ldj; }
   __device__ __forceinline__ float* x_J(int k) const { return (wide ? wbase() + B.woff.arena : p_arena()) + p_isl_J()[k]; }
   template <bool WD> __device__ __forceinline__ float* xs_J(int k) const { return (WD ? wbase() + B.woff.arena : p_arena()) + p_isl_J()[k]; }
   __device__ __forceinline__ static int jrow(int i, int blk, int ldj) { return (i >> 2) * blk + (i & 3) * ldj; }
@@ -745,7 +746,7 @@ struct Engine {
   //   wide  contact records, row arrays and J live in the env's global workspace (B.wide); PGS sweeps matrix-free over
   //         [J | M^-1 J' | record] blocks streamed through a cp.async ring, Newton keeps H on chip and reads J from global.
   // Only what exceeds the wide capacities as well is cut from an island's tail (whole pyramids, last contacts first) and counted.
-  __device__ __forceinline__ int wide_blkf_max() const { return 8 * r4(dim(DD_maxspan)) + 24; }
+  __device__ __forceinline__ int wide_blkf_max() const { return 8 * r4(dim(DD_maxspan)) + B2_WREC; }
   __device__ void make_rows(unsigned long long* counters) {
     const int* limj = I(DI_lim_jnt); const int* jq = I(DI_jnt_qposadr); const int* jd = I(DI_jnt_dofadr);
     const int* dtree = I(DI_dof_tree);
@@ -810,7 +811,7 @@ struct Engine {
           adr += n; used += r4(n * ldj) + (nw ? newton_floats(n, ndk) : a_floats(n));
         }
         if (adr > B.row_cap || used > arenaFloats() - scratch - 8) ok = false;
-        if (!ok) { wd = true; if (counters) atomicAdd(&counters[CTR_WIDE], 1ull); }
+        if (!ok) { wd = true; if (counters) { atomicAdd(&counters[CTR_WIDE], 1ull); atomicAdd(&counters[CTR_WIDE_ROWS], 1ull); } }
       }
       const int rcap = wd ? B.w_row_cap : B.row_cap;
       const int gavail = wd ? B.w_arena_floats - 8 : arenaFloats() - scratch - 8;     // where J goes
@@ -829,7 +830,7 @@ struct Engine {
         const int n0 = p_isl_n()[k], ndk = p_isl_nd()[k], nl = p_isl_nl()[k];
         const int maxrows = (wd || nw) ? rcap : B2_ISLAND_ROWS;       // the 128-row island limit is the fast PGS register layout's
         const int ldj = (wd && !nw) ? r4(ndk) : (ndk | 1);
-        auto needJ = [&](int n) { return (wd && !nw) ? ((n + 3) >> 2) * (8 * ldj + 24) : (wd ? r4(n * ldj) + r4(n) : r4(n * ldj)); };
+        auto needJ = [&](int n) { return (wd && !nw) ? ((n + 3) >> 2) * (8 * ldj + B2_WREC) : (wd ? r4(n * ldj) + r4(n) : r4(n * ldj)); };
         auto needS = [&](int n) { return !wd ? (nw ? newton_floats(n, ndk) : a_floats(n)) : (nw ? newton_floats(0, ndk) : r4(n) + 4 + r4(ndk)); };
         auto fits = [&](int n) { return wd ? (used + needJ(n) <= gavail && sused + needS(n) <= savail) : (used + needJ(n) + needS(n) <= gavail); };
         int n = min(n0, maxrows);
@@ -1331,7 +1332,7 @@ struct Engine {
   // ---- wide PGS: the same scalar row updates as solve_pgs (mj_solPGS's order within each island, islands decoupled), but
   // matrix-free.  With v = M^-1 J' f the residual of row i is J_i . v + R_i f_i + b_i and a force change d of row i moves v by
   // (M^-1 J_i') d, so a sweep needs J and B = M^-1 J' (n x nd each) instead of A (n x n): memory O(n nd), no row limit.
-  // Rows are kept in blocks of four in the env's global workspace, [J rows | B rows | record] (8 ldw + 24 floats, ldw = r4(nd)),
+  // Rows are kept in blocks of four in the env's global workspace, [J rows | B rows | record] (8 ldw + 40 floats, ldw = r4(nd)),
   // and streamed through a per-warp ring in shared memory: one bulk async copy (cp.async.bulk, completion on an mbarrier) per
   // block, as many stages deep as the free arena allows (L2 latency is ~3 block times, so two stages would stall).  Lanes own dofs: the four dots J_k . v
   // are reduced by one interleaved butterfly, every lane then runs the 4-row chain on the same values
@@ -1350,45 +1351,63 @@ struct Engine {
                    : "=r"(done) : "r"(b), "r"(parity) : "memory");
     }
   }
-  // `cnt` numbers the blocks this warp has streamed since its mbarriers were initialised: block c uses stage c % D, parity (c / D) & 1
+  // `cnt` numbers the blocks this warp has streamed since its mbarriers were initialised: block c uses stage c % D, parity (c / D) & 1.
+  // One block of look-ahead takes the warp reduction off the critical path: while the chain of block b runs, the dots of block
+  // b + 1 are taken against the v that lacks block b's update, and corrected afterwards with the 4x4 tile
+  // T_b = J_{b+1} B_b' from the record (s_{b+1} = J_{b+1} v_old + T_b d_b), which is the same number up to rounding.
+  template <int NC>
+  __device__ __forceinline__ void wide_dots(const float* blk, int ldw, const float (&v)[NC], float& s0, float& s1, float& s2, float& s3) const {
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < NC; q++) {
+      int c = lane + 32 * q;
+      if (c < ldw) { float vq = v[q]; s0 = fmaf(blk[c], vq, s0); s1 = fmaf(blk[ldw + c], vq, s1); s2 = fmaf(blk[2 * ldw + c], vq, s2); s3 = fmaf(blk[3 * ldw + c], vq, s3); }
+    }
+  }
+  __device__ __forceinline__ static void wide_reduce(float& s0, float& s1, float& s2, float& s3) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s0 += __shfl_xor_sync(B2_FULL, s0, o); s1 += __shfl_xor_sync(B2_FULL, s1, o);
+      s2 += __shfl_xor_sync(B2_FULL, s2, o); s3 += __shfl_xor_sync(B2_FULL, s3, o);
+    }
+  }
   template <int NC>
   __device__ __forceinline__ void wide_sweep(const float* g, int nb, int blkf, int ldw, float* ring, uint64_t* bars, int D, unsigned& cnt,
                                               float* f, float* vs, float& improvement) {
     float v[NC];
 #pragma unroll
     for (int q = 0; q < NC; q++) { int c = lane + 32 * q; v[q] = c < ldw ? vs[c] : 0.f; }
-    const int bytes = blkf * 4; const unsigned c0 = cnt;
+    const int bytes = blkf * 4;
+    // stage / parity of the current block, of the next one, and the stage the next copy goes to: all advanced incrementally
+    // (cnt keeps (stage, parity) packed as stage | parity << 8 across sweeps, so no division by the runtime depth D is needed)
+    unsigned st = cnt & 0xffu, par = cnt >> 8;
+    auto adv = [D](unsigned& s_, unsigned& p_) { if (++s_ == (unsigned)D) { s_ = 0; p_ ^= 1u; } };
+    unsigned si = st, pi = par;
     if (lane == 0) {
 #pragma unroll 1
-      for (int s = 0; s < D - 1 && s < nb; s++) { const unsigned st = (c0 + s) % D; ring_issue(ring + st * blkf, g + (size_t)s * blkf, bytes, bars + st); }
+      for (int s = 0; s < D - 1 && s < nb; s++) { ring_issue(ring + si * blkf, g + (size_t)s * blkf, bytes, bars + si); adv(si, pi); }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < D - 1 && s < nb; s++) adv(si, pi);
     }
+    ring_wait(bars + st, par);
+    float s0, s1, s2, s3;
+    wide_dots<NC>(ring + st * blkf, ldw, v, s0, s1, s2, s3); wide_reduce(s0, s1, s2, s3);
+    unsigned stn = st, parn = par;
 #pragma unroll 1
     for (int b = 0; b < nb; b++) {
-      const unsigned c = c0 + b, st = c % D;
-#ifdef B2_PHASE_TIMING
-      long long tw0 = clock64();
-#endif
-      ring_wait(bars + st, (c / D) & 1u);
-#ifdef B2_PHASE_TIMING
-      if (lane == 0 && B.phase_cycles) { atomicAdd(&B.phase_cycles[16], (unsigned long long)(clock64() - tw0)); atomicAdd(&B.phase_cycles[17], 1ull); }
-#endif
+      if (b + 1 < nb) adv(stn, parn);
+      ring_wait(bars + stn, parn);                   // the next block's J rows feed the look-ahead dots
       __syncwarp();                                  // every lane is done with the stage the next copy overwrites
-      if (lane == 0) { const int nx = b + D - 1; if (nx < nb) { const unsigned sn = (c0 + nx) % D; ring_issue(ring + sn * blkf, g + (size_t)nx * blkf, bytes, bars + sn); } }
+      if (b + D - 1 < nb) { if (lane == 0) ring_issue(ring + si * blkf, g + (size_t)(b + D - 1) * blkf, bytes, bars + si); adv(si, pi); }
       const float* blk = ring + st * blkf; const float* Bb = blk + 4 * ldw;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int q = 0; q < NC; q++) {
-        int c = lane + 32 * q;
-        if (c < ldw) { float vq = v[q]; s0 = fmaf(blk[c], vq, s0); s1 = fmaf(blk[ldw + c], vq, s1); s2 = fmaf(blk[2 * ldw + c], vq, s2); s3 = fmaf(blk[3 * ldw + c], vq, s3); }
-      }
+      float p0, p1, p2, p3;
+      wide_dots<NC>(ring + stn * blkf, ldw, v, p0, p1, p2, p3);
       const float4* rec = reinterpret_cast<const float4*>(blk + 8 * ldw);
       const float4 G0 = rec[0], G1 = rec[1], CC = rec[2], EE = rec[3], AI = rec[4], AD = rec[5];
+      const float4 T0 = rec[6], T1 = rec[7], T2 = rec[8], T3 = rec[9];
       const float4 fo = *reinterpret_cast<const float4*>(f + 4 * b);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        s0 += __shfl_xor_sync(B2_FULL, s0, o); s1 += __shfl_xor_sync(B2_FULL, s1, o);
-        s2 += __shfl_xor_sync(B2_FULL, s2, o); s3 += __shfl_xor_sync(B2_FULL, s3, o);
-      }
+      wide_reduce(p0, p1, p2, p3);                   // independent of the chain below: the two interleave
       const float h0 = fmaf(-AI.x, s0, fmaf(CC.x, fo.x, -EE.x)); const float n0 = fmaxf(h0, 0.f), d0 = n0 - fo.x;
       const float h1 = fmaf(-G0.x, d0, fmaf(-AI.y, s1, fmaf(CC.y, fo.y, -EE.y))); const float n1 = fmaxf(h1, 0.f), d1 = n1 - fo.y;
       const float h2 = fmaf(-G0.z, d1, fmaf(-G0.y, d0, fmaf(-AI.z, s2, fmaf(CC.z, fo.z, -EE.z)))); const float n2 = fmaxf(h2, 0.f), d2 = n2 - fo.z;
@@ -1403,8 +1422,14 @@ struct Engine {
         int c = lane + 32 * q;
         if (c < ldw) v[q] += fmaf(Bb[c], d0, Bb[ldw + c] * d1) + fmaf(Bb[2 * ldw + c], d2, Bb[3 * ldw + c] * d3);
       }
+      s0 = fmaf(T0.w, d3, fmaf(T0.z, d2, fmaf(T0.y, d1, fmaf(T0.x, d0, p0))));
+      s1 = fmaf(T1.w, d3, fmaf(T1.z, d2, fmaf(T1.y, d1, fmaf(T1.x, d0, p1))));
+      s2 = fmaf(T2.w, d3, fmaf(T2.z, d2, fmaf(T2.y, d1, fmaf(T2.x, d0, p2))));
+      s3 = fmaf(T3.w, d3, fmaf(T3.z, d2, fmaf(T3.y, d1, fmaf(T3.x, d0, p3))));
+      st = stn; par = parn;
     }
-    cnt = c0 + nb;
+    // the next sweep of this warp starts at the stage after the last block's
+    adv(st, par); cnt = st | (par << 8);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < NC; q++) { int c = lane + 32 * q; if (c < ldw) vs[c] = v[q]; }
@@ -1449,6 +1474,14 @@ struct Engine {
             if (q == 1) rec[0] = ainv * G[0];
             if (q == 2) { rec[1] = ainv * G[0]; rec[2] = ainv * G[1]; }
             if (q == 3) { rec[3] = ainv * G[0]; rec[4] = ainv * G[1]; rec[5] = ainv * G[2]; }
+            if ((j >> 2) + 1 < ((n + 3) >> 2)) {          // T[u][q] = J_{4(b+1)+u} . B_j, rows past n are zero
+              const float* nxt = blkp + blk; float T[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int c = 0; c < nd; c++) {
+                const float xc = x[32 * cols.dof(c)];
+                T[0] = fmaf(nxt[c], xc, T[0]); T[1] = fmaf(nxt[ldj + c], xc, T[1]); T[2] = fmaf(nxt[2 * ldj + c], xc, T[2]); T[3] = fmaf(nxt[3 * ldj + c], xc, T[3]);
+              }
+              rec[24 + q] = T[0]; rec[28 + q] = T[1]; rec[32 + q] = T[2]; rec[36 + q] = T[3];
+            }
           }
           sync();
         }
@@ -1574,6 +1607,9 @@ struct Engine {
   // accelerations with the exact Hessian H = M + J' diag(D active) J (dense Cholesky in shared memory, nd <= 64) and an
   // exact line search on the piecewise-quadratic cost (safeguarded Newton on its derivative).  The optimum is unique, so
   // parity with the fp64 oracle is on the converged solution, not on the iteration path.  Leaves efc_force in row_f.
+#ifndef B2_NEWTON_SPARSE128
+#define B2_NEWTON_SPARSE128 0   // sparse Hessian build for islands of 65-128 dofs: measured no gain on construction (r02), kept as a switch
+#endif
 #ifndef B2_NEWTON_RTOL
 #define B2_NEWTON_RTOL 1e-5f
 #endif
@@ -1666,10 +1702,12 @@ struct Engine {
         // H = M + J' diag(D active) J, lower triangle, then symmetric diagonal scaling H <- S H S with S = diag(H_ii^-1/2):
         // joint inertias span orders of magnitude (finger hinges vs the crane), which fp32 Cholesky does not survive
         // unscaled; the scaled matrix has a unit diagonal
-        if (nd >= 16 && nd <= 64) {
+        if (nd >= 16 && nd <= 128 && (nd <= 64 || B2_NEWTON_SPARSE128)) {
           // J rows are sparse (a contact touches the dof chains of its two bodies only): per group of rows that belong
           // to one contact / one limit, list the columns any active row touches and accumulate only their pairs (pays
-          // from ~16 dofs; a free body's 6-dof island has dense rows and takes the plain loop below)
+          // from ~16 dofs; a free body's 6-dof island has dense rows and takes the plain loop below).  Up to 128 columns:
+          // construction's humanoid standing in the materials is one island of 60-99 dofs, where the plain loop costs
+          // nd^2 n / 64 multiply-adds per lane
           for (int q = lane; q < nh; q += 32) H[q] = 0.f;
           sync();
           const int* rinfo = xs_row_info<WD>() + e0; int* clist = reinterpret_cast<int*>(y);
@@ -1680,15 +1718,21 @@ struct Engine {
             unsigned act = 0;
             for (int r = 0; r < g; r++) if (jar[i0 + r] < 0.f) act |= 1u << r;
             if (act) {
-              bool nz0 = false, nz1 = false;
+              bool nz[4] = {false, false, false, false};
               for (int r = 0; r < g; r++) if ((act >> r) & 1) {
                 const float* Jr = J + (i0 + r) * ldj;
-                nz0 |= lane < nd && Jr[lane] != 0.f; nz1 |= lane + 32 < nd && Jr[lane + 32] != 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; u++) nz[u] |= lane + 32 * u < nd && Jr[lane + 32 * u] != 0.f;
               }
-              const unsigned m0 = __ballot_sync(B2_FULL, nz0), m1 = __ballot_sync(B2_FULL, nz1);
-              const int k0 = __popc(m0), kk = k0 + __popc(m1);
-              if (nz0) clist[__popc(m0 & lt)] = lane;
-              if (nz1) clist[k0 + __popc(m1 & lt)] = lane + 32;
+              int kk = 0;
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                if (32 * u < nd) {
+                  const unsigned m = __ballot_sync(B2_FULL, nz[u]);
+                  if (nz[u]) clist[kk + __popc(m & lt)] = lane + 32 * u;
+                  kk += __popc(m);
+                }
+              }
               sync();
               for (int q = lane; q < kk * (kk + 1) / 2; q += 32) {
                 int a = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);

@@ -9,7 +9,7 @@ from __future__ import annotations
 from typing import Dict, Sequence
 
 STAT_KEYS = ["episodes", "return_sum", "length_sum", "nan_resets", "contacts_dropped", "rows_dropped",
-             "arena_overflows", "solver_iters", "substeps", "newton_iteration_caps", "wide_passes"]
+             "arena_overflows", "solver_iters", "substeps", "newton_iteration_caps", "wide_passes", "wide_passes_rows"]
 
 
 def shard_range(rank: int, world_size: int, envs_per_gpu: int):

@@ -19,6 +19,10 @@ BOUNDS = {"quadruped_parkour": (2e-3, 1e-4, 5e-4), "humanoid_soccer": (2e-3, 1e-
           "humanoid_dancing": (2e-3, 1e-4, 5e-4), "humanoid_construction": (1e-3, 1e-4, 5e-4), "humanoid_martial_arts": (1e-3, 1e-4, 5e-4)}
 
 
+SMALL = {"quadruped_parkour": dict(con_cap=32), "humanoid_soccer": dict(con_cap=32), "bipedal_rescue": dict(con_cap=48),
+         "humanoid_dancing": dict(con_cap=16), "humanoid_construction": dict(con_cap=64), "humanoid_martial_arts": dict(con_cap=48)}
+
+
 def rel(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-12))
@@ -34,7 +38,8 @@ def test_over_capacity_states_match_the_oracle(task):
     G = lambda k: g[f"{task}__{k}"]
     t = load_tables(task); dm = capi.DeviceModel(t, 0); om = ref.load_model(t)
     n = G("qpos").shape[0]
-    b = capi.Batch(dm, TASKS[task].describe(t), n, 0, 0)
+    # on-chip capacities small enough that every fixture state is over them whatever the library defaults are
+    b = capi.Batch(dm, TASKS[task].describe(t), n, 0, 0, **SMALL[task])
     f = lambda k: torch.tensor(G(k), dtype=torch.float32)
     b.set_state(f("qpos"), f("qvel"), f("ctrl"), f("warm"), torch.zeros(n))
     ncon, geom, dist = b.contacts(160)
@@ -73,7 +78,7 @@ def test_wide_tier_off_drops_and_counts():
     task = "quadruped_parkour"
     g = np.load(GOLD); G = lambda k: g[f"{task}__{k}"]
     t = load_tables(task); dm = capi.DeviceModel(t, 0); n = G("qpos").shape[0]
-    b = capi.Batch(dm, TASKS[task].describe(t), n, 0, 0, disable_wide=True)
+    b = capi.Batch(dm, TASKS[task].describe(t), n, 0, 0, disable_wide=True, con_cap=32)
     f = lambda k: torch.tensor(G(k), dtype=torch.float32)
     b.set_state(f("qpos"), f("qvel"), f("ctrl"), f("warm"), torch.zeros(n))
     b.forward()
