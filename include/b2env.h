@@ -49,7 +49,7 @@ typedef struct B2BatchOpts {
   int disable_wide;    /* non-zero: no global spill workspace; what exceeds the on-chip capacities is dropped and counted (A/B tests) */
   int warmstart_once_per_step; /* 0 (default): qacc_warmstart is saved at the end of every forward pass, as MuJoCo 3.x's mj_fwdConstraint does
                                   (RK4 stages 2-4 start from the previous stage); non-zero: once per mj_step (the round-1 reading) */
-  int reserved[1];
+  int fifo_queue;      /* non-zero: envs are stepped in index order; default: longest-last-step first (a long env pulled last is a tail) */
 } B2BatchOpts;
 
 /* Replaces mujoco.MjData(model) for n_envs lock-stepped environments (parkour_env.py:54).  env_offset is the global

@@ -32,7 +32,7 @@ class B2TaskDesc(ctypes.Structure):
 class B2BatchOpts(ctypes.Structure):
     _fields_ = [("envs_per_block", ctypes.c_int), ("arena_floats", ctypes.c_int), ("con_cap", ctypes.c_int),
                 ("row_cap", ctypes.c_int), ("warps_per_env", ctypes.c_int), ("disable_wide", ctypes.c_int),
-                ("warmstart_once_per_step", ctypes.c_int), ("reserved", ctypes.c_int * 1)]
+                ("warmstart_once_per_step", ctypes.c_int), ("fifo_queue", ctypes.c_int)]
 
 
 class B2Error(RuntimeError):
@@ -127,7 +127,7 @@ class Batch:
 
     def __init__(self, model: DeviceModel, task: Optional[B2TaskDesc], n_envs: int, seed: int = 0, env_offset: int = 0,
                  envs_per_block: int = 0, arena_floats: int = 0, con_cap: int = 0, row_cap: int = 0,
-                 warps_per_env: int = 0, disable_wide: bool = False, warmstart_once_per_step: bool = False):
+                 warps_per_env: int = 0, disable_wide: bool = False, warmstart_once_per_step: bool = False, fifo_queue: bool = False):
         import torch
         self.torch = torch
         self.model = model
@@ -139,6 +139,7 @@ class Batch:
         opts.warps_per_env = int(os.environ.get("B2_WPE", warps_per_env))
         opts.disable_wide = int(os.environ.get("B2_NO_WIDE", int(disable_wide)))
         opts.warmstart_once_per_step = int(os.environ.get("B2_WARM_ONCE", int(warmstart_once_per_step)))
+        opts.fifo_queue = int(os.environ.get("B2_FIFO", int(fifo_queue)))
         _ck(lib().b2_batch_create(model.handle, ctypes.byref(task) if task is not None else None, n_envs,
                                   ctypes.c_uint64(seed & (2**64 - 1)), env_offset, ctypes.byref(opts), ctypes.byref(h)))
         self.handle = h

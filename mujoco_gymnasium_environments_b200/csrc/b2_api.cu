@@ -35,9 +35,10 @@ struct B2Batch {
   cudaStream_t own_stream; cudaEvent_t ev_order; cudaStream_t last_stream; bool pending;   // caller-stream work not yet ordered before own_stream
   int episode_slot;   // index of the episode id in ti (RNG stream key), -1 none
   // b2_rollout: the T launches of a rollout as one instantiated CUDA graph, cached while T and the buffers stay the same
-  cudaGraphExec_t roll_exec; int roll_T; const void* roll_key[6];
+  cudaGraphExec_t roll_exec; int roll_T; const void* roll_key[6]; unsigned long long roll_launches;
   int obs_dim, act_dim, nti, ntf, ninj;
   int num_sms;
+  int* d_order; bool lpt;   // longest-last-step-first queue order, rebuilt before every b2_step
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -65,9 +66,11 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TEAM) : "memory");
     const int idx = *slot;
     if (idx >= B.n_envs) break;
-    const int env = B.first_env + idx;
+    const int env = B.order ? B.order[idx] : B.first_env + idx;
     if (mode == MODE_RESET && B.reset_mask && !B.reset_mask[env]) continue;
+    const long long t0 = clock64();
     b2_env_body<Task, W>(P, B, tp, mode, epstat, inject, team, env);
+    if (tl == 0 && mode == MODE_STEP) B.cost[env] = (unsigned)((clock64() - t0) >> 8);
   }
   if (tl == 0) {      // last team out re-arms the queue
     __threadfence();
@@ -228,6 +231,37 @@ struct NoTask {
   template <class EN> __device__ static void post_physics(EN&, const TaskParams&, int*, float*) {}
 };
 
+// Longest-processing-time-first order of the work queue: envs whose last control step was expensive (a fallen robot with 40
+// contacts sweeps three times the rows of a standing one, a blown-up one runs in the wide tier) tend to be expensive again,
+// and a long job pulled last is a tail every other SM waits for.  One CTA buckets the envs by last-step cost relative to the
+// mean (8 buckets, most expensive first); order inside a bucket is by env index.  Runs before every b2_step launch (~10 us).
+__global__ void b2_order_kernel(const unsigned* cost, int n, int* order) {
+  __shared__ unsigned long long ssum; __shared__ int cnt[8], base[8];
+  if (threadIdx.x == 0) ssum = 0ull;
+  if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long loc = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) loc += cost[e];
+  atomicAdd(&ssum, loc);
+  __syncthreads();
+  const float mean = (float)ssum / (float)n + 1.0f;
+  auto bucket = [mean](unsigned c) { const float r = (float)c / mean; return r > 3.0f ? 0 : r > 2.2f ? 1 : r > 1.7f ? 2 : r > 1.35f ? 3 : r > 1.1f ? 4 : r > 0.9f ? 5 : r > 0.7f ? 6 : 7; };
+  // stable within a bucket: each thread owns a contiguous slice of envs
+  const int per = (n + blockDim.x - 1) / blockDim.x, e0 = threadIdx.x * per, e1 = min(n, e0 + per);
+  int mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int e = e0; e < e1; e++) mine[bucket(cost[e])]++;
+  __shared__ int slice[8][1024];
+  for (int k = 0; k < 8; k++) slice[k][threadIdx.x] = mine[k];
+  __syncthreads();
+  if (threadIdx.x < 8) { int acc = 0; for (int t = 0; t < (int)blockDim.x; t++) { int v = slice[threadIdx.x][t]; slice[threadIdx.x][t] = acc; acc += v; } cnt[threadIdx.x] = acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int k = 0; k < 8; k++) { base[k] = acc; acc += cnt[k]; } }
+  __syncthreads();
+  int pos[8];
+  for (int k = 0; k < 8; k++) pos[k] = base[k] + slice[k][threadIdx.x];
+  for (int e = e0; e < e1; e++) { const int k = bucket(cost[e]); order[pos[k]++] = e; }
+}
+
 __global__ void b2_stats_kernel(const unsigned long long* counters, const double* epstat, int n, double* out) {
   __shared__ double acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.0;
@@ -294,6 +328,12 @@ static int launch(B2Batch* b, int mode, const float* inject, cudaStream_t s) {
   CK(cudaSetDevice(b->m->device));
   { int rc = order_after_last(b, s); if (rc) return rc; }
   if (b->v.n_envs <= 0 || b->v.first_env + b->v.n_envs > b->n_envs) { b->v.first_env = 0; b->v.n_envs = b->n_envs; }
+  b->v.order = nullptr;
+  if (mode == MODE_STEP && b->lpt && b->v.first_env == 0 && b->v.n_envs == b->n_envs && b->n_envs >= 4 * b->num_sms) {
+    b2_order_kernel<<<1, 1024, 0, s>>>(b->v.cost, b->n_envs, b->d_order);
+    g_launches++;
+    b->v.order = b->d_order;
+  }
 #define B2_CALL(T) launch_task<T>(b, mode, inject, s)
   B2_FOR_TASK(b, B2_CALL);
 #undef B2_CALL
@@ -441,6 +481,8 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&v.ti, N * v.nti * 4)); CK(cudaMalloc(&v.tf, N * v.ntf * 4));
   CK(cudaMalloc(&v.phase_cycles, 32 * 8)); CK(cudaMemset(v.phase_cycles, 0, 32 * 8));
   CK(cudaMalloc(&v.queue, 4 * 4)); CK(cudaMemset(v.queue, 0, 4 * 4));
+  CK(cudaMalloc(&v.cost, N * 4)); CK(cudaMemset(v.cost, 0, N * 4)); CK(cudaMalloc(&b->d_order, N * 4));
+  b->lpt = !(opts && opts->fifo_queue);
   CK(cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, m->device));
   CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 8)); CK(cudaMalloc(&b->d_stats, 16 * 8));
   CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));
@@ -474,7 +516,7 @@ void b2_batch_destroy(B2Batch* b) {
   if (!b) return;
   cudaSetDevice(b->m->device);
   BatchView& v = b->v;
-  cudaFree(v.wide); cudaFree(v.queue);
+  cudaFree(v.wide); cudaFree(v.queue); cudaFree(v.cost); cudaFree(b->d_order);
   cudaFree(v.qpos); cudaFree(v.qvel); cudaFree(v.warm); cudaFree(v.qfrc_applied); cudaFree(v.ctrl); cudaFree(v.time);
   cudaFree(v.ti); cudaFree(v.tf); cudaFree(v.phase_cycles); cudaFree(v.counters); cudaFree(b->epstat); cudaFree(b->d_stats);
   cudaFree(v.final_ti); cudaFree(v.final_tf); cudaFree(v.final_xpos);
@@ -540,13 +582,14 @@ int b2_rollout(B2Batch* b, int T, const float* act_dev, float* obs_dev, float* r
     if (b->roll_exec) { cudaGraphExecDestroy(b->roll_exec); b->roll_exec = nullptr; }
     cudaStream_t cap = s ? s : b->own_stream;            // the legacy default stream cannot be captured
     cudaGraph_t g = nullptr;
+    const unsigned long long launches_before = g_launches.load();
     CK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     int rc = B2_OK;
     for (int t = 0; t < T && rc == B2_OK; t++)
       rc = b2_step(b, act_dev + (size_t)t * N * b->act_dim, obs_dev + (size_t)t * N * b->obs_dim, rew_dev + (size_t)t * N, term_dev + (size_t)t * N,
                    trunc_dev + (size_t)t * N, final_obs_dev ? final_obs_dev + (size_t)t * N * b->obs_dim : nullptr, cap);
     cudaError_t e = cudaStreamEndCapture(cap, &g);
-    g_launches -= (unsigned long long)T;                 // counted per replay below, not per capture
+    b->roll_launches = g_launches.load() - launches_before; g_launches = launches_before;      // counted per replay below, not per capture
     if (rc != B2_OK) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(B2_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&b->roll_exec, g, 0);
@@ -555,7 +598,7 @@ int b2_rollout(B2Batch* b, int T, const float* act_dev, float* obs_dev, float* r
     b->roll_T = T; memcpy(b->roll_key, key, sizeof(key));
   }
   CK(cudaGraphLaunch(b->roll_exec, s));                // launching into the legacy stream is fine; only capturing on it is not
-  g_launches += (unsigned long long)T;
+  g_launches += b->roll_launches;
   return B2_OK;
 }
 int b2_host_buffers(B2Batch* b, float** act, float** obs, float** rew, uint8_t** term, uint8_t** trunc) {

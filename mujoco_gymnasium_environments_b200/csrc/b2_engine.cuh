@@ -125,6 +125,8 @@ struct BatchView {
   float* debug_out; int debug_n;                     // optional [N][debug_n] dump of solver intermediates (bring-up / tests)
   unsigned long long* counters;                      // [N][CTR_COUNT]
   int* queue;                                        // [0] next env of this launch, [1] teams that have left (work queue of the persistent CTAs)
+  unsigned* cost;                                    // [N] device cycles (>> 8) each env's last control step took
+  const int* order;                                  // [N] queue position -> env, longest-last-step first (nullptr: identity)
   unsigned long long* phase_cycles;                  // [16] per-phase clock64 sums (only with -DB2_PHASE_TIMING)
   unsigned long long seed;
   int arena_floats, con_cap, row_cap;
