@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -59,6 +60,8 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
   constexpr int TEAM = 32 * W;
   const int team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
   uint64_t* bar = (uint64_t*)(b2_smem + B.model_floats + B.envs_per_block * B.ws_floats);
+  volatile int* active = (volatile int*)(bar + 1);       // teams of this CTA that may still pull work (lockstep mode)
+  if (threadIdx.x == 0) *active = B.envs_per_block;
   stage_model(P, (int*)b2_smem, b2_smem + r4(P.n_ints_staged), bar);
   volatile int* slot = (volatile int*)(b2_smem + B.model_floats + team * B.ws_floats + B.off.misc) + MISC_ENV;
   for (;;) {
@@ -71,6 +74,14 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
     const long long t0 = clock64();
     b2_env_body<Task, W>(P, B, tp, mode, epstat, inject, team, env);
     if (tl == 0 && mode == MODE_STEP) B.cost[env] = (unsigned)((clock64() - t0) >> 8);
+  }
+  if (B.lockstep) {
+    // a team that is out of work keeps arriving at the CTA barrier of the forward passes until every team of the CTA is done
+    if (tl == 0) atomicSub((int*)active, 1);
+    for (;;) {
+      asm volatile("bar.sync 0;" ::: "memory");
+      if (*active == 0) break;
+    }
   }
   if (tl == 0) {      // last team out re-arms the queue
     __threadfence();
@@ -217,7 +228,7 @@ __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& 
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1, LOCKSTEP = 0;
   static constexpr int SOLVER = -1;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
@@ -396,11 +407,11 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   b->m = m; b->n_envs = n_envs;
   struct Guard { B2Batch* b; ~Guard() { if (b) b2_batch_destroy(b); } } guard{b};      // released on success
   memset(&b->tp, 0, sizeof(b->tp));
-  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6; bool cold = false; b->ninj = 1;
+  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6, task_lockstep = 0; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); memcpy(b->tp.aux_i, task->aux_i, sizeof(task->aux_i)); memcpy(b->tp.aux_f, task->aux_f, sizeof(task->aux_f)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; b->episode_slot = -1; break;
-#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; b->episode_slot = T::EPISODE_SLOT; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; b->episode_slot = T::EPISODE_SLOT; task_lockstep = T::LOCKSTEP; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -483,6 +494,9 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   CK(cudaMalloc(&v.queue, 4 * 4)); CK(cudaMemset(v.queue, 0, 4 * 4));
   CK(cudaMalloc(&v.cost, N * 4)); CK(cudaMemset(v.cost, 0, N * 4)); CK(cudaMalloc(&b->d_order, N * 4));
   b->lpt = !(opts && opts->fifo_queue);
+  // per-task default (A/B-measured on B200: +13 % dancing, whose forward passes are instruction-fetch bound and alike in length;
+  // -9..-21 % where PGS / Newton iteration counts vary between envs); B2_LOCKSTEP overrides for experiments
+  { const char* ls = getenv("B2_LOCKSTEP"); v.lockstep = ls ? atoi(ls) : task_lockstep; }
   CK(cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, m->device));
   CK(cudaMalloc(&v.counters, N * CTR_COUNT * 8)); CK(cudaMalloc(&b->epstat, N * 4 * 8)); CK(cudaMalloc(&b->d_stats, 16 * 8));
   CK(cudaMemset(v.qvel, 0, N * v.nvp * 4)); CK(cudaMemset(v.warm, 0, N * v.nvp * 4)); CK(cudaMemset(v.qfrc_applied, 0, N * v.nvp * 4));

@@ -127,6 +127,7 @@ struct BatchView {
   int* queue;                                        // [0] next env of this launch, [1] teams that have left (work queue of the persistent CTAs)
   unsigned* cost;                                    // [N] device cycles (>> 8) each env's last control step took
   const int* order;                                  // [N] queue position -> env, longest-last-step first (nullptr: identity)
+  int lockstep;                                      // the teams of a CTA start every forward pass together (CTA barrier): they then run the same code at the same time and share instruction-cache lines
   unsigned long long* phase_cycles;                  // [16] per-phase clock64 sums (only with -DB2_PHASE_TIMING)
   unsigned long long seed;
   int arena_floats, con_cap, row_cap;
@@ -1958,6 +1959,7 @@ struct Engine {
     for (int stage = 0; stage < nstage; stage++) {
 #pragma unroll 1
       for (int attempt = 0; attempt < 2; attempt++) {
+        if (B.lockstep) asm volatile("bar.sync 0;" ::: "memory");      // every thread of the CTA: teams without work keep arriving (b2_env_kernel)
         if (wl == 0) { kinematics(); com_pos(); }
         team_sync(); B2_TICK(0);
         bool restart = false;

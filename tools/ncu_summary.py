@@ -24,4 +24,6 @@ with open(out, "w") as f:
             if h in want or "issue_stalled" in h and "per_issue_active" in h:
                 f.write(f"{h} [{u}] = {v}\n")
     f.write("\n## hottest CUDA source lines (warp-stall samples / executed warp-instructions)\n" + hot)
+    ic = subprocess.run([sys.executable, "tools/ncu_icache.py", rep], capture_output=True, text=True).stdout
+    f.write("\n## instruction-fetch view (tools/ncu_icache.py)\n" + ic)
 print("wrote", out)
