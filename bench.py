@@ -40,13 +40,13 @@ WORKLOADS = {
                              "action_space x {s}, same-step auto-reset"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the task's default size, from the
-# `ncu --set full` captures summarised under profiles/ (r01_i quadruped, r01_f dancing, r01_g soccer, r01_h rescue,
-# r01_j construction, r01_k martial arts, r01_l arm).
-# Below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2.
-NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.233728e6 + 287.744e3), "humanoid_dancing": (8192, 9.365248e6 + 721.408e3),
-               "humanoid_soccer": (4096, 4.960768e6 + 33.024e3), "bipedal_rescue": (2048, 3.231744e6 + 72.96e3),
-               "humanoid_construction": (2048, 4.57088e6 + 48.384e3), "humanoid_martial_arts": (4096, 5.356544e6 + 18.688e3),
-               "robotic_arm_assembly": (2048, 3.184896e6 + 268.032e3)}
+# `ncu --set full` captures summarised under profiles/r02_f_<task>.txt (step 104 of a full-range rollout).
+# Below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2; rescue's 29 MB of
+# writes are its wide-tier workspace (J and M^-1 J' blocks of the over-capacity passes) being evicted from L2.
+NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.436736e6 + 140.032e3), "humanoid_dancing": (8192, 9.633024e6 + 261.632e3),
+               "humanoid_soccer": (4096, 5.025536e6 + 1.024e3), "bipedal_rescue": (2048, 4.692992e6 + 29.490944e6),
+               "humanoid_construction": (2048, 4.714752e6 + 132.352e3), "humanoid_martial_arts": (4096, 5.178368e6 + 3.328e3),
+               "robotic_arm_assembly": (2048, 3.00032e6 + 141.824e3)}
 TASK = "quadruped_parkour"
 WORKLOAD = WORKLOADS[TASK][2]
 
@@ -180,10 +180,9 @@ def _finite(x):
 # issue-slot utilisation of the step kernel (sm__inst_issued / cycle / 4 schedulers) from the committed `ncu --set full`
 # captures of one launch at the task's BASELINE size: the secondary bound of a path that is four orders of magnitude away from
 # its HBM roofline.  Static, like NCU_TRAFFIC: a bench run takes no profile.
-NCU_ISSUE_PCT = {"quadruped_parkour": (24.3, "profiles/r01_i_quadruped.txt"), "humanoid_dancing": (26.0, "profiles/r01_f_dancing_rk4.txt"),
-                 "humanoid_soccer": (21.0, "profiles/r01_g_soccer.txt"), "bipedal_rescue": (17.0, "profiles/r01_h_rescue_cold_pairs.txt"),
-                 "humanoid_construction": (9.3, "profiles/r01_j_construction_newton.txt"), "humanoid_martial_arts": (12.9, "profiles/r01_k_martial_arts_newton.txt"),
-                 "robotic_arm_assembly": (10.6, "profiles/r01_l_arm_condim6.txt")}
+NCU_ISSUE_PCT = {t: (v, f"profiles/r02_f_{t}.txt") for t, v in (("quadruped_parkour", 28.35), ("humanoid_dancing", 17.44), ("humanoid_soccer", 27.36),
+                                                                  ("bipedal_rescue", 18.92), ("humanoid_construction", 10.44),
+                                                                  ("humanoid_martial_arts", 11.23), ("robotic_arm_assembly", 17.02))}
 PREROLL = 100     # un-timed control steps before the warm-up: the bench times the stationary regime, not the first seconds after reset
 
 
@@ -246,7 +245,7 @@ def run_task(task, N, K, warmup, preroll, action_scale, rank, world, local, peak
     achieved = spec.bytes_per_env_step * N / (kern_ms * 1e-3) / 1e9
     out["roofline"] = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                            traffic=(NCU_TRAFFIC[task][1] if NCU_TRAFFIC.get(task, (0, 0))[0] == N else None),
-                           traffic_source="static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, copied from profiles/ (not measured by this run)",
+                           traffic_source="static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, copied from profiles/r02_f_<task>.txt (not measured by this run)",
                            peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                            bytes_per_env_step=spec.bytes_per_env_step, kernel_ms=kern_ms,
                            fp32_issue=dict(issue_slots_busy_pct=NCU_ISSUE_PCT[task][0], source="static: " + NCU_ISSUE_PCT[task][1]),
