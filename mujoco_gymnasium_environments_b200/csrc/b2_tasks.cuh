@@ -850,7 +850,7 @@ struct MartialArtsTask {
 // tf: [0] cumulative_reward
 // ids: [0..8] component bodies in assembly order, [9] body of ee_site    aux_f: [3k..3k+2] target of component k, [27..29] ee_site offset
 struct ArmTask {
-  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 4, EPISODE_SLOT = 2, LOCKSTEP = 0, ARENA_FLOATS = 4000;
+  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 4, EPISODE_SLOT = 2, LOCKSTEP = 1, ARENA_FLOATS = 4000;
   static constexpr int SOLVER = 2;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
