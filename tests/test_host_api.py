@@ -1,0 +1,83 @@
+"""Host-side pieces of the round-2 boundary that need no GPU: the Gymnasium registration table, the lazily built per-env
+infos, the per-task info builders and the batch-options struct."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from mujoco_gymnasium_environments_b200 import capi, registration
+from mujoco_gymnasium_environments_b200.tasks import TASKS, load_tables
+from mujoco_gymnasium_environments_b200.vector_env import LazyInfos
+
+
+def test_registration_table_matches_the_reference_ids():
+    # quadruped_parkour_env/__init__.py:16-24, humanoid_soccer_env/__init__.py:18-26, humanoid_construction_env/__init__.py:18-26,
+    # robotic_arm_assembly_env/__init__.py:12-17
+    by_id = {r["id"]: r for r in registration.REGISTRY}
+    assert by_id["QuadrupedParkour-v0"]["max_episode_steps"] == 6000 and by_id["QuadrupedParkour-v0"]["reward_threshold"] == 8000.0
+    assert by_id["HumanoidSoccer-v0"]["max_episode_steps"] == 2500          # registered value; the class truncates at 5000
+    assert by_id["HumanoidConstruction-v0"]["max_episode_steps"] == 3000 and by_id["RoboticArmAssembly-v0"]["max_episode_steps"] == 150000
+    for r in registration.REGISTRY:
+        mod, cls = r["entry_point"].split(":")
+        assert mod == "mujoco_gymnasium_environments_b200.envs"
+        import importlib
+        assert hasattr(importlib.import_module(mod), cls)
+    assert "QuadrupedParkour-v1" in registration.NOT_REGISTERED
+    try:
+        import gymnasium  # noqa: F401
+        assert registration.register_all(prefix="B200Test/") == ["B200Test/" + r["id"] for r in registration.REGISTRY]
+    except ImportError:
+        assert registration.register_all() == []
+
+
+@pytest.mark.parametrize("task", list(TASKS))
+def test_vector_info_has_the_reference_keys_and_env_shaped_values(task):
+    spec = TASKS[task]; t = load_tables(task); n = 5
+    ti = torch.arange(n * 64, dtype=torch.int32).reshape(n, 64) % 7; tf = torch.rand((n, 64)); x = torch.rand((n, t.nbody, 3))
+    info = spec.vector_info(torch, ti, tf, x, t)
+    numeric = {"current_move", "task", "task_phase", "held_component", "assembly_progress"}     # strings in the reference, indices here
+    skipped = {"combo_chain", "component_status", "ball_contact", "robot_upright"}               # not derivable from the task state rows alone
+    for k in spec.info_keys:
+        if k in skipped:
+            continue
+        assert k in info, (task, k)
+        v = info[k]
+        leaves = list(v.values()) if isinstance(v, dict) else [v]
+        for leaf in leaves:
+            assert leaf.shape[0] == n, (task, k)
+
+
+def test_lazy_infos_builds_once_and_only_on_demand():
+    calls = []
+
+    class FakeSpec:
+        info_keys = ["step_count"]
+
+        @staticmethod
+        def vector_info(torch_, ti, tf, xpos, tables):
+            calls.append(1)
+            return {"step_count": ti[:, 0]}
+
+    class FakeEnv:
+        spec = FakeSpec(); tables = None; torch = torch
+
+        def task_state(self, with_xpos=False):
+            return torch.ones((3, 4), dtype=torch.int32), torch.zeros((3, 4)), torch.zeros((3, 2, 3))
+
+    infos = LazyInfos(FakeEnv(), {"final_obs": torch.zeros((3, 2)), "_final_obs": torch.zeros(3, dtype=torch.bool)})
+    assert infos["final_obs"].shape == (3, 2) and not calls          # eager entries cost nothing
+    assert torch.equal(infos["step_count"], torch.ones(3, dtype=torch.int32)) and len(calls) == 1
+    assert "task_ti" in infos and "nonexistent" not in infos and len(calls) == 1
+    with pytest.raises(KeyError):
+        infos["nonexistent"]
+    assert set(infos.keys()) >= {"final_obs", "_final_obs", "step_count", "task_ti", "task_tf"}
+
+
+def test_batch_opts_struct_is_eight_ints_with_the_documented_fields():
+    names = [f[0] for f in capi.B2BatchOpts._fields_]
+    assert names == ["envs_per_block", "arena_floats", "con_cap", "row_cap", "warps_per_env", "disable_wide", "warmstart_once_per_step", "fifo_queue"]
+    assert ctypes.sizeof(capi.B2BatchOpts) == 32
+    hdr = open(__file__.replace("tests/test_host_api.py", "include/b2env.h")).read()
+    for n in names:
+        assert n in hdr, n
