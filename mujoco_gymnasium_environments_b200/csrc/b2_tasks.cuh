@@ -686,7 +686,7 @@ struct RescueTask {
 // tf: [0] total_reward [1] task_progress [2] wind_strength [3] rain_intensity [4] temperature
 // ids: [0] humanoid body      inject: task index, wind, rain, temperature
 struct ConstructionTask {
-  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 2, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 2, LOCKSTEP = 0, ARENA_FLOATS = 6000;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
