@@ -43,7 +43,7 @@ WORKLOADS = {
 # `ncu --set full` captures summarised under profiles/r02_f_<task>.txt (step 104 of a full-range rollout).
 # Below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2; rescue's 29 MB of
 # writes are its wide-tier workspace (J and M^-1 J' blocks of the over-capacity passes) being evicted from L2.
-NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.436736e6 + 140.032e3), "humanoid_dancing": (8192, 9.633024e6 + 261.632e3),
+NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.436736e6 + 140.032e3), "humanoid_dancing": (8192, 9.999872e+06),
                "humanoid_soccer": (4096, 5.025536e6 + 1.024e3), "bipedal_rescue": (2048, 4.692992e6 + 29.490944e6),
                "humanoid_construction": (2048, 4.714752e6 + 132.352e3), "humanoid_martial_arts": (4096, 5.178368e6 + 3.328e3),
                "robotic_arm_assembly": (2048, 3.00032e6 + 141.824e3)}
@@ -180,7 +180,7 @@ def _finite(x):
 # issue-slot utilisation of the step kernel (sm__inst_issued / cycle / 4 schedulers) from the committed `ncu --set full`
 # captures of one launch at the task's BASELINE size: the secondary bound of a path that is four orders of magnitude away from
 # its HBM roofline.  Static, like NCU_TRAFFIC: a bench run takes no profile.
-NCU_ISSUE_PCT = {t: (v, f"profiles/r02_f_{t}.txt") for t, v in (("quadruped_parkour", 28.35), ("humanoid_dancing", 17.44), ("humanoid_soccer", 27.36),
+NCU_ISSUE_PCT = {t: (v, "profiles/r02_g_humanoid_dancing_lockstep_E5.txt" if t == "humanoid_dancing" else f"profiles/r02_f_{t}.txt") for t, v in (("quadruped_parkour", 28.35), ("humanoid_dancing", 21.71), ("humanoid_soccer", 27.36),
                                                                   ("bipedal_rescue", 18.92), ("humanoid_construction", 10.44),
                                                                   ("humanoid_martial_arts", 11.23), ("robotic_arm_assembly", 17.02))}
 PREROLL = 100     # un-timed control steps before the warm-up: the bench times the stationary regime, not the first seconds after reset
