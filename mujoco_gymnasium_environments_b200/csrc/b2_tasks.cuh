@@ -530,7 +530,7 @@ struct SoccerTask {
 //      (26 consecutive) [4] victim1_x joint (victim joints are 6 apart, y = x + 1)
 // inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
 struct RescueTask {
-  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 2, EPISODE_SLOT = 4, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, ARENA_FLOATS = 7400;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
