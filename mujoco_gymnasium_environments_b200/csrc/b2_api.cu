@@ -245,7 +245,7 @@ struct NoTask {
 // Longest-processing-time-first order of the work queue: envs whose last control step was expensive (a fallen robot with 40
 // contacts sweeps three times the rows of a standing one, a blown-up one runs in the wide tier) tend to be expensive again,
 // and a long job pulled last is a tail every other SM waits for.  One CTA buckets the envs by last-step cost relative to the
-// mean (8 buckets, most expensive first); order inside a bucket is by env index.  Runs before every b2_step launch (~10 us).
+// mean (8 buckets, most expensive first); order inside a bucket is by env index.  Runs before every b2_step launch (~60 us cold under ncu, 0.4 % of a step).
 __global__ void b2_order_kernel(const unsigned* cost, int n, int* order) {
   __shared__ unsigned long long ssum; __shared__ int cnt[8], base[8];
   if (threadIdx.x == 0) ssum = 0ull;
