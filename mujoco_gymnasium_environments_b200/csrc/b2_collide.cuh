@@ -11,9 +11,8 @@
 //   box-box          15-axis separating-axis test; face case clips the incident face against the reference face
 //                    (the pair's own raw slot doubles as the polygon scratch), edge case = closest points of two edges
 //   plane-cylinder   mjc_PlaneCylinder restated (up to four contacts)
-//   capsule-cylinder one contact at the segment point nearest the cylinder (convex 1-D search, centre of plateaus)
-//   cylinder-box     rim samples of the cylinder against the box + deepest box vertex in the cylinder (<= 4 contacts)
-//   cylinder-cylinder  one contact: side-side at the closest axis points, or the deepest rim sample of either
+//   capsule-cylinder, cylinder-box, cylinder-cylinder   mjc_Convex: libccd's Minkowski Portal Refinement restated
+//                    (b2_mpr.cuh), one contact per pair
 #pragma once
 #include "b2_math.cuh"
 
@@ -142,112 +141,6 @@ __device__ __forceinline__ int c_sphere_cylinder(float* dst, V3 p1, float r1, V3
   raw_put(dst, dist, mulmat(m2, cp + n * (dist * 0.5f)) + p2, mulmat(m2, n * -1.f), v3(0, 0, 0));
   return 1;
 }
-// capsule vs cylinder: the signed distance of the segment point c + a t to the solid cylinder is convex in t.  Coarse
-// bracket from 9 samples, ternary refinement, then the middle of the sub-level set {f <= fmin + 1e-5}: a plateau (segment
-// parallel to the side or to a cap) yields the centre of the contact patch whatever the rounding.
-__device__ __forceinline__ float capcyl_f(V3 c0, V3 a, float t, const float* s2) {
-  V3 cp, n; return point_cylinder(c0 + a * t, s2[0], s2[1], cp, n);
-}
-__device__ __noinline__ int c_capsule_cylinder(float* dst, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
-                                               const float* s2, float margin) {
-  V3 ax = matcol(m1, 2), c0 = mulmatT(m2, p1 - p2), a = mulmatT(m2, ax);
-  float l = s1[1], fb = 0.f; int ib = 0;
-  if (capcyl_f(c0, a, 0.f, s2) - l - s1[0] > margin) return 0;       // the distance is 1-Lipschitz along the segment
-  for (int i = 0; i <= 8; i++) { float f = capcyl_f(c0, a, -l + 0.25f * l * (float)i, s2); if (i == 0 || f < fb) { fb = f; ib = i; } }
-  float lo = -l + 0.25f * l * (float)(ib > 0 ? ib - 1 : 0), hi = -l + 0.25f * l * (float)(ib < 8 ? ib + 1 : 8);
-  for (int it = 0; it < 24; it++) {
-    float w = (hi - lo) / 3.0f, t1 = lo + w, t2 = hi - w;
-    if (capcyl_f(c0, a, t1, s2) <= capcyl_f(c0, a, t2, s2)) hi = t2; else lo = t1;
-  }
-  float tm = 0.5f * (lo + hi), lev = capcyl_f(c0, a, tm, s2) + 1e-5f, tl = -l, tr = l;
-  if (capcyl_f(c0, a, -l, s2) > lev) {
-    float x = -l, y = tm;
-    for (int it = 0; it < 24; it++) { float mid = 0.5f * (x + y); if (capcyl_f(c0, a, mid, s2) <= lev) y = mid; else x = mid; }
-    tl = y;
-  }
-  if (capcyl_f(c0, a, l, s2) > lev) {
-    float x = tm, y = l;
-    for (int it = 0; it < 24; it++) { float mid = 0.5f * (x + y); if (capcyl_f(c0, a, mid, s2) <= lev) x = mid; else y = mid; }
-    tr = x;
-  }
-  return c_sphere_cylinder(dst, p1 + ax * (0.5f * (tl + tr)), s1[0], p2, m2, s2, margin);
-}
-// signed distance of p (box frame) to the solid box; closest surface point and outward normal
-__device__ __forceinline__ float point_box(V3 p, const float* s, V3& cp, V3& n) {
-  float d0 = fabsf(p.x) - s[0], d1 = fabsf(p.y) - s[1], d2 = fabsf(p.z) - s[2];
-  if (d0 <= 0.f && d1 <= 0.f && d2 <= 0.f) {      // inside: leave through the nearest face (x, y, z on ties)
-    int k = 0; float dk = d0;
-    if (d1 > dk) { k = 1; dk = d1; }
-    if (d2 > dk) { k = 2; dk = d2; }
-    float sg = sel3(p, k) < 0.f ? -1.f : 1.f;
-    n = v3(k == 0 ? sg : 0.f, k == 1 ? sg : 0.f, k == 2 ? sg : 0.f);
-    cp = v3(k == 0 ? sg * s[0] : p.x, k == 1 ? sg * s[1] : p.y, k == 2 ? sg * s[2] : p.z);
-    return dk;
-  }
-  cp = v3(clampf(p.x, -s[0], s[0]), clampf(p.y, -s[1], s[1]), clampf(p.z, -s[2], s[2]));
-  V3 v = p - cp; float dd = norm(v);
-  n = v * (1.0f / dd);
-  return dd;
-}
-// eight points per cylinder rim, visited 0,90,180,270 then 45,135,225,315 degrees (a cap lying flat keeps its symmetric four)
-__device__ __forceinline__ V3 rim_point(const float* s, int j) {
-  const int q = j & 7; const float h = 0.70710678f;
-  float c = q == 0 ? 1.f : q == 2 ? -1.f : (q == 1 || q == 3) ? 0.f : (q == 4 || q == 7) ? h : -h;
-  float sn = q == 1 ? 1.f : q == 3 ? -1.f : (q == 0 || q == 2) ? 0.f : (q == 4 || q == 5) ? h : -h;
-  return v3(s[0] * c, s[0] * sn, j < 8 ? s[1] : -s[1]);
-}
-// cylinder vs box: rim points of the cylinder within the margin of the box (top cap first), then the box vertex deepest
-// in the cylinder; at most four contacts
-__device__ __noinline__ int c_cylinder_box(float* dst, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
-                                           const float* s2, float margin, int maxn) {
-  int cnt = 0; const int cap = maxn < 4 ? maxn : 4;
-  for (int j = 0; j < 16 && cnt < cap; j++) {
-    V3 cp, n; float dd = point_box(mulmatT(m2, mulmat(m1, rim_point(s1, j)) + (p1 - p2)), s2, cp, n);
-    if (dd > margin) continue;
-    raw_put(dst + B2_RAW * cnt, dd, mulmat(m2, cp + n * (dd * 0.5f)) + p2, mulmat(m2, n * -1.f), v3(0, 0, 0));
-    cnt++;
-  }
-  if (cnt >= cap) return cnt;
-  float best = 3.0e38f; V3 bcp = v3(0, 0, 0), bn = v3(0, 0, 1);
-  for (int i = 0; i < 8; i++) {
-    V3 v = v3((i & 1) ? s2[0] : -s2[0], (i & 2) ? s2[1] : -s2[1], (i & 4) ? s2[2] : -s2[2]);
-    V3 cp, n; float dd = point_cylinder(mulmatT(m1, mulmat(m2, v) + (p2 - p1)), s1[0], s1[1], cp, n);
-    if (dd < best) { best = dd; bcp = cp; bn = n; }
-  }
-  if (best > margin) return cnt;
-  raw_put(dst + B2_RAW * cnt, best, mulmat(m1, bcp + bn * (best * 0.5f)) + p1, mulmat(m1, bn), v3(0, 0, 0));
-  return cnt + 1;
-}
-// cylinder vs cylinder: one contact, the deepest of side-against-side (closest points of the axes, both strictly inside
-// the segments), rim points of 1 in 2, rim points of 2 in 1; a later candidate must be deeper by more than 1e-6
-__device__ __noinline__ int c_cylinder_cylinder(float* dst, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
-                                                const float* s2, float margin) {
-  float best = 3.0e38f; V3 bpos = v3(0, 0, 0), bn = v3(0, 0, 1);
-  V3 a1 = matcol(m1, 2), a2 = matcol(m2, 2), dif = p2 - p1;
-  float cab = dot(a1, a2), u = dot(a1, dif), v = dot(a2, dif), det = 1.0f - cab * cab, x1, x2; bool side;
-  if (det > 1e-6f) { x1 = (u - cab * v) / det; x2 = (cab * u - v) / det; side = fabsf(x1) < s1[1] && fabsf(x2) < s2[1]; }
-  else {
-    float lo = fmaxf(u - s2[1], -s1[1]), hi = fminf(u + s2[1], s1[1]);
-    x1 = 0.5f * (lo + hi); x2 = (cab < 0.f ? -1.f : 1.f) * (x1 - u); side = lo < hi;
-  }
-  if (side) {
-    V3 q1 = p1 + a1 * x1, d = (p2 + a2 * x2) - q1; float dd = norm(d);
-    // (nearly) intersecting axes have no side-against-side direction
-    if (dd > 1e-6f) { best = dd - s1[0] - s2[0]; bn = d * (1.0f / dd); bpos = q1 + bn * (s1[0] + 0.5f * best); }
-  }
-  for (int g = 0; g < 2; g++) {
-    V3 pa = g ? p2 : p1, pb = g ? p1 : p2; const float* ma = g ? m2 : m1; const float* mb = g ? m1 : m2;
-    const float* sa = g ? s2 : s1; const float* sb = g ? s1 : s2;
-    for (int j = 0; j < 16; j++) {
-      V3 cp, n; float dd = point_cylinder(mulmatT(mb, mulmat(ma, rim_point(sa, j)) + (pa - pb)), sb[0], sb[1], cp, n);
-      if (dd < best - 1e-6f) { best = dd; bpos = mulmat(mb, cp + n * (dd * 0.5f)) + pb; bn = mulmat(mb, n) * (g ? 1.f : -1.f); }
-    }
-  }
-  if (best > margin + 1e-6f) return 0;    // stacked coaxial cylinders touch exactly (arm base / shoulder): the tie is a contact in both precisions
-  raw_put(dst, best, bpos, bn, v3(0, 0, 0));
-  return 1;
-}
-
 // ---- capsule vs capsule (mjc_CapsuleCapsule restated: closest points of two segments, parallel case by end tests)
 __device__ __noinline__ int c_capsule_capsule(float* dst, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
                                               const float* s2, float margin) {
@@ -438,6 +331,10 @@ __device__ __noinline__ int c_box_box(float* dst, V3 p1, const float* m1, const 
   return cnt;
 }
 
+}  // namespace b2
+#include "b2_mpr.cuh"
+namespace b2 {
+
 // ---- dispatch: geom 1 has the lower type id
 __device__ __forceinline__ int collide_pair(int t1, int t2, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
                                             const float* s2, float margin, float* dst, int maxn) {
@@ -459,11 +356,10 @@ __device__ __forceinline__ int collide_pair(int t1, int t2, V3 p1, const float* 
   if (t1 == GT_CAPSULE) {
     if (t2 == GT_CAPSULE) return c_capsule_capsule(dst, p1, m1, s1, p2, m2, s2, margin);
     if (t2 == GT_BOX) return c_capsule_box(dst, p1, m1, s1, p2, m2, s2, margin);
-    if (t2 == GT_CYLINDER) return c_capsule_cylinder(dst, p1, m1, s1, p2, m2, s2, margin);
+    if (t2 == GT_CYLINDER) return c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
     return 0;
   }
-  if (t1 == GT_CYLINDER && t2 == GT_BOX) return c_cylinder_box(dst, p1, m1, s1, p2, m2, s2, margin, maxn);
-  if (t1 == GT_CYLINDER && t2 == GT_CYLINDER) return c_cylinder_cylinder(dst, p1, m1, s1, p2, m2, s2, margin);
+  if (t1 == GT_CYLINDER && (t2 == GT_BOX || t2 == GT_CYLINDER)) return c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   if (t1 == GT_BOX && t2 == GT_BOX) return c_box_box(dst, p1, m1, s1, p2, m2, s2, margin);
   return 0;
 }

@@ -1651,6 +1651,9 @@ struct Engine {
     for (int k = 0; k < nisl; k++) {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
+#ifdef B2_PHASE_TIMING
+      const long long tn0 = clock64();
+#endif
       const float* J = xs_J<WD>(k); const Cols cols = island_cols(k);       // wide: J (plain rows) and jv in the global workspace, H on chip
       float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;   // H: packed lower triangle
       float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
@@ -1864,6 +1867,13 @@ struct Engine {
       for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); p_qfc()[d] = Mv[c]; p_qacc()[d] = Mv[c]; }
       sync();
       if (it >= iters && lane == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
+#ifdef B2_PHASE_TIMING
+      if (lane == 0 && B.phase_cycles) {      // Newton solves by island size class: [20..23] <= 8 dofs, [24..27] <= 40, [28..31] larger: solves, iterations, rows, cycles
+        const int cls = nd <= 8 ? 20 : nd <= 40 ? 24 : 28;
+        atomicAdd(&B.phase_cycles[cls], 1ull); atomicAdd(&B.phase_cycles[cls + 1], (unsigned long long)it);
+        atomicAdd(&B.phase_cycles[cls + 2], (unsigned long long)n); atomicAdd(&B.phase_cycles[cls + 3], (unsigned long long)(clock64() - tn0));
+      }
+#endif
       itmax = max(itmax, it);
     }
     if (lane == 0) p_red()[wl] = (float)itmax;

@@ -51,7 +51,7 @@ FLT_FIELDS = [
 # static upper bound on contacts one geom pair can generate, by (type1,type2) with type1<=type2
 # (plane0 sphere2 capsule3 cylinder5 box6); SURVEY App. B.4
 _MAXCON = {(0, 2): 1, (0, 3): 2, (0, 5): 4, (0, 6): 4, (2, 2): 1, (2, 3): 1, (2, 5): 1, (2, 6): 1,
-           (3, 3): 2, (3, 5): 1, (3, 6): 2, (5, 5): 1, (5, 6): 4, (6, 6): 8}
+           (3, 3): 2, (3, 5): 1, (3, 6): 2, (5, 5): 1, (5, 6): 1, (6, 6): 8}
 
 
 def derived_tables(m: ModelTables) -> Dict[str, np.ndarray]:

@@ -570,138 +570,196 @@ static int sphere_cylinder(RawCon *c, const real *pos1, real r1, const real *pos
   for (int k = 0; k < 3; k++) { c->pos[k] += pos2[k]; c->frame[3+k] = 0; }
   return 1;
 }
-/* capsule (geom1) vs cylinder (geom2): one contact at the segment point nearest the cylinder.  The signed distance
- * f(t) of the segment point c + a t to the solid cylinder is convex in t: coarse bracket from 9 samples, ternary
- * refinement, then the middle of the sub-level set {f <= fmin + 1e-5}, so that a plateau (segment parallel to the side
- * or to a cap) yields the centre of the contact patch whatever the rounding. */
-static real capcyl_f(const real *c0, const real *a, real t, const real *size2) {
-  real p[3] = {c0[0] + a[0]*t, c0[1] + a[1]*t, c0[2] + a[2]*t}, cp[3], n[3];
-  return point_cylinder(p, size2[0], size2[1], cp, n);
+/* ---- convex pairs: capsule-cylinder, cylinder-cylinder, cylinder-box (mjc_Convex, engine_collision_convex.c).
+ * MuJoCo routes these pair types through libccd's Minkowski Portal Refinement (ccdMPRPenetration, libccd src/mpr.c;
+ * the default convex path of MuJoCo 2.3 - 3.2, selectable later with the nativeccd flag off), one contact per pair
+ * (multiccd is off by default).  Restated below with libccd's own tolerances and sign tests: CCD_EPS = DBL_EPSILON (MuJoCo
+ * builds libccd in double), mpr_tolerance 1e-6, mpr_iterations 50 (mjOption defaults; no task overrides them).  Each geom
+ * is inflated by margin/2 inside its support function (mjccd_support) and dist = margin - depth (mjc_MPRIteration).
+ * mjc_fixNormal only touches spheres and ellipsoids, neither of which takes this path in the seven tasks.
+ * One deviation: libccd's portal-discovery and portal-refinement loops are unbounded; they are capped at MPR_LOOP_CAP
+ * passes here (and in the kernel) and report "no contact" beyond it. */
+#define CCD_EPS 2.2204460492503131e-16
+#define MPR_TOL 1e-6
+#define MPR_MAXIT 50
+#define MPR_LOOP_CAP 100
+typedef struct { int type; const real *pos, *mat, *size; real margin; } CcdObj;
+typedef struct { real v[3], v1[3], v2[3]; } CcdSup;
+static inline int ccd_zero(real x) { return fabs(x) < CCD_EPS; }
+static inline int ccd_eq(real a_, real b_) {
+  real ab = fabs(a_ - b_);
+  if (ab < CCD_EPS) return 1;
+  real a = fabs(a_), b = fabs(b_);
+  return b > a ? ab < CCD_EPS * b : ab < CCD_EPS * a;
 }
-static int capsule_cylinder(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
-                            const real *mat2, const real *size2, real margin) {
-  real ax[3] = {mat1[2], mat1[5], mat1[8]}, dif[3] = {pos1[0]-pos2[0], pos1[1]-pos2[1], pos1[2]-pos2[2]}, c0[3], a[3];
-  to_local(c0, mat2, dif); to_local(a, mat2, ax);
-  real l = size1[1], fb = 0; int ib = 0;
-  if (capcyl_f(c0, a, 0, size2) - l - size1[0] > margin) return 0;   /* the distance is 1-Lipschitz along the segment */
-  for (int i = 0; i <= 8; i++) { real f = capcyl_f(c0, a, -l + 0.25*l*i, size2); if (i == 0 || f < fb) { fb = f; ib = i; } }
-  real lo = -l + 0.25*l*(ib > 0 ? ib - 1 : 0), hi = -l + 0.25*l*(ib < 8 ? ib + 1 : 8);
-  for (int it = 0; it < 24; it++) {
-    real w = (hi - lo) / 3.0, m1 = lo + w, m2 = hi - w;
-    if (capcyl_f(c0, a, m1, size2) <= capcyl_f(c0, a, m2, size2)) hi = m2; else lo = m1;
-  }
-  real tm = 0.5*(lo + hi), lev = capcyl_f(c0, a, tm, size2) + 1e-5, tl = -l, tr = l;
-  if (capcyl_f(c0, a, -l, size2) > lev) {
-    real x = -l, y = tm;
-    for (int it = 0; it < 24; it++) { real mid = 0.5*(x + y); if (capcyl_f(c0, a, mid, size2) <= lev) y = mid; else x = mid; }
-    tl = y;
-  }
-  if (capcyl_f(c0, a, l, size2) > lev) {
-    real x = tm, y = l;
-    for (int it = 0; it < 24; it++) { real mid = 0.5*(x + y); if (capcyl_f(c0, a, mid, size2) <= lev) x = mid; else y = mid; }
-    tr = x;
-  }
-  real ts = 0.5*(tl + tr), p[3] = {pos1[0] + ax[0]*ts, pos1[1] + ax[1]*ts, pos1[2] + ax[2]*ts};
-  return sphere_cylinder(c, p, size1[0], pos2, mat2, size2, margin);
-}
-/* signed distance of p (box frame) to the solid box with half sizes s; closest surface point cp, outward normal n */
-static real point_box(const real *p, const real *s, real *cp, real *n) {
-  real d[3] = {fabs(p[0]) - s[0], fabs(p[1]) - s[1], fabs(p[2]) - s[2]};
-  n[0] = n[1] = n[2] = 0;
-  if (d[0] <= 0 && d[1] <= 0 && d[2] <= 0) {       /* inside: leave through the nearest face (x, y, z on ties) */
-    int k = 0; if (d[1] > d[k]) k = 1; if (d[2] > d[k]) k = 2;
-    real sg = p[k] < 0 ? -1.0 : 1.0;
-    cp[0] = p[0]; cp[1] = p[1]; cp[2] = p[2]; cp[k] = sg*s[k]; n[k] = sg;
-    return d[k];
-  }
-  real v[3];
-  for (int k = 0; k < 3; k++) { cp[k] = p[k] < -s[k] ? -s[k] : (p[k] > s[k] ? s[k] : p[k]); v[k] = p[k] - cp[k]; }
-  real dd = norm3(v);
-  n[0] = v[0]/dd; n[1] = v[1]/dd; n[2] = v[2]/dd;
-  return dd;
-}
-/* eight points per cylinder rim, visited 0,90,180,270 then 45,135,225,315 degrees so that the first four of a cap lying
- * flat are its symmetric support */
-static const real RIM_C[8] = {1, 0, -1, 0, 0.70710678118654752, -0.70710678118654752, -0.70710678118654752, 0.70710678118654752};
-static const real RIM_S[8] = {0, 1, 0, -1, 0.70710678118654752, 0.70710678118654752, -0.70710678118654752, -0.70710678118654752};
-/* cylinder (geom1) vs box (geom2): up to four contacts.  Rim points of the cylinder (top cap first) that lie within the
- * margin of the box, then the box vertex deepest in the cylinder (first vertex on ties). */
-static int cylinder_box(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
-                        const real *mat2, const real *size2, real margin) {
-  int cnt = 0;
-  for (int j = 0; j < 16 && cnt < 4; j++) {
-    real pl[3] = {size1[0]*RIM_C[j & 7], size1[0]*RIM_S[j & 7], j < 8 ? size1[1] : -size1[1]}, w[3], pb[3], cp[3], n[3];
-    mulmatvec3(w, mat1, pl);
-    for (int k = 0; k < 3; k++) w[k] += pos1[k] - pos2[k];
-    to_local(pb, mat2, w);
-    real dd = point_box(pb, size2, cp, n);
-    if (dd > margin) continue;
-    real posl[3] = {cp[0] + n[0]*dd*0.5, cp[1] + n[1]*dd*0.5, cp[2] + n[2]*dd*0.5}, nl[3] = {-n[0], -n[1], -n[2]};
-    c[cnt].dist = dd;
-    mulmatvec3(c[cnt].frame, mat2, nl); mulmatvec3(c[cnt].pos, mat2, posl);
-    for (int k = 0; k < 3; k++) { c[cnt].pos[k] += pos2[k]; c[cnt].frame[3+k] = 0; }
-    cnt++;
-  }
-  if (cnt >= 4) return cnt;
-  real best = 1e300, bcp[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
-  for (int i = 0; i < 8; i++) {
-    real v[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])}, w[3], pl[3], cp[3], n[3];
-    mulmatvec3(w, mat2, v);
-    for (int k = 0; k < 3; k++) w[k] += pos2[k] - pos1[k];
-    to_local(pl, mat1, w);
-    real dd = point_cylinder(pl, size1[0], size1[1], cp, n);
-    if (dd < best) { best = dd; memcpy(bcp, cp, sizeof(cp)); memcpy(bn, n, sizeof(n)); }
-  }
-  if (best > margin) return cnt;
-  real posl[3] = {bcp[0] + bn[0]*best*0.5, bcp[1] + bn[1]*best*0.5, bcp[2] + bn[2]*best*0.5};
-  c[cnt].dist = best;
-  mulmatvec3(c[cnt].frame, mat1, bn); mulmatvec3(c[cnt].pos, mat1, posl);
-  for (int k = 0; k < 3; k++) { c[cnt].pos[k] += pos1[k]; c[cnt].frame[3+k] = 0; }
-  return cnt + 1;
-}
-/* cylinder vs cylinder: one contact, the deepest of (side against side at the closest points of the two axes when both
- * lie strictly inside the segments; rim points of 1 in 2; rim points of 2 in 1).  A later candidate replaces the
- * current one only if it is deeper by more than 1e-6, so exact ties keep the first in both precisions. */
-static int cylinder_cylinder(RawCon *c, const real *pos1, const real *mat1, const real *size1, const real *pos2,
-                             const real *mat2, const real *size2, real margin) {
-  real best = 1e300, bpos[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
-  real a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
-  real dif[3] = {pos2[0]-pos1[0], pos2[1]-pos1[1], pos2[2]-pos1[2]};
-  real cab = dot3(a1, a2), u = dot3(a1, dif), v = dot3(a2, dif), det = 1.0 - cab*cab, x1, x2; int side = 0;
-  if (det > 1e-6) { x1 = (u - cab*v) / det; x2 = (cab*u - v) / det; side = fabs(x1) < size1[1] && fabs(x2) < size2[1]; }
-  else {                                            /* parallel axes: middle of the overlap */
-    real lo = u - size2[1] > -size1[1] ? u - size2[1] : -size1[1], hi = u + size2[1] < size1[1] ? u + size2[1] : size1[1];
-    x1 = 0.5*(lo + hi); x2 = (cab < 0 ? -1.0 : 1.0) * (x1 - u); side = lo < hi;
-  }
-  if (side) {
-    real q1[3], q2[3], d[3];
-    for (int k = 0; k < 3; k++) { q1[k] = pos1[k] + a1[k]*x1; q2[k] = pos2[k] + a2[k]*x2; d[k] = q2[k] - q1[k]; }
-    real dd = norm3(d);
-    if (dd > 1e-6) {                               /* (nearly) intersecting axes have no side-against-side direction */
-      best = dd - size1[0] - size2[0];
-      for (int k = 0; k < 3; k++) { bn[k] = d[k]/dd; bpos[k] = q1[k] + bn[k]*(size1[0] + 0.5*best); }
+static inline int ccd_vec_is_origin(const real *v) { return ccd_eq(v[0], 0) && ccd_eq(v[1], 0) && ccd_eq(v[2], 0); }
+static inline real sign0(real x) { return x < 0 ? -1.0 : (x > 0 ? 1.0 : 0.0); }   /* mju_sign */
+static inline void ccd_normalize(real *v) { real s = 1.0 / sqrt(dot3(v, v)); v[0] *= s; v[1] *= s; v[2] *= s; }
+/* mjccd_support: farthest point of the (margin-inflated) geom along the unit direction dir, world frame */
+static void ccd_support1(const CcdObj *o, const real *dir, real *res) {
+  real ld[3], r[3] = {0, 0, 0};
+  to_local(ld, o->mat, dir);
+  switch (o->type) {
+    case B2_GEOM_SPHERE: r[0] = ld[0]*o->size[0]; r[1] = ld[1]*o->size[0]; r[2] = ld[2]*o->size[0]; break;
+    case B2_GEOM_CAPSULE:
+      r[0] = ld[0]*o->size[0]; r[1] = ld[1]*o->size[0]; r[2] = ld[2]*o->size[0] + sign0(ld[2])*o->size[1]; break;
+    case B2_GEOM_CYLINDER: {
+      real t = sqrt(ld[0]*ld[0] + ld[1]*ld[1]);
+      if (t > MINVAL) { r[0] = ld[0]/t*o->size[0]; r[1] = ld[1]/t*o->size[0]; }
+      r[2] = sign0(ld[2])*o->size[1]; break;
     }
+    case B2_GEOM_BOX: for (int k = 0; k < 3; k++) r[k] = sign0(ld[k])*o->size[k]; break;
   }
-  for (int g = 0; g < 2; g++) {
-    const real *pa = g ? pos2 : pos1, *ma = g ? mat2 : mat1, *sa = g ? size2 : size1;     /* the cylinder whose rim is sampled */
-    const real *pb = g ? pos1 : pos2, *mb = g ? mat1 : mat2, *sb = g ? size1 : size2;     /* the solid it is tested against */
-    for (int j = 0; j < 16; j++) {
-      real pl[3] = {sa[0]*RIM_C[j & 7], sa[0]*RIM_S[j & 7], j < 8 ? sa[1] : -sa[1]}, w[3], q[3], cp[3], n[3];
-      mulmatvec3(w, ma, pl);
-      for (int k = 0; k < 3; k++) w[k] += pa[k] - pb[k];
-      to_local(q, mb, w);
-      real dd = point_cylinder(q, sb[0], sb[1], cp, n);
-      if (dd < best - 1e-6) {
-        real posl[3] = {cp[0] + n[0]*dd*0.5, cp[1] + n[1]*dd*0.5, cp[2] + n[2]*dd*0.5}, nw[3];
-        best = dd;
-        mulmatvec3(bpos, mb, posl); mulmatvec3(nw, mb, n);
-        for (int k = 0; k < 3; k++) { bpos[k] += pb[k]; bn[k] = g ? nw[k] : -nw[k]; }   /* normal from geom 1 to geom 2 */
+  mulmatvec3(res, o->mat, r);
+  for (int k = 0; k < 3; k++) res[k] += o->pos[k] + dir[k]*o->margin;
+}
+static void ccd_support(const CcdObj *o1, const CcdObj *o2, const real *dir, CcdSup *s) {   /* __ccdSupport */
+  real nd[3] = {-dir[0], -dir[1], -dir[2]};
+  ccd_support1(o1, dir, s->v1); ccd_support1(o2, nd, s->v2);
+  for (int k = 0; k < 3; k++) s->v[k] = s->v1[k] - s->v2[k];
+}
+static void portal_dir(const CcdSup *p, real *dir) {
+  real a[3], b[3];
+  for (int k = 0; k < 3; k++) { a[k] = p[2].v[k] - p[1].v[k]; b[k] = p[3].v[k] - p[1].v[k]; }
+  cross3(dir, a, b); ccd_normalize(dir);
+}
+static int portal_reach_tolerance(const CcdSup *p, const CcdSup *v4, const real *dir) {
+  real dv4 = dot3(v4->v, dir), d1 = dv4 - dot3(p[1].v, dir), d2 = dv4 - dot3(p[2].v, dir), d3 = dv4 - dot3(p[3].v, dir);
+  if (d2 < d1) d1 = d2;
+  if (d3 < d1) d1 = d3;
+  return ccd_eq(d1, MPR_TOL) || d1 < MPR_TOL;
+}
+static void expand_portal(CcdSup *p, const CcdSup *v4) {
+  real v4v0[3]; cross3(v4v0, v4->v, p[0].v);
+  if (dot3(p[1].v, v4v0) > 0) { if (dot3(p[2].v, v4v0) > 0) p[1] = *v4; else p[3] = *v4; }
+  else { if (dot3(p[3].v, v4v0) > 0) p[2] = *v4; else p[1] = *v4; }
+}
+/* discoverPortal: -1 no intersection, 0 portal found, 1 origin on v1, 2 origin on the v0-v1 segment */
+static int discover_portal(const CcdObj *o1, const CcdObj *o2, CcdSup *p) {
+  real dir[3], va[3], vb[3], dot;
+  for (int k = 0; k < 3; k++) { p[0].v1[k] = o1->pos[k]; p[0].v2[k] = o2->pos[k]; p[0].v[k] = o1->pos[k] - o2->pos[k]; }
+  if (ccd_vec_is_origin(p[0].v)) p[0].v[0] += CCD_EPS * 10.0;
+  for (int k = 0; k < 3; k++) dir[k] = -p[0].v[k];
+  ccd_normalize(dir);
+  ccd_support(o1, o2, dir, &p[1]);
+  dot = dot3(p[1].v, dir);
+  if (ccd_zero(dot) || dot < 0) return -1;
+  cross3(dir, p[0].v, p[1].v);
+  if (ccd_zero(dot3(dir, dir))) return ccd_vec_is_origin(p[1].v) ? 1 : 2;
+  ccd_normalize(dir);
+  ccd_support(o1, o2, dir, &p[2]);
+  dot = dot3(p[2].v, dir);
+  if (ccd_zero(dot) || dot < 0) return -1;
+  for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+  cross3(dir, va, vb); ccd_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) { CcdSup t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+  for (int pass = 0; pass < MPR_LOOP_CAP; pass++) {
+    ccd_support(o1, o2, dir, &p[3]);
+    dot = dot3(p[3].v, dir);
+    if (ccd_zero(dot) || dot < 0) return -1;
+    int cont = 0;
+    cross3(va, p[1].v, p[3].v); dot = dot3(va, p[0].v);
+    if (dot < 0 && !ccd_zero(dot)) { p[2] = p[3]; cont = 1; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v); dot = dot3(va, p[0].v);
+      if (dot < 0 && !ccd_zero(dot)) { p[1] = p[3]; cont = 1; }
+    }
+    if (!cont) return 0;
+    for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+    cross3(dir, va, vb); ccd_normalize(dir);
+  }
+  return -1;
+}
+static int refine_portal(const CcdObj *o1, const CcdObj *o2, CcdSup *p) {
+  real dir[3]; CcdSup v4;
+  for (int pass = 0; pass < MPR_LOOP_CAP; pass++) {
+    portal_dir(p, dir);
+    real dot = dot3(dir, p[1].v);
+    if (ccd_zero(dot) || dot > 0) return 0;                       /* portalEncapsulesOrigin */
+    ccd_support(o1, o2, dir, &v4);
+    dot = dot3(v4.v, dir);
+    if (!(ccd_zero(dot) || dot > 0) || portal_reach_tolerance(p, &v4, dir)) return -1;
+    expand_portal(p, &v4);
+  }
+  return -1;
+}
+static real point_seg_dist2(const real *x0, const real *b, real *wit) {   /* __ccdVec3PointSegmentDist2 with P = origin */
+  real d[3] = {b[0]-x0[0], b[1]-x0[1], b[2]-x0[2]};
+  real t = -dot3(x0, d) / dot3(d, d);
+  if (t < 0 || ccd_zero(t)) { memcpy(wit, x0, 3*sizeof(real)); return dot3(x0, x0); }
+  if (t > 1 || ccd_eq(t, 1)) { memcpy(wit, b, 3*sizeof(real)); return dot3(b, b); }
+  for (int k = 0; k < 3; k++) wit[k] = d[k]*t + x0[k];
+  return dot3(wit, wit);
+}
+static real point_tri_dist2(const real *x0, const real *B, const real *C, real *wit) {   /* ccdVec3PointTriDist2 with P = origin */
+  real d1[3], d2[3];
+  for (int k = 0; k < 3; k++) { d1[k] = B[k] - x0[k]; d2[k] = C[k] - x0[k]; }
+  real v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  real dd = w*v - r*r, s, t;
+  if (ccd_zero(dd)) s = t = -1.0;
+  else { s = (q*r - w*p) / dd; t = (-s*r - q) / w; }
+  if ((ccd_zero(s) || s > 0) && (ccd_eq(s, 1) || s < 1) && (ccd_zero(t) || t > 0) && (ccd_eq(t, 1) || t < 1) &&
+      (ccd_eq(t + s, 1) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + d1[k]*s + d2[k]*t;
+    return dot3(wit, wit);
+  }
+  real w2[3], dist = point_seg_dist2(x0, B, wit), dist2 = point_seg_dist2(x0, C, w2);
+  if (dist2 < dist) { dist = dist2; memcpy(wit, w2, sizeof(w2)); }
+  dist2 = point_seg_dist2(B, C, w2);
+  if (dist2 < dist) { dist = dist2; memcpy(wit, w2, sizeof(w2)); }
+  return dist;
+}
+static void find_pos(const CcdSup *p, real *pos) {
+  real dir[3], vec[3], b[4], sum;
+  portal_dir(p, dir);
+  cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
+  cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
+  cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
+  cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
+  sum = b[0] + b[1] + b[2] + b[3];
+  if (ccd_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
+    cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
+    cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  real inv = 1.0 / sum, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+  for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { p1[k] += p[i].v1[k]*b[i]; p2[k] += p[i].v2[k]*b[i]; }
+  for (int k = 0; k < 3; k++) pos[k] = 0.5 * (p1[k]*inv + p2[k]*inv);
+}
+/* ccdMPRPenetration + mjc_MPRIteration: 0 or 1 contact, normal from geom 1 to geom 2 */
+static int mpr_convex(RawCon *c, int t1, const real *pos1, const real *mat1, const real *size1, int t2, const real *pos2,
+                      const real *mat2, const real *size2, real margin) {
+  CcdObj o1 = {t1, pos1, mat1, size1, 0.5*margin}, o2 = {t2, pos2, mat2, size2, 0.5*margin};
+  CcdSup p[4]; real depth, dir[3], pos[3];
+  int res = discover_portal(&o1, &o2, p);
+  if (res < 0) return 0;
+  if (res == 1) return 0;            /* findPenetrTouch: depth 0, zero direction -> mjc_MPRIteration discards it */
+  if (res == 2) {                    /* findPenetrSegment */
+    for (int k = 0; k < 3; k++) { pos[k] = 0.5*(p[1].v1[k] + p[1].v2[k]); dir[k] = p[1].v[k]; }
+    depth = sqrt(dot3(dir, dir)); ccd_normalize(dir);
+  } else {
+    if (refine_portal(&o1, &o2, p) < 0) return 0;
+    CcdSup v4; real pd[3];
+    for (int it = 0; ; it++) {       /* findPenetr */
+      portal_dir(p, pd);
+      ccd_support(&o1, &o2, pd, &v4);
+      if (portal_reach_tolerance(p, &v4, pd) || it > MPR_MAXIT) {
+        depth = sqrt(point_tri_dist2(p[1].v, p[2].v, p[3].v, dir));
+        if (ccd_zero(depth)) return 0;                             /* zero direction: discarded */
+        ccd_normalize(dir);
+        find_pos(p, pos);
+        break;
       }
+      expand_portal(p, &v4);
     }
   }
-  if (best > margin + 1e-6) return 0;     /* stacked coaxial cylinders touch exactly (arm base / shoulder): the tie is a contact in both precisions */
-  c->dist = best;
-  for (int k = 0; k < 3; k++) { c->pos[k] = bpos[k]; c->frame[k] = bn[k]; c->frame[3+k] = 0; }
+  if (ccd_vec_is_origin(dir)) return 0;
+  if (!(depth == depth) || !(dir[0] == dir[0]) || !(pos[0] == pos[0]) || !(pos[1] == pos[1]) || !(pos[2] == pos[2])) return 0;   /* collapsed portal */
+  c->dist = margin - depth;
+  for (int k = 0; k < 3; k++) { c->pos[k] = pos[k]; c->frame[k] = dir[k]; c->frame[3+k] = 0; }
+  normalize3(c->frame);
   return 1;
 }
 
@@ -887,12 +945,21 @@ int ref_collide_raw(int t1, int t2, const double *p1, const double *m1, const do
     else if (t2 == B2_GEOM_CYLINDER) n = sphere_cylinder(raw, p1, s1[0], p2, m2, s2, margin);
   } else if (t1 == B2_GEOM_CAPSULE) {
     if (t2 == B2_GEOM_CAPSULE) n = capsule_capsule(raw, p1, m1, s1, p2, m2, s2, margin);
-    else if (t2 == B2_GEOM_CYLINDER) n = capsule_cylinder(raw, p1, m1, s1, p2, m2, s2, margin);
+    else if (t2 == B2_GEOM_CYLINDER) n = mpr_convex(raw, t1, p1, m1, s1, t2, p2, m2, s2, margin);
     else if (t2 == B2_GEOM_BOX) n = capsule_box(raw, p1, m1, s1, p2, m2, s2, margin);
-  } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) n = cylinder_box(raw, p1, m1, s1, p2, m2, s2, margin);
-  else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_CYLINDER) n = cylinder_cylinder(raw, p1, m1, s1, p2, m2, s2, margin);
+  } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) n = mpr_convex(raw, t1, p1, m1, s1, t2, p2, m2, s2, margin);
+  else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_CYLINDER) n = mpr_convex(raw, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) n = box_box(raw, p1, m1, s1, p2, m2, s2, margin);
   for (int k = 0; k < n && k < 8; k++) { out80[10*k] = raw[k].dist; memcpy(out80 + 10*k + 1, raw[k].pos, 3*sizeof(real)); memcpy(out80 + 10*k + 4, raw[k].frame, 6*sizeof(real)); }
+  return n;
+}
+
+/* the MPR path on any pair of sphere / capsule / cylinder / box (known-answer tests against the closed-form pairs) */
+int ref_mpr_raw(int t1, int t2, const double *p1, const double *m1, const double *s1, const double *p2,
+                const double *m2, const double *s2, double margin, double *out10) {
+  RawCon raw; memset(&raw, 0, sizeof(raw));
+  int n = mpr_convex(&raw, t1, p1, m1, s1, t2, p2, m2, s2, margin);
+  if (n) { out10[0] = raw.dist; memcpy(out10 + 1, raw.pos, 3*sizeof(real)); memcpy(out10 + 4, raw.frame, 6*sizeof(real)); }
   return n;
 }
 
@@ -917,13 +984,13 @@ static int collide_pair(const RefModel *m, const RefData *d, int g1, int g2, rea
   } else if (t1 == B2_GEOM_CAPSULE) {
     switch (t2) {
       case B2_GEOM_CAPSULE: return capsule_capsule(out, p1, m1, s1, p2, m2, s2, margin);
-      case B2_GEOM_CYLINDER: return capsule_cylinder(out, p1, m1, s1, p2, m2, s2, margin);
+      case B2_GEOM_CYLINDER: return mpr_convex(out, t1, p1, m1, s1, t2, p2, m2, s2, margin);
       case B2_GEOM_BOX: return capsule_box(out, p1, m1, s1, p2, m2, s2, margin);
     }
   } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_BOX) {
-    return cylinder_box(out, p1, m1, s1, p2, m2, s2, margin);
+    return mpr_convex(out, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   } else if (t1 == B2_GEOM_CYLINDER && t2 == B2_GEOM_CYLINDER) {
-    return cylinder_cylinder(out, p1, m1, s1, p2, m2, s2, margin);
+    return mpr_convex(out, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   } else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) {
     return box_box(out, p1, m1, s1, p2, m2, s2, margin);
   }

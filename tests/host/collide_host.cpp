@@ -15,3 +15,9 @@ extern "C" int h_collide_pair(int t1, int t2, const float* p1, const float* m1, 
   using namespace b2;
   return collide_pair(t1, t2, ld3(p1), m1, s1, ld3(p2), m2, s2, margin, out80, 8);
 }
+// the convex (MPR) path on any pair of sphere / capsule / cylinder / box
+extern "C" int h_mpr_pair(int t1, int t2, const float* p1, const float* m1, const float* s1, const float* p2,
+                          const float* m2, const float* s2, float margin, float* out10) {
+  using namespace b2;
+  return c_convex_mpr(out10, t1, ld3(p1), m1, s1, t2, ld3(p2), m2, s2, margin);
+}

@@ -73,3 +73,34 @@ def test_fp32_narrow_phase_matches_oracle(libs, pair):
             assert np.abs(o32[:n64, 0] - o64[:n64, 0]).max() < 2e-6, (pair, it)          # dist
             assert np.abs(o32[:n64, 1:7] - o64[:n64, 1:7]).max() < 5e-4, (pair, it)       # pos, normal
     assert ncontact > 100
+
+
+@pytest.mark.parametrize("pair", [(2, 3), (3, 3), (3, 6), (6, 6), (3, 5), (5, 5), (5, 6)])
+def test_convex_path_matches_oracle_on_any_pair(libs, pair):
+    """The kernel's MPR (csrc/b2_mpr.cuh, fp64 inside an fp32 interface) against the oracle's on the same fp32-rounded
+    inputs, world coordinates of order 1 m, penetrations from grazing to deep: same contacts, results to fp32 output rounding."""
+    H, R = libs
+    H.h_mpr_pair.argtypes = H.h_collide_pair.argtypes
+    R.ref_mpr_raw.argtypes = R.ref_collide_raw.argtypes
+    t1, t2 = pair
+    rng = np.random.default_rng(7 + 100 * t1 + t2)
+
+    def rq():
+        q = rng.normal(size=4); return q / np.linalg.norm(q)
+
+    sizes = dict(SIZES); sizes[5] = TALL
+    n = 0
+    for it in range(3000):
+        s1 = sizes[t1](rng); s2 = sizes[t2](rng)
+        m1 = quat_to_mat(rq()).ravel() if it % 4 else np.eye(3).ravel(); m2 = quat_to_mat(rq()).ravel() if it % 8 else np.eye(3).ravel()
+        p1 = rng.normal(size=3); p2 = p1 + rng.normal(size=3) * 0.3
+        a = [np.ascontiguousarray(x, np.float32) for x in (p1, m1, s1, p2, m2, s2)]
+        b = [np.ascontiguousarray(x, np.float64) for x in a]
+        o32 = np.zeros(10, np.float32); o64 = np.zeros(10)
+        n32 = H.h_mpr_pair(t1, t2, *[x.ctypes.data_as(FP) for x in a], 0.01, o32.ctypes.data_as(FP))
+        n64 = R.ref_mpr_raw(t1, t2, *[x.ctypes.data_as(DP) for x in b], float(np.float32(0.01)), o64.ctypes.data_as(DP))
+        assert n32 == n64, (pair, it)
+        if n64:
+            n += 1
+            assert abs(o32[0] - o64[0]) < 1e-7 and np.abs(o32[1:4] - o64[1:4]).max() < 5e-7 and np.abs(o32[4:7] - o64[4:7]).max() < 2e-7, (pair, it)
+    assert n > 250

@@ -63,6 +63,14 @@ def test_lockstep_uniformity_at_full_size(task):
     if task == "humanoid_dancing":
         e.prev_joint_vel = d.qvel[6:].copy()
     hi = env.single_action_space.high
+    twins = []
+    if task == "robotic_arm_assembly":      # compared up to the oracle's own response to an fp32-sized perturbation (oracle/twin.py)
+        from oracle.twin import SLACK, perturbed
+        prng = np.random.default_rng(2)
+        for _ in range(4):
+            g = REF[task](env.tables); _ref_reset(task, g, inj)
+            g.data.qpos[:] = perturbed(st["qpos"], prng); g.data.qvel[:] = perturbed(st["qvel"], prng); g.data.qacc_warmstart[:] = st["qacc_warmstart"]
+            twins.append(g)
     for s in range(2):
         a = (rng.uniform(-1, 1, env.spec.act_dim) * hi * 0.02).astype(np.float32)
         obs, rew, term, trunc, _ = env.step(np.tile(a, (n, 1)))
@@ -71,7 +79,10 @@ def test_lockstep_uniformity_at_full_size(task):
         assert torch.equal(term, term[0:1].expand_as(term)) and torch.equal(trunc, trunc[0:1].expand_as(trunc))
         ro, rr, rt, rtr, _ = e.step(a)
         tol = 2e-2 if task == "robotic_arm_assembly" else 2e-3
-        assert float(np.max(np.abs(obs[0].cpu().numpy() - ro) / (1.0 + np.abs(ro)))) < tol, (task, s)
+        slack = 0.0
+        for g in twins:
+            slack = np.maximum(slack, SLACK * np.abs(g.step(a)[0] - ro))
+        assert float(np.max(np.maximum(np.abs(obs[0].cpu().numpy() - ro) - slack, 0.0) / (1.0 + np.abs(ro)))) < tol, (task, s)
         assert bool(term[0]) == rt and bool(trunc[0]) == rtr
     env.close()
 

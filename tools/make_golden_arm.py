@@ -16,7 +16,11 @@ t = load_tables("robotic_arm_assembly")
 om = ref.load_model(t)
 rng = np.random.default_rng(20261025)
 CAP = 128
-S = dict(qpos=[], qvel=[], ctrl=[], warm=[], qpos1=[], qvel1=[], qacc=[], qpos5=[], ncon=[], pairs=[], dist=[], dims=[], nefc=[])
+S = dict(qpos=[], qvel=[], ctrl=[], warm=[], qpos1=[], qvel1=[], qacc=[], qpos5=[], ncon=[], pairs=[], dist=[], dims=[], nefc=[],
+         qacc_sens=[], qpos1_sens=[], qvel1_sens=[], qpos5_sens=[])
+from oracle.twin import perturbed, spread
+prng = np.random.default_rng(5)
+NTWIN = 8
 env = RoboticArmAssemblyRef(t); d = env.data
 
 
@@ -58,6 +62,18 @@ def record(d):
     S["ncon"].append(len(con)); S["pairs"].append(pairs); S["dist"].append(dist); S["dims"].append(dims)
     ref.mj_step(om, e, 4)
     S["qpos5"].append(e.qpos.copy())
+    # the oracle's own response to fp32-sized perturbations of this state (oracle/twin.py): flat cylinder caps resting on flat
+    # faces make MPR's contact point a function of the last bits
+    tw = dict(qacc=[], qpos1=[], qvel1=[], qpos5=[])
+    for _ in range(NTWIN):
+        g = ref.RefData(om)
+        g.qpos[:] = perturbed(q, prng); g.qvel[:] = perturbed(v, prng); g.ctrl[:] = c; g.qacc_warmstart[:] = w
+        ref.mj_forward(om, g); tw["qacc"].append(g.qacc.copy())
+        g.qacc_warmstart[:] = w
+        ref.mj_step(om, g); tw["qpos1"].append(g.qpos.copy()); tw["qvel1"].append(g.qvel.copy())
+        ref.mj_step(om, g, 4); tw["qpos5"].append(g.qpos.copy())
+    for k_ in tw:
+        S[k_ + "_sens"].append(spread(tw[k_], S[k_][-1]))
 
 
 for k in range(2):
@@ -80,6 +96,26 @@ obs = np.zeros((STEPS, 110), np.float32); rew = np.zeros(STEPS); term = np.zeros
 for s in range(STEPS):
     obs[s], rew[s], term[s], _, _ = env.step(acts[s])
 out.update(task_actions=acts, task_obs0=obs0, task_obs=obs, task_rew=rew, task_term=term)
+# twins of the task rollout: same actions from a perturbed post-reset state
+tobs = np.zeros((NTWIN, STEPS, 110)); trew = np.zeros((NTWIN, STEPS))
+for k_ in range(NTWIN):
+    g = RoboticArmAssemblyRef(t); g.reset()
+    g.data.qpos[:] = perturbed(g.data.qpos, prng); g.data.qvel[:] = perturbed(g.data.qvel, prng)
+    for s in range(STEPS):
+        tobs[k_, s], trew[k_, s], _, _, _ = g.step(acts[s])
+out.update(task_obs_sens=spread(tobs, obs), task_rew_sens=spread(trew, rew))
+# twins of reset(): the ten settle steps from a perturbed copy of the state reset() writes (ctrl 0, as in reset())
+t0 = np.zeros((NTWIN, 110))
+for k_ in range(NTWIN):
+    g = RoboticArmAssemblyRef(t); g.reset()
+    ref.mj_resetData(g.model, g.data)
+    q0 = np.array(g.data.qpos); q0[0:7] = [0, -0.5, 0.5, 0, 0.5, 0, 0]
+    for c_ in g.SEQ:
+        a_ = g.comp_qadr[c_]; q0[a_:a_ + 3] = g.INITIAL[c_]; q0[a_ + 3:a_ + 7] = [1, 0, 0, 0]
+    g.data.qpos[:] = perturbed(q0, prng); g.data.qvel[:] = perturbed(np.zeros_like(np.array(g.data.qvel)), prng)
+    ref.mj_step(g.model, g.data, 10)
+    t0[k_] = g._get_observation()
+out.update(task_obs0_sens=spread(t0, obs0))
 env = RoboticArmAssemblyRef(t); env.reset(); d = env.data
 d.qvel[:] = 0; d.qacc_warmstart[:] = 0          # the arm is mounted through the table top and flails after reset: start the grasp from rest
 craft(env, "cpu")
@@ -90,6 +126,13 @@ cobs = np.zeros((4, 110), np.float32); crew = np.zeros(4); cterm = np.zeros(4, b
 for s in range(4):
     cobs[s], crew[s], cterm[s], _, _ = env.step(cacts[s])
     cheld[s] = env.SEQ.index(env.held_component) if env.held_component else -1; cphase[s] = env.PHASES[env.task_phase]
+tobs = np.zeros((NTWIN, 4, 110)); trew = np.zeros((NTWIN, 4))
+for k_ in range(NTWIN):
+    g = RoboticArmAssemblyRef(t); g.reset()
+    g.data.qpos[:] = perturbed(cq, prng); g.data.qvel[:] = perturbed(cv, prng); g.data.qacc_warmstart[:] = cw
+    for s in range(4):
+        tobs[k_, s], trew[k_, s], _, _, _ = g.step(cacts[s])
+out.update(craft_obs_sens=spread(tobs, cobs), craft_rew_sens=spread(trew, crew))
 print("crafted pickup: held", cheld, "phase", cphase, "reward", crew.round(1), "status", env.component_status["cpu"])
 out.update(craft_qpos=cq, craft_qvel=cv, craft_warm=cw, craft_actions=cacts, craft_obs=cobs, craft_rew=crew, craft_term=cterm, craft_held=cheld, craft_phase=cphase)
 path = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "robotic_arm_assembly.npz")

@@ -33,6 +33,9 @@ print(task, "N", N, "scale", scale, "envs/cta", env.batch.envs_per_block, "smem"
 nw = max(out[15], 1)
 print(f"wide PGS solves {out[15]}: rows/solve {out[8]/nw:.0f} iters/solve {out[7]/nw:.1f} ring depth {out[14]/nw:.1f}; cycles/solve: B build+records {out[4]/nw:.0f}, init (v, cost) {out[5]/nw:.0f}, sweeps {out[6]/nw:.0f}")
 print(f"  ring waits {out[17]} ({out[17]/nw:.0f}/solve): {out[16]/max(out[17],1):.0f} cycles each; warp-0 time at the per-iteration team barrier {out[18]/nw:.0f} cycles/solve")
+for name, c in (("<= 8 dofs", 20), ("9-40 dofs", 24), ("> 40 dofs", 28)):
+    if out[c]:
+        print(f"  Newton islands {name}: {out[c]} solves ({out[c]/max(st['substeps'],1):.1f}/substep), {out[c+1]/out[c]:.2f} iterations, {out[c+2]/out[c]:.0f} rows, {out[c+3]/out[c]:.0f} cycles each = {out[c+3]/max(st['substeps'],1):.0f} cycles/substep")
 out = list(out); out[4] = out[5] = out[6] = out[7] = out[8] = 0
 for n, v in zip(names, out[:14]):
     print(f"{n:32s} {100*v/tot:5.1f}%  {v/max(st['substeps'],1):10.0f} cycles/substep")
