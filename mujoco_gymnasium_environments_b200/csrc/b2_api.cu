@@ -93,7 +93,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 template <class Task, int W>
 __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& B, const TaskParams& tp, int mode, double* epstat,
                                             const float* inject, int team, int env) {
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6> E(P, B, B.model_floats + team * B.ws_floats, team, env);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6, Task::NEWTON_TEAM_ND> E(P, B, B.model_floats + team * B.ws_floats, team, env);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   E.team_sync();      // the previous env's stores to this workspace are done
@@ -228,7 +228,7 @@ __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& 
 
 // a task that only runs physics (b2_physics_step / b2_forward on a model without task logic)
 struct NoTask {
-  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = -1;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
@@ -309,6 +309,9 @@ static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s
   CK(cudaGetLastError());
   return B2_OK;
 }
+#ifdef B2_ONLY_TASK      /* bring-up builds (tools/phase_timing.py, A/B experiments): one task's kernel only, compiles in a fraction of the time */
+#define B2_FOR_TASK(b, CALL) return CALL(B2_ONLY_TASK)
+#else
 #define B2_FOR_TASK(b, CALL) \
   switch ((b)->tp.task) { \
     case TASK_NONE: return CALL(NoTask); \
@@ -321,6 +324,7 @@ static int launch_task(B2Batch* b, int mode, const float* inject, cudaStream_t s
     case TASK_ROBOTIC_ARM_ASSEMBLY: return CALL(ArmTask); \
   } \
   return fail(B2_ERR_UNSUPPORTED, "unknown task id")
+#endif
 static int configure(B2Batch* b) {
 #define B2_CALL(T) configure_task<T>(b)
   B2_FOR_TASK(b, B2_CALL);

@@ -171,7 +171,8 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // from the model (physics-only batches).
 // C6: the model has condim-6 pairs (10-row pyramids: two tangential, one torsional, two rolling directions); otherwise every
 // contact is a 4-row pyramid and the row bookkeeping uses the cheaper fixed-size arithmetic.
-template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1, bool C6 = false>
+// TEAMND: Newton islands with more dofs than this are solved by the whole team, smaller ones by one warp each.
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1, bool C6 = false, int TEAMND = 16>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -1625,7 +1626,12 @@ struct Engine {
 #ifndef B2_NEWTON_GRADNOISE
 #define B2_NEWTON_GRADNOISE 1e-5f
 #endif
-  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
+  // H (packed lower triangle), nine vectors of nd, jv; islands solved by the whole team also keep a dense packed copy of their
+  // block of M (the sparse ancestor rows need shared-memory atomics to multiply by)
+  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) {
+    const int nh = r4(nd * (nd + 1) / 2);
+    return nh + ((W > 1 && nd > TEAMND) ? nh : 0) + 9 * r4(nd) + r4(n) + 8;
+  }
   // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
   // shared-memory atomics (one warp, <= a few hundred entries)
   __device__ __forceinline__ void newton_mulM(const Cols& cols, int nd, const float* x, float* y) {
@@ -1643,6 +1649,284 @@ struct Engine {
     }
     sync();
   }
+  // ---- team-wide Newton solve of one island (same mathematics and memory layout as the one-warp loop in solve_newton below).
+  // An env of the Newton tasks has one big island (the humanoid or the arm with whatever it touches, 30-99 dofs) beside a few
+  // 6-dof free bodies; with one warp per island two of the team's three warps sat at the closing barrier for 80 % of the pass
+  // (r02 profiles: stalled_barrier 7.7-11.7 per issue).  Here every phase of the iteration is spread over the team's threads:
+  // rows of J over threads, the Hessian's column pairs of a contact group over threads (each warp compacts the group's column
+  // list for itself), the Cholesky trailing update as rows over lanes x columns over warps, M s on warp 0 while the other
+  // warps form J s.  All exit tests use team-reduced values summed in a fixed order, so the control flow is team-uniform and
+  // the result does not depend on timing.  The triangular solves stay on warp 0 (a dependent chain).
+  // sums of two values over the team, same result in every thread; alternates between the two halves of `red` so that one
+  // barrier per call is enough (a half is rewritten only after the barrier of the following call)
+  __device__ __forceinline__ void team_sum2(float& x, float& y2, int& par) {
+    warp_sum2(x, y2);
+    float* r = p_red() + 8 * par; par ^= 1;
+    if (lane == 0) { r[2 * wl] = x; r[2 * wl + 1] = y2; }
+    team_sync();
+    x = r[0]; y2 = r[1];
+#pragma unroll
+    for (int q = 1; q < W; q++) { x += r[2 * q]; y2 += r[2 * q + 1]; }
+  }
+  __device__ __forceinline__ float team_max(float x, int& par) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x = fmaxf(x, __shfl_xor_sync(B2_FULL, x, o));
+    float* r = p_red() + 8 * par; par ^= 1;
+    if (lane == 0) r[2 * wl] = x;
+    team_sync();
+    x = r[0];
+#pragma unroll
+    for (int q = 1; q < W; q++) x = fmaxf(x, r[2 * q]);
+    return x;
+  }
+  // y = Md x for a dense packed lower triangle (one column per thread; the caller places the barriers)
+  __device__ __forceinline__ void team_mulMd(const float* Md, int nd, const float* x, float* y) {
+    for (int c = tl; c < nd; c += TEAM) {
+      const float* Mc = Md + c * (c + 1) / 2; float s0 = 0.f, s1 = 0.f;
+      int e = 0;
+      for (; e + 1 <= c; e += 2) { s0 = fmaf(Mc[e], x[e], s0); s1 = fmaf(Mc[e + 1], x[e + 1], s1); }
+      if (e <= c) s0 = fmaf(Mc[e], x[e], s0);
+      for (e = c + 1; e < nd; e++) s1 = fmaf(Md[e * (e + 1) / 2 + c], x[e], s1);
+      y[c] = s0 + s1;
+    }
+  }
+  template <bool WD> __device__ __forceinline__ int newton_island_team(int k, unsigned long long* counters) {
+    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
+    const int iters = dim(DD_iterations);
+    const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
+    const int n = p_isl_n()[k];
+    const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
+#ifdef B2_PHASE_TIMING
+    const long long tn0 = clock64(); long long tq = tn0;
+#define B2_NTT(slot) do { if (tl == 0 && B.phase_cycles) { const long long t_ = clock64(); atomicAdd(&B.phase_cycles[slot], (unsigned long long)(t_ - tq)); tq = t_; } } while (0)
+#else
+#define B2_NTT(slot) do { } while (0)
+#endif
+    const float* J = xs_J<WD>(k); const Cols cols = island_cols(k);
+    float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;
+    float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
+    float* wrm = y + ndp; float* jv = WD ? xs_J<WD>(k) + r4(n * ldj) : wrm + ndp;
+    float* Md = wrm + ndp + (WD ? 0 : r4(n));      // dense packed copy of the island's block of M
+    float* Dr = xs_row_R<WD>() + e0; float* aref = xs_row_res<WD>() + e0; float* jar = xs_row_f<WD>() + e0; const float* bb = xs_row_b<WD>() + e0;
+    int par = 0;
+    for (int c = tl; c < nd; c += TEAM) { int d = cols.dof(c); as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d]; }
+    for (int q = tl; q < nh; q += TEAM) Md[q] = 0.f;
+    team_sync();
+    for (int c = tl; c < nd; c += TEAM) {
+      int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
+      for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); Md[r * (r + 1) / 2 + cc] = p_M()[m0 + u]; }
+    }
+    for (int i = tl; i < n; i += TEAM) {
+      const float* Ji = J + i * ldj; float s = 0.f;
+      for (int c = 0; c < nd; c++) s = fmaf(Ji[c], as[c], s);
+      aref[i] = s - bb[i]; Dr[i] = fminf(1.0f / Dr[i], 1e8f);
+    }
+    for (int c = tl; c < nd; c += TEAM) y[c] = wrm[c] - as[c];
+    team_sync();
+    team_mulMd(Md, nd, y, Mv);
+    team_sync();
+    float cw = 0.f, cs = 0.f;
+    for (int i = tl; i < n; i += TEAM) {
+      const float* Ji = J + i * ldj; float sw = 0.f, ss = 0.f;
+      for (int c = 0; c < nd; c++) { sw = fmaf(Ji[c], wrm[c], sw); ss = fmaf(Ji[c], as[c], ss); }
+      sw -= aref[i]; ss -= aref[i];
+      if (sw < 0.f) cw += 0.5f * Dr[i] * sw * sw;
+      if (ss < 0.f) cs += 0.5f * Dr[i] * ss * ss;
+    }
+    for (int c = tl; c < nd; c += TEAM) cw += 0.5f * Mv[c] * y[c];
+    team_sum2(cw, cs, par);
+    for (int c = tl; c < nd; c += TEAM) a[c] = (cw < cs) ? wrm[c] : as[c];
+    team_sync();
+    team_mulMd(Md, nd, a, Ma);
+    team_sync();
+    B2_NTT(22);
+    int it = 0;
+    for (; it < iters; it++) {
+      for (int i = tl; i < n; i += TEAM) {
+        const float* Ji = J + i * ldj; float s = 0.f;
+        for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
+        jar[i] = s - aref[i];
+      }
+      team_sync();
+      float g2 = 0.f, nres = 0.f;
+      for (int c = tl; c < nd; c += TEAM) {
+        float g = Ma[c] - fs[c], sabs = fabsf(Ma[c]) + fabsf(fs[c]);
+        for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) { float t = J[i * ldj + c] * (Dr[i] * x); g += t; sabs += fabsf(t); } }
+        grad[c] = g; g2 = fmaf(g, g, g2);
+        if (fabsf(g) > B2_NEWTON_GRADNOISE * sabs) nres += 1.f;
+      }
+      team_sum2(g2, nres, par);
+      B2_NTT(23);
+      if (scale * sqrtf(g2) < tol) break;
+      if (nres == 0.f) break;      // every gradient entry below the rounding noise of its own terms (see the one-warp loop)
+      // H = M + J' diag(D active) J, lower triangle, one entry per thread.  The active rows' D goes to jv first (zero for the
+      // others; jv is free until the search direction exists), so the inner loop has no branch.
+      for (int i = tl; i < n; i += TEAM) jv[i] = jar[i] < 0.f ? Dr[i] : 0.f;
+      team_sync();
+      for (int q = tl; q < nh; q += TEAM) {
+        int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+        while (r * (r + 1) / 2 > q) r--;
+        while ((r + 1) * (r + 2) / 2 <= q) r++;
+        const int c = q - r * (r + 1) / 2; float h0 = Md[q], h1 = 0.f;
+        const float* Jr = J + r; const float* Jc = J + c;
+        int i = 0;
+        for (; i + 1 < n; i += 2) {
+          h0 = fmaf(Jr[i * ldj] * jv[i], Jc[i * ldj], h0); h1 = fmaf(Jr[(i + 1) * ldj] * jv[i + 1], Jc[(i + 1) * ldj], h1);
+        }
+        if (i < n) h0 = fmaf(Jr[i * ldj] * jv[i], Jc[i * ldj], h0);
+        H[q] = h0 + h1;
+      }
+      team_sync();
+      B2_NTT(24);
+      for (int c = tl; c < nd; c += TEAM) Mv[c] = rsqrtf(fmaxf(H[c * (c + 1) / 2 + c], 1e-30f));   // Mv doubles as the scale vector here
+      team_sync();
+      for (int r = wl; r < nd; r += W) { float sr = Mv[r]; float* Hr = H + r * (r + 1) / 2; for (int c = lane; c <= r; c += 32) Hr[c] *= sr * Mv[c]; }
+      team_sync();
+      B2_NTT(25);
+      // Cholesky H = L L' in place, right-looking in panels of four pivots: every thread factors the panel's 4 x 4 diagonal block
+      // for itself (ten broadcast loads), rows below the panel are solved against it one row per thread in registers, and the
+      // trailing update subtracts four rank-one terms per entry (rows over lanes, columns over warps).  Two barriers per panel
+      // instead of two per pivot; reciprocal pivots go to wrm as in the one-warp loop.
+      for (int p0 = 0; p0 < nd; p0 += 4) {
+        const int b = min(4, nd - p0);
+        const float* D0 = H + p0 * (p0 + 1) / 2 + p0; const float* D1 = D0 + p0 + 1; const float* D2 = D1 + p0 + 2; const float* D3 = D2 + p0 + 3;
+        const float i00 = rsqrtf(fmaxf(D0[0], 1e-7f));
+        float l10 = 0.f, l20 = 0.f, l21 = 0.f, l30 = 0.f, l31 = 0.f, l32 = 0.f, i11 = 1.f, i22 = 1.f, i33 = 1.f;
+        if (b > 1) { l10 = D1[0] * i00; i11 = rsqrtf(fmaxf(fmaf(-l10, l10, D1[1]), 1e-7f)); }
+        if (b > 2) { l20 = D2[0] * i00; l21 = fmaf(-l20, l10, D2[1]) * i11; i22 = rsqrtf(fmaxf(fmaf(-l21, l21, fmaf(-l20, l20, D2[2])), 1e-7f)); }
+        if (b > 3) {
+          l30 = D3[0] * i00; l31 = fmaf(-l30, l10, D3[1]) * i11; l32 = fmaf(-l31, l21, fmaf(-l30, l20, D3[2])) * i22;
+          i33 = rsqrtf(fmaxf(fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, D3[3]))), 1e-7f));
+        }
+        for (int i = p0 + b + tl; i < nd; i += TEAM) {
+          float* Hi = H + i * (i + 1) / 2 + p0;
+          const float x0 = Hi[0] * i00; Hi[0] = x0;
+          if (b > 1) { const float x1 = fmaf(-x0, l10, Hi[1]) * i11; Hi[1] = x1;
+            if (b > 2) { const float x2 = fmaf(-x1, l21, fmaf(-x0, l20, Hi[2])) * i22; Hi[2] = x2;
+              if (b > 3) { Hi[3] = fmaf(-x2, l32, fmaf(-x1, l31, fmaf(-x0, l30, Hi[3]))) * i33; } } }
+        }
+        team_sync();      // panel rows are final, and everyone has read the diagonal block: its factor may replace it now
+        if (tl == 0) {
+          wrm[p0] = i00;
+          if (b > 1) { wrm[p0 + 1] = i11; const_cast<float*>(D1)[0] = l10; }
+          if (b > 2) { wrm[p0 + 2] = i22; const_cast<float*>(D2)[0] = l20; const_cast<float*>(D2)[1] = l21; }
+          if (b > 3) { wrm[p0 + 3] = i33; const_cast<float*>(D3)[0] = l30; const_cast<float*>(D3)[1] = l31; const_cast<float*>(D3)[2] = l32; }
+        }
+        if (b == 4) {
+          for (int i = p0 + 4 + lane; i < nd; i += 32) {
+            float* Hi = H + i * (i + 1) / 2; const float a0 = Hi[p0], a1 = Hi[p0 + 1], a2 = Hi[p0 + 2], a3 = Hi[p0 + 3];
+#pragma unroll 2
+            for (int c = p0 + 4 + wl; c <= i; c += W) {
+              const float* Hc = H + c * (c + 1) / 2 + p0;
+              Hi[c] = fmaf(-a3, Hc[3], fmaf(-a2, Hc[2], fmaf(-a1, Hc[1], fmaf(-a0, Hc[0], Hi[c]))));
+            }
+          }
+        }
+        team_sync();      // the trailing update reaches the next panel's diagonal block (a shorter last panel has no rows below it)
+      }
+      B2_NTT(26);
+      if (wl == 0) {
+        // search = -H^-1 grad on warp 0, unknowns in registers (lane owns rows lane, lane + 32, ...): a step is one shuffle,
+        // one multiply by the reciprocal pivot and the lane's own multiply-adds; the column of L is loaded ahead of the chain
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = lane + 32 * u; v[u] = i < nd ? -grad[i] * Mv[i] : 0.f; }
+#pragma unroll
+        for (int ub = 0; ub < 4; ub++) {
+          if (32 * ub < nd) {
+            const int rend = min(32, nd - 32 * ub);
+            for (int rr = 0; rr < rend; rr++) {
+              const int r = 32 * ub + rr;
+              float hcol[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) { const int i = lane + 32 * u; hcol[u] = (u >= ub && i > r && i < nd) ? H[i * (i + 1) / 2 + r] : 0.f; }
+              const float zr = __shfl_sync(B2_FULL, v[ub], rr) * wrm[r];
+              if (lane == rr) v[ub] = zr;
+#pragma unroll
+              for (int u = 0; u < 4; u++) if (u >= ub) v[u] = fmaf(-hcol[u], zr, v[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int ub = 3; ub >= 0; ub--) {
+          if (32 * ub < nd) {
+            const int rend = min(32, nd - 32 * ub);
+            for (int rr = rend - 1; rr >= 0; rr--) {
+              const int r = 32 * ub + rr; const float* Hr = H + r * (r + 1) / 2;
+              float hrow[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) { const int i = lane + 32 * u; hrow[u] = (u <= ub && i < r) ? Hr[i] : 0.f; }
+              const float xr = __shfl_sync(B2_FULL, v[ub], rr) * wrm[r];
+              if (lane == rr) v[ub] = xr;
+#pragma unroll
+              for (int u = 0; u < 4; u++) if (u <= ub) v[u] = fmaf(-hrow[u], xr, v[u]);
+            }
+          }
+        }
+        // undo the scaling, s = S (S H S)^-1 S (-g); y <- fp32 noise floor of each acceleration, (|f_smooth| + |M a|) / H_cc
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int c = lane + 32 * u; if (c < nd) { const float sc = Mv[c]; srch[c] = v[u] * sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); } }
+      }
+      team_sync();
+      B2_NTT(27);
+      // M s and J s, then the two quadratic coefficients of the smooth part
+      team_mulMd(Md, nd, srch, Mv);
+      for (int i = tl; i < n; i += TEAM) {
+        const float* Ji = J + i * ldj; float sj = 0.f;
+        for (int c = 0; c < nd; c++) sj = fmaf(Ji[c], srch[c], sj);
+        jv[i] = sj;
+      }
+      float q1 = 0.f, q2 = 0.f;
+      for (int c = tl; c < nd; c += TEAM) { q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], Mv[c], q2); }      // own column of Mv
+      team_sum2(q1, q2, par);
+      B2_NTT(28);
+      // exact minimisation along the search direction (same safeguarded Newton on the slope as the one-warp loop)
+      float alpha = 0.f, lo = 0.f, hi = -1.f;
+      for (int ls = 0; ls < 40; ls++) {
+        float d1 = 0.f, d2 = 0.f, dn = 0.f;
+        for (int i = tl; i < n; i += TEAM) { float x = fmaf(alpha, jv[i], jar[i]); if (x < 0.f) { float t = Dr[i] * jv[i]; d1 = fmaf(t, x, d1); d2 = fmaf(t, jv[i], d2); dn += fabsf(t * x); } }
+        team_sum2(d1, d2, par);
+        if (ls == 0) { float z = 0.f; team_sum2(dn, z, par); }
+        d1 += q1 + alpha * q2; d2 += q2;
+        if (ls == 0 && fabsf(d1) <= 2.4e-7f * (dn + fabsf(q1))) { alpha = 1.0f; break; }
+        if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
+        if (d1 < 0.f) lo = alpha; else hi = alpha;
+        if (!(d2 > 0.f)) break;
+        float na = alpha - d1 / d2;
+        if (hi > 0.f && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+        if (na < 0.f) na = 0.f;
+        bool done = fabsf(na - alpha) < 1e-7f * (1.0f + fabsf(alpha));
+        alpha = na;
+        if (done) break;
+      }
+      B2_NTT(29);
+      float amx = B2_NEWTON_AFLOOR;
+      for (int c = tl; c < nd; c += TEAM) { a[c] = fmaf(alpha, srch[c], a[c]); Ma[c] = fmaf(alpha, Mv[c], Ma[c]); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
+      amx = team_max(amx, par);
+      float nmov = 0.f, z = 0.f;
+      for (int c = tl; c < nd; c += TEAM) if (fabsf(alpha * srch[c]) > fmaf(B2_NEWTON_RTOL, amx, B2_NEWTON_NOISE * y[c])) nmov += 1.f;
+      team_sum2(nmov, z, par);
+      B2_NTT(30);
+      if (nmov == 0.f) { it++; break; }
+    }
+    team_sync();
+    for (int i = tl; i < n; i += TEAM) {
+      const float* Ji = J + i * ldj; float s = 0.f;
+      for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
+      s -= aref[i];
+      jar[i] = s < 0.f ? -Dr[i] * s : 0.f;
+    }
+    for (int c = tl; c < nd; c += TEAM) y[c] = a[c] - as[c];
+    team_sync();
+    team_mulMd(Md, nd, y, Mv);
+    for (int c = tl; c < nd; c += TEAM) { int d = cols.dof(c); p_qfc()[d] = Mv[c]; p_qacc()[d] = Mv[c]; }      // own column of Mv
+    if (it >= iters && tl == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
+    B2_NTT(31);
+#ifdef B2_PHASE_TIMING
+    if (tl == 0 && B.phase_cycles) { atomicAdd(&B.phase_cycles[20], 1ull); atomicAdd(&B.phase_cycles[21], (unsigned long long)it); }
+#endif
+    return it;
+  }
   template <bool WD> __device__ __forceinline__ void solve_newton(unsigned long long* counters) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
@@ -1651,8 +1935,14 @@ struct Engine {
     for (int k = 0; k < nisl; k++) {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
+      if (W > 1 && nd > TEAMND) continue;      // solved by the whole team, below
 #ifdef B2_PHASE_TIMING
-      const long long tn0 = clock64();
+      const long long tn0 = clock64(); long long tq = tn0; const bool tbig = nd > 8;
+      // islands above 8 dofs by phase: [22] setup, [23] J a + gradient, [24] H build, [25] + M and scaling, [26] Cholesky, [27] triangular solves,
+      // [28] M s, J s, [29] line search, [30] update and exit tests, [31] finish
+#define B2_NT(slot) do { if (tbig && lane == 0 && B.phase_cycles) { const long long t_ = clock64(); atomicAdd(&B.phase_cycles[slot], (unsigned long long)(t_ - tq)); tq = t_; } } while (0)
+#else
+#define B2_NT(slot) do { } while (0)
 #endif
       const float* J = xs_J<WD>(k); const Cols cols = island_cols(k);       // wide: J (plain rows) and jv in the global workspace, H on chip
       float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;   // H: packed lower triangle
@@ -1685,6 +1975,7 @@ struct Engine {
       for (int c = lane; c < nd; c += 32) a[c] = (cw < cs) ? wrm[c] : as[c];
       sync();
       newton_mulM(cols, nd, a, Ma);
+      B2_NT(22);
       int it = 0;
       for (; it < iters; it++) {
         for (int i = lane; i < n; i += 32) {
@@ -1701,6 +1992,7 @@ struct Engine {
           resolved |= fabsf(g) > B2_NEWTON_GRADNOISE * sabs;
         }
         g2 = warp_sum(g2);
+        B2_NT(23);
         if (scale * sqrtf(g2) < tol) break;
         // every gradient entry is below the rounding noise of its own terms: the Newton step it would produce is below the
         // step-size criterion at the end of the loop, so the factorisation is skipped (typically the second one of a solve)
@@ -1763,6 +2055,7 @@ struct Engine {
           }
           sync();
         }
+        B2_NT(24);
         for (int c = lane; c < nd; c += 32) {
           int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
           for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); H[r * (r + 1) / 2 + cc] += p_M()[m0 + u]; }
@@ -1772,6 +2065,7 @@ struct Engine {
         sync();
         for (int r = 0; r < nd; r++) { float sr = Mv[r]; float* Hr = H + r * (r + 1) / 2; for (int c = lane; c <= r; c += 32) Hr[c] *= sr * Mv[c]; }
         sync();
+        B2_NT(25);
         // Cholesky H = L L' in place (right-looking; lanes over the rows below the pivot).  The reciprocal pivots go to wrm
         // (the warm start is not needed once the iteration has begun), so a pivot costs one rsqrt and two warp barriers and
         // the triangular solves below multiply instead of dividing
@@ -1787,6 +2081,7 @@ struct Engine {
             for (int c = p + 1; c <= i; c++) Hi[c] = fmaf(-lip, H[c * (c + 1) / 2 + p], Hi[c]);
           }
         }
+        B2_NT(26);
         // search = -H^-1 grad: L z = -S grad, L' x = z, both column-oriented (once an unknown is final every lane subtracts
         // its multiple from the entries it owns): one warp barrier per pivot and no reductions.  z lives in srch, x in y.
         for (int c = lane; c < nd; c += 32) y[c] = -grad[c] * Mv[c];
@@ -1804,6 +2099,7 @@ struct Engine {
           for (int i = lane; i < r; i += 32) srch[i] = fmaf(-Hr[i], xr, srch[i]);
         }
         sync();
+        B2_NT(27);
         // undo the scaling, s = S (S H S)^-1 S (-g); y <- fp32 noise floor of each acceleration, (|f_smooth| + |M a|) / H_cc
         for (int c = lane; c < nd; c += 32) { float sc = Mv[c]; srch[c] = y[c] * sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); }
         sync();
@@ -1817,6 +2113,7 @@ struct Engine {
         }
         warp_sum2(q1, q2);
         sync();
+        B2_NT(28);
         // exact minimisation along the search direction
         float alpha = 0.f, lo = 0.f, hi = -1.f;
         for (int ls = 0; ls < 40; ls++) {
@@ -1837,6 +2134,7 @@ struct Engine {
           alpha = na;
           if (done) break;
         }
+        B2_NT(29);
         // fp32 termination: no acceleration moves by more than 1e-5 of the island's largest one plus its own rounding
         // floor (the gradient test above cannot fire once the stiff rows' rounding noise exceeds the tolerance)
         float amx = B2_NEWTON_AFLOOR;
@@ -1850,6 +2148,7 @@ struct Engine {
 #ifdef B2_NEWTON_DEBUG
         if (it >= iters - 6 && lane == 0) printf("newton blk %d wb %d isl %d nd %d n %d it %d |g| %.4g alpha %.6g amx %.4g q1 %.4g q2 %.4g\n", (int)blockIdx.x, wb, k, nd, n, it, sqrtf(g2), alpha, amx, q1, q2);
 #endif
+        B2_NT(30);
         if (!moving) { it++; break; }
       }
       // efc_force at the solution (reporting only: a stiff row's force is below fp32 resolution of J a - aref).  The
@@ -1868,13 +2167,20 @@ struct Engine {
       sync();
       if (it >= iters && lane == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
 #ifdef B2_PHASE_TIMING
-      if (lane == 0 && B.phase_cycles) {      // Newton solves by island size class: [20..23] <= 8 dofs, [24..27] <= 40, [28..31] larger: solves, iterations, rows, cycles
-        const int cls = nd <= 8 ? 20 : nd <= 40 ? 24 : 28;
-        atomicAdd(&B.phase_cycles[cls], 1ull); atomicAdd(&B.phase_cycles[cls + 1], (unsigned long long)it);
-        atomicAdd(&B.phase_cycles[cls + 2], (unsigned long long)n); atomicAdd(&B.phase_cycles[cls + 3], (unsigned long long)(clock64() - tn0));
+      B2_NT(31);
+      if (lane == 0 && B.phase_cycles) {      // [16..19] islands <= 8 dofs: solves, iterations, rows, cycles; [20] [21] larger islands: solves, iterations
+        if (!tbig) {
+          atomicAdd(&B.phase_cycles[16], 1ull); atomicAdd(&B.phase_cycles[17], (unsigned long long)it);
+          atomicAdd(&B.phase_cycles[18], (unsigned long long)n); atomicAdd(&B.phase_cycles[19], (unsigned long long)(clock64() - tn0));
+        } else { atomicAdd(&B.phase_cycles[20], 1ull); atomicAdd(&B.phase_cycles[21], (unsigned long long)it); }
       }
 #endif
       itmax = max(itmax, it);
+    }
+    if (W > 1) {
+      for (int k = 0; k < nisl; k++)
+        if (p_isl_n()[k] && p_isl_nd()[k] > TEAMND) itmax = max(itmax, newton_island_team<WD>(k, counters));
+      team_sync();
     }
     if (lane == 0) p_red()[wl] = (float)itmax;
     team_sync();

@@ -32,7 +32,7 @@ struct TaskParams {
 // ids: [0] torso body, [1..4] foot bodies, [5] platform_slide joint id, [6] pendulum_swing joint id,
 //      [7] platform_motor actuator id, [8] pendulum_motor actuator id
 struct QuadrupedTask {
-  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 48, ARENA_SPAN = 0, MAX_EPB = 4, EPISODE_SLOT = 4, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 48, ARENA_SPAN = 0, MAX_EPB = 4, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
 
@@ -173,7 +173,7 @@ struct QuadrupedTask {
 //     [13..15] xpos[torso] of the last forward pass [16..35] move durations [36..58] prev_joint_vel = qvel[6:]
 // ids: [0] torso body [1] right_foot geom [2] left_foot geom [3] dance_floor geom [4] stage geom
 struct DancingTask {
-  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 5, EPISODE_SLOT = 4, LOCKSTEP = 1, ARENA_FLOATS = 0;
+  static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 5, EPISODE_SLOT = 4, LOCKSTEP = 1, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
@@ -357,7 +357,7 @@ struct DancingTask {
 //      [9] goalkeeper_y joint [10] ball_joint [11] first body of the torso subtree [12] bodies in it
 // inject: robot_x, robot_y, angle, 29 joint noises, goalkeeper_y, wind_strength, wind_angle, friction variation (unused)
 struct SoccerTask {
-  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
   static constexpr int NJOINT = 29, NOBSJ = 25;
@@ -530,7 +530,7 @@ struct SoccerTask {
 //      (26 consecutive) [4] victim1_x joint (victim joints are 6 apart, y = x + 1)
 // inject: robot_x, robot_y, then (x_offset, y_offset) for the five victims
 struct RescueTask {
-  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, ARENA_FLOATS = 7400;
+  static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 7400;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
   static constexpr int NVICT = 5;
@@ -686,7 +686,7 @@ struct RescueTask {
 // tf: [0] total_reward [1] task_progress [2] wind_strength [3] rain_intensity [4] temperature
 // ids: [0] humanoid body      inject: task index, wind, rain, temperature
 struct ConstructionTask {
-  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 2, LOCKSTEP = 0, ARENA_FLOATS = 6000;
+  static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 2, EPISODE_SLOT = 2, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 14000;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 
@@ -766,8 +766,11 @@ struct ConstructionTask {
 // ti: [0] current_step [1] techniques_performed [2] episode id [3] falls
 // tf: [0] total reward [1] stance_stability_time
 // ids: [0] torso [1] right_hand [2] left_hand [3] right_ankle [4] left_ankle [5] dummy1 [6] dummy2     inject: dx, dy
+#ifndef B2_MARTIAL_EPB
+#define B2_MARTIAL_EPB 2      // teams per SM (A/B on B200 with the team-wide Newton solve: 2 -> 969 k, 3 -> 897 k env-steps/s)
+#endif
 struct MartialArtsTask {
-  static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 80, ARENA_SPAN = 47, MAX_EPB = 3, EPISODE_SLOT = 2, LOCKSTEP = 0, ARENA_FLOATS = 0;
+  static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 80, ARENA_SPAN = 47, MAX_EPB = B2_MARTIAL_EPB, EPISODE_SLOT = 2, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
   static constexpr bool CONDIM6 = false, RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
 
@@ -849,8 +852,11 @@ struct MartialArtsTask {
 //     2 transport 4 insert) [5..13] component status (0 in_bin 1 held 2 assembled 3 dropped)
 // tf: [0] cumulative_reward
 // ids: [0..8] component bodies in assembly order, [9] body of ee_site    aux_f: [3k..3k+2] target of component k, [27..29] ee_site offset
+#ifndef B2_ARM_TEAM_ND
+#define B2_ARM_TEAM_ND (1 << 20)      // the arm's islands are the 9-dof arm plus the 6-dof parts it touches: one warp each (A/B below)
+#endif
 struct ArmTask {
-  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 4, EPISODE_SLOT = 2, LOCKSTEP = 1, ARENA_FLOATS = 4000;
+  static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 4, EPISODE_SLOT = 2, LOCKSTEP = 1, NEWTON_TEAM_ND = B2_ARM_TEAM_ND, ARENA_FLOATS = 4000;
   static constexpr int SOLVER = 2;
   static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
 

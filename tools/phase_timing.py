@@ -33,9 +33,13 @@ print(task, "N", N, "scale", scale, "envs/cta", env.batch.envs_per_block, "smem"
 nw = max(out[15], 1)
 print(f"wide PGS solves {out[15]}: rows/solve {out[8]/nw:.0f} iters/solve {out[7]/nw:.1f} ring depth {out[14]/nw:.1f}; cycles/solve: B build+records {out[4]/nw:.0f}, init (v, cost) {out[5]/nw:.0f}, sweeps {out[6]/nw:.0f}")
 print(f"  ring waits {out[17]} ({out[17]/nw:.0f}/solve): {out[16]/max(out[17],1):.0f} cycles each; warp-0 time at the per-iteration team barrier {out[18]/nw:.0f} cycles/solve")
-for name, c in (("<= 8 dofs", 20), ("9-40 dofs", 24), ("> 40 dofs", 28)):
-    if out[c]:
-        print(f"  Newton islands {name}: {out[c]} solves ({out[c]/max(st['substeps'],1):.1f}/substep), {out[c+1]/out[c]:.2f} iterations, {out[c+2]/out[c]:.0f} rows, {out[c+3]/out[c]:.0f} cycles each = {out[c+3]/max(st['substeps'],1):.0f} cycles/substep")
+if out[16]:
+    print(f"  Newton islands <= 8 dofs: {out[16]} solves ({out[16]/max(st['substeps'],1):.1f}/substep), {out[17]/out[16]:.2f} iterations, {out[18]/out[16]:.0f} rows, {out[19]/out[16]:.0f} cycles each")
+if out[20]:
+    nb = out[20]; tb = sum(out[22:32])
+    print(f"  Newton islands > 8 dofs: {nb} solves ({nb/max(st['substeps'],1):.2f}/substep), {out[21]/nb:.2f} iterations, {tb/nb:.0f} cycles each:")
+    for nm, c in (("setup", 22), ("J a + gradient", 23), ("H build", 24), ("+ M, scaling", 25), ("Cholesky", 26), ("triangular solves", 27), ("M s, J s", 28), ("line search", 29), ("update, exit tests", 30), ("finish", 31)):
+        print(f"     {nm:20s} {100*out[c]/tb:5.1f}%  {out[c]/nb:9.0f} cycles/solve")
 out = list(out); out[4] = out[5] = out[6] = out[7] = out[8] = 0
 for n, v in zip(names, out[:14]):
     print(f"{n:32s} {100*v/tot:5.1f}%  {v/max(st['substeps'],1):10.0f} cycles/substep")
