@@ -1626,29 +1626,9 @@ struct Engine {
 #ifndef B2_NEWTON_GRADNOISE
 #define B2_NEWTON_GRADNOISE 1e-5f
 #endif
-  // H (packed lower triangle), nine vectors of nd, jv; islands solved by the whole team also keep a dense packed copy of their
-  // block of M (the sparse ancestor rows need shared-memory atomics to multiply by)
-  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) {
-    const int nh = r4(nd * (nd + 1) / 2);
-    return nh + ((W > 1 && nd > TEAMND) ? nh : 0) + 9 * r4(nd) + r4(n) + 8;
-  }
-  // y = M x over one island's columns; M stays in its sparse per-dof ancestor rows, the symmetric half is scattered with
-  // shared-memory atomics (one warp, <= a few hundred entries)
-  __device__ __forceinline__ void newton_mulM(const Cols& cols, int nd, const float* x, float* y) {
-    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
-    for (int c = lane; c < nd; c += 32) y[c] = 0.f;
-    sync();
-    for (int c = lane; c < nd; c += 32) {
-      int d = cols.dof(c), m0 = madr[d], dep = ddepth[d]; float xc = x[c], s = 0.f;
-      for (int u = 0; u <= dep; u++) {
-        int ca = p_dof_col()[mcol[m0 + u]]; float v = p_M()[m0 + u];
-        s = fmaf(v, x[ca], s);
-        if (ca != c) atomicAdd(&y[ca], v * xc);
-      }
-      atomicAdd(&y[c], s);
-    }
-    sync();
-  }
+  // H and a dense copy of the island's block of M (packed lower triangles: multiplying by the sparse ancestor rows of M needs
+  // shared-memory atomics), nine vectors of nd, jv
+  __host__ __device__ __forceinline__ static int newton_floats(int n, int nd) { return 2 * r4(nd * (nd + 1) / 2) + 9 * r4(nd) + r4(n) + 8; }
   // ---- team-wide Newton solve of one island (same mathematics and memory layout as the one-warp loop in solve_newton below).
   // An env of the Newton tasks has one big island (the humanoid or the arm with whatever it touches, 30-99 dofs) beside a few
   // 6-dof free bodies; with one warp per island two of the team's three warps sat at the closing barrier for 80 % of the pass
@@ -1678,6 +1658,16 @@ struct Engine {
 #pragma unroll
     for (int q = 1; q < W; q++) x = fmaxf(x, r[2 * q]);
     return x;
+  }
+  // y = Md x on one warp (lanes over columns); closes with a warp barrier
+  __device__ __forceinline__ void warp_mulMd(const float* Md, int nd, const float* x, float* y) {
+    for (int c = lane; c < nd; c += 32) {
+      const float* Mc = Md + c * (c + 1) / 2; float s0 = 0.f, s1 = 0.f;
+      for (int e = 0; e <= c; e++) s0 = fmaf(Mc[e], x[e], s0);
+      for (int e = c + 1; e < nd; e++) s1 = fmaf(Md[e * (e + 1) / 2 + c], x[e], s1);
+      y[c] = s0 + s1;
+    }
+    sync();
   }
   // y = Md x for a dense packed lower triangle (one column per thread; the caller places the barriers)
   __device__ __forceinline__ void team_mulMd(const float* Md, int nd, const float* x, float* y) {
@@ -1745,13 +1735,16 @@ struct Engine {
       for (int i = tl; i < n; i += TEAM) {
         const float* Ji = J + i * ldj; float s = 0.f;
         for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
-        jar[i] = s - aref[i];
+        s -= aref[i];
+        jar[i] = s; jv[i] = s < 0.f ? Dr[i] : 0.f;      // D of the active rows, zero for the others (jv is free until the search direction exists)
       }
       team_sync();
       float g2 = 0.f, nres = 0.f;
       for (int c = tl; c < nd; c += TEAM) {
         float g = Ma[c] - fs[c], sabs = fabsf(Ma[c]) + fabsf(fs[c]);
-        for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) { float t = J[i * ldj + c] * (Dr[i] * x); g += t; sabs += fabsf(t); } }
+        const float* Jc = J + c;
+#pragma unroll 4
+        for (int i = 0; i < n; i++) { const float t = Jc[i * ldj] * (jv[i] * jar[i]); g += t; sabs += fabsf(t); }
         grad[c] = g; g2 = fmaf(g, g, g2);
         if (fabsf(g) > B2_NEWTON_GRADNOISE * sabs) nres += 1.f;
       }
@@ -1759,10 +1752,8 @@ struct Engine {
       B2_NTT(23);
       if (scale * sqrtf(g2) < tol) break;
       if (nres == 0.f) break;      // every gradient entry below the rounding noise of its own terms (see the one-warp loop)
-      // H = M + J' diag(D active) J, lower triangle, one entry per thread.  The active rows' D goes to jv first (zero for the
-      // others; jv is free until the search direction exists), so the inner loop has no branch.
-      for (int i = tl; i < n; i += TEAM) jv[i] = jar[i] < 0.f ? Dr[i] : 0.f;
-      team_sync();
+      // H = M + J' diag(D active) J, lower triangle, one entry per thread; jv holds D of the active rows and zero for the
+      // others, so the inner loop has no branch
       for (int q = tl; q < nh; q += TEAM) {
         int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
         while (r * (r + 1) / 2 > q) r--;
@@ -1927,6 +1918,174 @@ struct Engine {
 #endif
     return it;
   }
+  // ---- Newton solve of a free body's island (<= 6 dofs, <= 32 rows) in registers: lane i owns row i of J, the island's
+  // vectors are replicated in every lane, sums over rows are warp butterflies, and the 6 x 6 Hessian is factored by every lane
+  // for itself.  Same mathematics and exit tests as the loop in solve_newton; no shared-memory round trips or warp barriers
+  // inside the iteration (the generic loop spends ~30 k cycles on such an island, nearly all of it latency between its many
+  // short phases).  Shared memory holds only the dense block of M (in the island's H slot) and the rows' inputs / outputs.
+  template <bool WD> __device__ __forceinline__ int newton_island_small(int k, unsigned long long* counters) {
+    constexpr int ND = 6;
+    const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
+    const int iters = dim(DD_iterations);
+    const float scale = P.opt[DO_pgs_scale], tol = P.opt[DO_tolerance];
+    const int n = p_isl_n()[k], nd = p_isl_nd()[k], ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
+    const float* J = xs_J<WD>(k); const Cols cols = island_cols(k);
+    float* Md = island_A(k);
+    float* Dr = xs_row_R<WD>() + e0; float* jar = xs_row_f<WD>() + e0; const float* bb = xs_row_b<WD>() + e0;
+    const bool row = lane < n;
+    for (int q = lane; q < nh; q += 32) Md[q] = 0.f;
+    sync();
+    if (lane < nd) {
+      int d = cols.dof(lane), m0 = madr[d], dep = ddepth[d];
+      for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(lane, ca), cc = min(lane, ca); Md[r * (r + 1) / 2 + cc] = p_M()[m0 + u]; }
+    }
+    float Jr[ND], as[ND], fs[ND], a[ND], Ma[ND], wr[ND];
+#pragma unroll
+    for (int c = 0; c < ND; c++) {
+      const bool on = c < nd; const int d = on ? cols.dof(c) : 0;
+      Jr[c] = (row && on) ? J[lane * ldj + c] : 0.f;
+      as[c] = on ? p_qas()[d] : 0.f; fs[c] = on ? p_qfs()[d] : 0.f; wr[c] = on ? p_warm()[d] : 0.f;
+    }
+    const float Dl = row ? fminf(1.0f / Dr[lane], 1e8f) : 0.f;
+    sync();
+    // y = Md x: lane c forms entry c, then every lane collects all of them
+    auto mulM = [&](const float (&x)[ND], float (&y)[ND]) {
+      float yc = 0.f;
+      if (lane < nd) {
+#pragma unroll
+        for (int e = 0; e < ND; e++) if (e < nd) { const int r = max(lane, e), cc = min(lane, e); yc = fmaf(Md[r * (r + 1) / 2 + cc], x[e], yc); }
+      }
+#pragma unroll
+      for (int c = 0; c < ND; c++) y[c] = __shfl_sync(B2_FULL, yc, c);
+    };
+    auto rowdot = [&](const float (&x)[ND]) { float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < ND; c++) s = fmaf(Jr[c], x[c], s);
+      return s; };
+    const float aref = rowdot(as) - (row ? bb[lane] : 0.f);
+    {
+      float y[ND], My[ND];
+#pragma unroll
+      for (int c = 0; c < ND; c++) y[c] = wr[c] - as[c];
+      mulM(y, My);
+      const float sw = rowdot(wr) - aref, ss = rowdot(as) - aref;
+      float cw = (row && sw < 0.f) ? 0.5f * Dl * sw * sw : 0.f, cs = (row && ss < 0.f) ? 0.5f * Dl * ss * ss : 0.f;
+      warp_sum2(cw, cs);
+#pragma unroll
+      for (int c = 0; c < ND; c++) cw = fmaf(0.5f * My[c], y[c], cw);
+#pragma unroll
+      for (int c = 0; c < ND; c++) a[c] = (cw < cs) ? wr[c] : as[c];
+    }
+    mulM(a, Ma);
+    float jr = 0.f;
+    int it = 0;
+    for (; it < iters; it++) {
+      jr = rowdot(a) - aref;
+      const bool act = row && jr < 0.f;
+      const float t = act ? Dl * jr : 0.f, w = act ? Dl : 0.f;
+      float grad[ND]; float g2 = 0.f; bool resolved = false;
+#pragma unroll
+      for (int c = 0; c < ND; c++) {
+        float g = Jr[c] * t, sa = fabsf(g);
+        warp_sum2(g, sa);
+        g += Ma[c] - fs[c]; sa += fabsf(Ma[c]) + fabsf(fs[c]);
+        grad[c] = g; g2 = fmaf(g, g, g2);
+        resolved |= c < nd && fabsf(g) > B2_NEWTON_GRADNOISE * sa;
+      }
+      if (scale * sqrtf(g2) < tol) break;
+      if (!resolved) break;
+      // H = M + J' diag(D active) J (all lanes hold all of it), scaled to a unit diagonal, Cholesky in registers
+      float H[ND][ND], sc[ND], ip[ND];
+#pragma unroll
+      for (int r = 0; r < ND; r++) {
+#pragma unroll
+        for (int c = 0; c <= r; c++) {
+          float h = 0.f;
+          if (r < nd) { h = w * Jr[r] * Jr[c]; h = warp_sum(h) + Md[r * (r + 1) / 2 + c]; }
+          H[r][c] = h;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < ND; c++) sc[c] = c < nd ? rsqrtf(fmaxf(H[c][c], 1e-30f)) : 1.f;
+#pragma unroll
+      for (int r = 0; r < ND; r++) {
+#pragma unroll
+        for (int c = 0; c <= r; c++) H[r][c] = r < nd ? H[r][c] * sc[r] * sc[c] : (r == c ? 1.f : 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < ND; p++) {
+        const float inv = rsqrtf(fmaxf(H[p][p], 1e-7f)); ip[p] = inv;
+#pragma unroll
+        for (int i = p + 1; i < ND; i++) H[i][p] *= inv;
+#pragma unroll
+        for (int i = p + 1; i < ND; i++) {
+#pragma unroll
+          for (int c = p + 1; c <= i; c++) H[i][c] = fmaf(-H[i][p], H[c][p], H[i][c]);
+        }
+      }
+      float x[ND];
+#pragma unroll
+      for (int c = 0; c < ND; c++) x[c] = -grad[c] * sc[c];
+#pragma unroll
+      for (int r = 0; r < ND; r++) {
+        x[r] *= ip[r];
+#pragma unroll
+        for (int i = r + 1; i < ND; i++) x[i] = fmaf(-H[i][r], x[r], x[i]);
+      }
+#pragma unroll
+      for (int r = ND - 1; r >= 0; r--) {
+        x[r] *= ip[r];
+#pragma unroll
+        for (int i = 0; i < r; i++) x[i] = fmaf(-H[r][i], x[r], x[i]);
+      }
+      float srch[ND], Mv[ND], noise[ND];
+#pragma unroll
+      for (int c = 0; c < ND; c++) { srch[c] = c < nd ? x[c] * sc[c] : 0.f; noise[c] = sc[c] * sc[c] * (fabsf(fs[c]) + fabsf(Ma[c])); }
+      mulM(srch, Mv);
+      float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < ND; c++) { q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], Mv[c], q2); }
+      const float jvl = rowdot(srch), tj = Dl * jvl;
+      float alpha = 0.f, lo = 0.f, hi = -1.f;
+      for (int ls = 0; ls < 40; ls++) {
+        const float xx = fmaf(alpha, jvl, jr); const bool on = row && xx < 0.f;
+        float d1 = on ? tj * xx : 0.f, d2 = on ? tj * jvl : 0.f, dn = on ? fabsf(tj * xx) : 0.f;
+        if (ls == 0) warp_sum3(d1, d2, dn); else warp_sum2(d1, d2);
+        d1 += q1 + alpha * q2; d2 += q2;
+        if (ls == 0 && fabsf(d1) <= 2.4e-7f * (dn + fabsf(q1))) { alpha = 1.0f; break; }
+        if (fabsf(d1) < 1e-6f * (1.0f + fabsf(q1))) break;
+        if (d1 < 0.f) lo = alpha; else hi = alpha;
+        if (!(d2 > 0.f)) break;
+        float na = alpha - d1 / d2;
+        if (hi > 0.f && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+        if (na < 0.f) na = 0.f;
+        const bool done = fabsf(na - alpha) < 1e-7f * (1.0f + fabsf(alpha));
+        alpha = na;
+        if (done) break;
+      }
+      float amx = B2_NEWTON_AFLOOR;
+#pragma unroll
+      for (int c = 0; c < ND; c++) { a[c] = fmaf(alpha, srch[c], a[c]); Ma[c] = fmaf(alpha, Mv[c], Ma[c]); amx = fmaxf(amx, fmaxf(fabsf(a[c]), fabsf(as[c]))); }
+      bool moving = false;
+#pragma unroll
+      for (int c = 0; c < ND; c++) moving |= c < nd && fabsf(alpha * srch[c]) > fmaf(B2_NEWTON_RTOL, amx, B2_NEWTON_NOISE * noise[c]);
+      if (!moving) { it++; break; }
+    }
+    // efc_force at the solution (reporting only) and qfrc_constraint = M (a - a_smooth)
+    const float sres = rowdot(a) - aref;
+    if (row) { jar[lane] = sres < 0.f ? -Dl * sres : 0.f; Dr[lane] = Dl; }
+    {
+      float y[ND], My[ND];
+#pragma unroll
+      for (int c = 0; c < ND; c++) y[c] = a[c] - as[c];
+      mulM(y, My);
+#pragma unroll
+      for (int c = 0; c < ND; c++) if (lane == c && c < nd) { const int d = cols.dof(c); p_qfc()[d] = My[c]; p_qacc()[d] = My[c]; }
+    }
+    sync();
+    if (it >= iters && lane == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
+    return it;
+  }
   template <bool WD> __device__ __forceinline__ void solve_newton(unsigned long long* counters) {
     const int* madr = I(DI_dof_Madr); const int* ddepth = I(DI_dof_depth); const int* mcol = I(DI_Mcol);
     const int nisl = p_misc()[MISC_NISL], iters = dim(DD_iterations);
@@ -1936,6 +2095,20 @@ struct Engine {
       const int n = p_isl_n()[k]; if (!n || p_isl_warp()[k] != wl) continue;
       const int nd = p_isl_nd()[k], ndp = r4(nd), ldj = p_isl_ldj()[k], e0 = p_isl_adr()[k], nh = nd * (nd + 1) / 2;
       if (W > 1 && nd > TEAMND) continue;      // solved by the whole team, below
+      if (nd <= 6 && n <= 32) {                // a free body: in registers
+#ifdef B2_PHASE_TIMING
+        const long long ts0 = clock64();
+#endif
+        const int its = newton_island_small<WD>(k, counters);
+#ifdef B2_PHASE_TIMING
+        if (lane == 0 && B.phase_cycles) {
+          atomicAdd(&B.phase_cycles[16], 1ull); atomicAdd(&B.phase_cycles[17], (unsigned long long)its);
+          atomicAdd(&B.phase_cycles[18], (unsigned long long)n); atomicAdd(&B.phase_cycles[19], (unsigned long long)(clock64() - ts0));
+        }
+#endif
+        itmax = max(itmax, its);
+        continue;
+      }
 #ifdef B2_PHASE_TIMING
       const long long tn0 = clock64(); long long tq = tn0; const bool tbig = nd > 8;
       // islands above 8 dofs by phase: [22] setup, [23] J a + gradient, [24] H build, [25] + M and scaling, [26] Cholesky, [27] triangular solves,
@@ -1948,9 +2121,15 @@ struct Engine {
       float* H = island_A(k); float* a = H + r4(nh); float* as = a + ndp; float* fs = as + ndp;   // H: packed lower triangle
       float* Ma = fs + ndp; float* grad = Ma + ndp; float* srch = grad + ndp; float* Mv = srch + ndp; float* y = Mv + ndp;
       float* wrm = y + ndp; float* jv = WD ? xs_J<WD>(k) + r4(n * ldj) : wrm + ndp;
+      float* Md = wrm + ndp + (WD ? 0 : r4(n));      // dense packed copy of the island's block of M
       float* Dr = xs_row_R<WD>() + e0; float* aref = xs_row_res<WD>() + e0; float* jar = xs_row_f<WD>() + e0; const float* bb = xs_row_b<WD>() + e0;
       for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); as[c] = p_qas()[d]; fs[c] = p_qfs()[d]; wrm[c] = p_warm()[d]; }
+      for (int q = lane; q < nh; q += 32) Md[q] = 0.f;
       sync();
+      for (int c = lane; c < nd; c += 32) {
+        int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
+        for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); Md[r * (r + 1) / 2 + cc] = p_M()[m0 + u]; }
+      }
       // D = 1/R, capped at 1e8: MuJoCo floors R at 1e-15 (a body that cannot move along the row), and a penalty that
       // stiff puts J'D(Ja - aref) below fp32 resolution; the cap changes the constrained acceleration by <= force * 1e-8
       for (int i = lane; i < n; i += 32) {
@@ -1961,7 +2140,7 @@ struct Engine {
       // start from the cheaper of qacc_warmstart and qacc_smooth
       for (int c = lane; c < nd; c += 32) y[c] = wrm[c] - as[c];
       sync();
-      newton_mulM(cols, nd, y, Mv);
+      warp_mulMd(Md, nd, y, Mv);
       float cw = 0.f, cs = 0.f;
       for (int i = lane; i < n; i += 32) {
         const float* Ji = J + i * ldj; float sw = 0.f, ss = 0.f;
@@ -1974,20 +2153,23 @@ struct Engine {
       warp_sum2(cw, cs);
       for (int c = lane; c < nd; c += 32) a[c] = (cw < cs) ? wrm[c] : as[c];
       sync();
-      newton_mulM(cols, nd, a, Ma);
+      warp_mulMd(Md, nd, a, Ma);
       B2_NT(22);
       int it = 0;
       for (; it < iters; it++) {
         for (int i = lane; i < n; i += 32) {
           const float* Ji = J + i * ldj; float s = 0.f;
           for (int c = 0; c < nd; c++) s = fmaf(Ji[c], a[c], s);
-          jar[i] = s - aref[i];
+          s -= aref[i];
+          jar[i] = s; jv[i] = s < 0.f ? Dr[i] : 0.f;      // D of the active rows, zero for the others (jv is free until the search direction exists)
         }
         sync();
         float g2 = 0.f; bool resolved = false;
         for (int c = lane; c < nd; c += 32) {
           float g = Ma[c] - fs[c], sabs = fabsf(Ma[c]) + fabsf(fs[c]);
-          for (int i = 0; i < n; i++) { float x = jar[i]; if (x < 0.f) { float t = J[i * ldj + c] * (Dr[i] * x); g += t; sabs += fabsf(t); } }
+          const float* Jc = J + c;
+#pragma unroll 4
+          for (int i = 0; i < n; i++) { const float t = Jc[i * ldj] * (jv[i] * jar[i]); g += t; sabs += fabsf(t); }      // no branch: the loads of the next rows are in flight
           grad[c] = g; g2 = fmaf(g, g, g2);
           resolved |= fabsf(g) > B2_NEWTON_GRADNOISE * sabs;
         }
@@ -2050,16 +2232,15 @@ struct Engine {
             while (r * (r + 1) / 2 > q) r--;
             while ((r + 1) * (r + 2) / 2 <= q) r++;
             int c = q - r * (r + 1) / 2; float h = 0.f;
-            for (int i = 0; i < n; i++) if (jar[i] < 0.f) h = fmaf(J[i * ldj + r] * Dr[i], J[i * ldj + c], h);
+            const float* Jr = J + r; const float* Jc = J + c;
+#pragma unroll 4
+            for (int i = 0; i < n; i++) h = fmaf(Jr[i * ldj] * jv[i], Jc[i * ldj], h);
             H[q] = h;
           }
           sync();
         }
         B2_NT(24);
-        for (int c = lane; c < nd; c += 32) {
-          int d = cols.dof(c), m0 = madr[d], dep = ddepth[d];
-          for (int u = 0; u <= dep; u++) { int ca = p_dof_col()[mcol[m0 + u]]; int r = max(c, ca), cc = min(c, ca); H[r * (r + 1) / 2 + cc] += p_M()[m0 + u]; }
-        }
+        for (int q = lane; q < nh; q += 32) H[q] += Md[q];
         sync();
         for (int c = lane; c < nd; c += 32) Mv[c] = rsqrtf(fmaxf(H[c * (c + 1) / 2 + c], 1e-30f));   // Mv doubles as the scale vector here
         sync();
@@ -2103,7 +2284,7 @@ struct Engine {
         // undo the scaling, s = S (S H S)^-1 S (-g); y <- fp32 noise floor of each acceleration, (|f_smooth| + |M a|) / H_cc
         for (int c = lane; c < nd; c += 32) { float sc = Mv[c]; srch[c] = y[c] * sc; y[c] = sc * sc * (fabsf(fs[c]) + fabsf(Ma[c])); }
         sync();
-        newton_mulM(cols, nd, srch, Mv);
+        warp_mulMd(Md, nd, srch, Mv);
         float q1 = 0.f, q2 = 0.f;
         for (int c = lane; c < nd; c += 32) { q1 = fmaf(srch[c], Ma[c] - fs[c], q1); q2 = fmaf(srch[c], Mv[c], q2); }
         for (int i = lane; i < n; i += 32) {
@@ -2162,7 +2343,7 @@ struct Engine {
       }
       for (int c = lane; c < nd; c += 32) y[c] = a[c] - as[c];
       sync();
-      newton_mulM(cols, nd, y, Mv);
+      warp_mulMd(Md, nd, y, Mv);
       for (int c = lane; c < nd; c += 32) { int d = cols.dof(c); p_qfc()[d] = Mv[c]; p_qacc()[d] = Mv[c]; }
       sync();
       if (it >= iters && lane == 0 && counters) atomicAdd(&counters[CTR_ARENA_SPILL], 1ull);
