@@ -356,10 +356,11 @@ __device__ __forceinline__ int collide_pair(int t1, int t2, V3 p1, const float* 
   if (t1 == GT_CAPSULE) {
     if (t2 == GT_CAPSULE) return c_capsule_capsule(dst, p1, m1, s1, p2, m2, s2, margin);
     if (t2 == GT_BOX) return c_capsule_box(dst, p1, m1, s1, p2, m2, s2, margin);
-    if (t2 == GT_CYLINDER) return c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
+    if (t2 == GT_CYLINDER) return convex_far_apart(t1, p1, m1, s1, t2, p2, m2, s2, margin) ? 0 : c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
     return 0;
   }
-  if (t1 == GT_CYLINDER && (t2 == GT_BOX || t2 == GT_CYLINDER)) return c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
+  if (t1 == GT_CYLINDER && (t2 == GT_BOX || t2 == GT_CYLINDER))
+    return convex_far_apart(t1, p1, m1, s1, t2, p2, m2, s2, margin) ? 0 : c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   if (t1 == GT_BOX && t2 == GT_BOX) return c_box_box(dst, p1, m1, s1, p2, m2, s2, margin);
   return 0;
 }

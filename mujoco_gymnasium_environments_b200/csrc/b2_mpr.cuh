@@ -34,10 +34,15 @@ __device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y -
 __device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+#ifdef B2_HOST_BUILD
 __device__ __forceinline__ D3 dunit(D3 a) { return a * (1.0 / sqrt(ddot(a, a))); }
+#else
+__device__ __forceinline__ D3 dunit(D3 a) { return a * rsqrt(ddot(a, a)); }      // within an ulp of 1 / sqrt: one instruction sequence instead of two
+#endif
 
 struct CcdObj { int type; D3 pos; const float* mat; const float* size; double margin; };
-struct CcdSup { D3 v, v1, v2; };      // point of the Minkowski difference and its witnesses on geom 1 and geom 2
+struct CcdSup { D3 v; V3 w1; };      // point of the Minkowski difference (fp64: it decides) and its witness on geom 1 relative to geom 1's
+                                     // centre (fp32: only the reported position is formed from it; the witness on geom 2 is w1 - v)
 
 __device__ __forceinline__ bool ccd_zero(double x) { return fabs(x) < B2_CCD_EPS; }
 __device__ __forceinline__ bool ccd_eq(double a_, double b_) {
@@ -58,15 +63,20 @@ __device__ __forceinline__ D3 ccd_support1(const CcdObj& o, D3 dir) {
   if (o.type == 2) r = ld * s0;                                                              // sphere
   else if (o.type == 3) r = d3(ld.x * s0, ld.y * s0, ld.z * s0 + dsign0(ld.z) * s1);         // capsule
   else if (o.type == 5) {                                                                    // cylinder
-    const double t = sqrt(ld.x * ld.x + ld.y * ld.y);
-    if (t > 1e-15) { r.x = ld.x / t * s0; r.y = ld.y / t * s0; }
+    const double t2 = ld.x * ld.x + ld.y * ld.y;
+#ifdef B2_HOST_BUILD
+    if (t2 > 1e-30) { const double t = sqrt(t2); r.x = ld.x / t * s0; r.y = ld.y / t * s0; }
+#else
+    if (t2 > 1e-30) { const double k = rsqrt(t2) * s0; r.x = ld.x * k; r.y = ld.y * k; }
+#endif
     r.z = dsign0(ld.z) * s1;
   } else r = d3(dsign0(ld.x) * s0, dsign0(ld.y) * s1, dsign0(ld.z) * (double)o.size[2]);    // box
   return d3(m[0] * r.x + m[1] * r.y + m[2] * r.z + (o.pos.x + dir.x * o.margin), m[3] * r.x + m[4] * r.y + m[5] * r.z + (o.pos.y + dir.y * o.margin),
             m[6] * r.x + m[7] * r.y + m[8] * r.z + (o.pos.z + dir.z * o.margin));
 }
 __device__ __noinline__ void ccd_support(const CcdObj& o1, const CcdObj& o2, D3 dir, CcdSup& s) {   // __ccdSupport
-  s.v1 = ccd_support1(o1, dir); s.v2 = ccd_support1(o2, dir * -1.0); s.v = s.v1 - s.v2;
+  const D3 a = ccd_support1(o1, dir); s.v = a - ccd_support1(o2, dir * -1.0);
+  s.w1 = v3((float)(a.x - o1.pos.x), (float)(a.y - o1.pos.y), (float)(a.z - o1.pos.z));
 }
 __device__ __forceinline__ D3 portal_dir(const CcdSup* p) { return dunit(dcross(p[2].v - p[1].v, p[3].v - p[1].v)); }
 __device__ __forceinline__ bool portal_reach_tolerance(const CcdSup* p, const CcdSup& v4, D3 dir) {
@@ -108,7 +118,7 @@ __device__ __forceinline__ double point_tri_dist2(D3 x0, D3 B, D3 C, D3& wit) {
 }
 // discoverPortal: -1 no intersection, 0 portal found, 1 origin on v1, 2 origin on the v0-v1 segment
 __device__ __forceinline__ int discover_portal(const CcdObj& o1, const CcdObj& o2, CcdSup* p) {
-  p[0].v1 = o1.pos; p[0].v2 = o2.pos; p[0].v = o1.pos - o2.pos;
+  p[0].w1 = v3(0.f, 0.f, 0.f); p[0].v = o1.pos - o2.pos;
   if (ccd_is_origin(p[0].v)) p[0].v.x += B2_CCD_EPS * 10.0;
   D3 dir = dunit(p[0].v * -1.0);
   ccd_support(o1, o2, dir, p[1]);
@@ -139,9 +149,35 @@ __device__ __forceinline__ int discover_portal(const CcdObj& o1, const CcdObj& o
   return -1;
 }
 
+// fp32 support point of the un-inflated geom along a unit direction, relative to the geom's centre (pre-cull below)
+__device__ __forceinline__ V3 support_f32(int type, const float* mat, const float* size, V3 dir) {
+  const V3 ld = mulmatT(mat, dir); V3 r = v3(0.f, 0.f, 0.f);
+  if (type == 2) r = ld * size[0];
+  else if (type == 3) r = v3(ld.x * size[0], ld.y * size[0], fmaf(ld.z, size[0], (ld.z < 0.f ? -size[1] : size[1])));
+  else if (type == 5) {
+    const float t = sqrtf(ld.x * ld.x + ld.y * ld.y);
+    if (t > 1e-15f) { r.x = ld.x / t * size[0]; r.y = ld.y / t * size[0]; }
+    r.z = ld.z < 0.f ? -size[1] : size[1];
+  } else r = v3(ld.x < 0.f ? -size[0] : size[0], ld.y < 0.f ? -size[1] : size[1], ld.z < 0.f ? -size[2] : size[2]);
+  return mulmat(mat, r);
+}
+// Pure pruning in front of the fp64 path: the centre-to-centre direction is MPR's own first search direction; if the two
+// geoms are separated along it by more than the margin (with 1e-5 to spare for fp32 rounding), discoverPortal would return
+// "no intersection" from its first support point, so the pair is dropped without the call.  Cannot change a result.
+__device__ __forceinline__ bool convex_far_apart(int t1, V3 pos1, const float* m1, const float* s1, int t2, V3 pos2, const float* m2, const float* s2, float margin) {
+  const V3 c = pos2 - pos1; const float len = norm(c);
+  if (len < 1e-6f) return false;
+  const V3 d = c * (1.0f / len);
+  // extent of geom 1 towards geom 2 plus extent of geom 2 towards geom 1, against the centre distance
+  return dot(support_f32(t1, m1, s1, d), d) - dot(support_f32(t2, m2, s2, d * -1.f), d) + margin + 1e-5f < len;
+}
+
 // ccdMPRPenetration + mjc_MPRIteration: writes at most one raw contact, normal from geom 1 to geom 2
 __device__ __noinline__ int c_convex_mpr(float* dst, int t1, V3 pos1, const float* m1, const float* s1, int t2, V3 pos2, const float* m2,
                                          const float* s2, float margin) {
+#ifdef B2_NO_MPR      /* A/B only: what the convex path costs a task */
+  return 0;
+#endif
   CcdObj o1, o2;
   o1.type = t1; o1.pos = d3(pos1.x, pos1.y, pos1.z); o1.mat = m1; o1.size = s1; o1.margin = 0.5 * (double)margin;
   o2.type = t2; o2.pos = d3(pos2.x, pos2.y, pos2.z); o2.mat = m2; o2.size = s2; o2.margin = 0.5 * (double)margin;
@@ -149,7 +185,7 @@ __device__ __noinline__ int c_convex_mpr(float* dst, int t1, V3 pos1, const floa
   const int res = discover_portal(o1, o2, p);
   if (res < 0 || res == 1) return 0;     // touching at v1 has no direction: mjc_MPRIteration discards it
   if (res == 2) {                        // findPenetrSegment
-    pos = (p[1].v1 + p[1].v2) * 0.5;
+    pos = d3(p[1].w1.x, p[1].w1.y, p[1].w1.z) + o1.pos - p[1].v * 0.5;      // (v1 + v2) / 2 with v2 = v1 - v
     depth = sqrt(ddot(p[1].v, p[1].v)); n = dunit(p[1].v);
   } else {
     bool inside = false; D3 dir; CcdSup v4;
@@ -182,9 +218,11 @@ __device__ __noinline__ int c_convex_mpr(float* dst, int t1, V3 pos1, const floa
       sum = b1 + b2 + b3;
     }
     const double inv = 1.0 / sum;
-    const D3 a1 = (p[0].v1 * b0 + p[1].v1 * b1 + p[2].v1 * b2 + p[3].v1 * b3) * inv;
-    const D3 a2 = (p[0].v2 * b0 + p[1].v2 * b1 + p[2].v2 * b2 + p[3].v2 * b3) * inv;
-    pos = (a1 + a2) * 0.5;
+    const double w0 = b0 * inv, w1 = b1 * inv, w2 = b2 * inv, w3 = b3 * inv;      // sum to one: the shift by geom 1's centre passes through
+    const D3 a1 = d3(p[0].w1.x * w0 + p[1].w1.x * w1 + p[2].w1.x * w2 + p[3].w1.x * w3, p[0].w1.y * w0 + p[1].w1.y * w1 + p[2].w1.y * w2 + p[3].w1.y * w3,
+                     p[0].w1.z * w0 + p[1].w1.z * w1 + p[2].w1.z * w2 + p[3].w1.z * w3);
+    const D3 av = p[0].v * w0 + p[1].v * w1 + p[2].v * w2 + p[3].v * w3;
+    pos = a1 + o1.pos - av * 0.5;
   }
   if (ccd_is_origin(n)) return 0;
   if (!(depth == depth) || !(n.x == n.x) || !(pos.x == pos.x) || !(pos.y == pos.y) || !(pos.z == pos.z)) return 0;
