@@ -93,7 +93,7 @@ b2_env_kernel(const __grid_constant__ DevModel P, const __grid_constant__ BatchV
 template <class Task, int W>
 __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& B, const TaskParams& tp, int mode, double* epstat,
                                             const float* inject, int team, int env) {
-  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6, Task::NEWTON_TEAM_ND> E(P, B, B.model_floats + team * B.ws_floats, team, env);
+  Engine<W, Task::PGS_HOIST, Task::COOP_MIN, Task::COLD_PAIRS, Task::DYN_ISLANDS, Task::SOLVER, Task::CONDIM6, Task::NEWTON_TEAM_ND, Task::CONVEX_PAIRS> E(P, B, B.model_floats + team * B.ws_floats, team, env);
   const int lane = E.lane, tl = E.tl; const bool w0 = E.wl == 0;
   constexpr int TEAM = 32 * W;
   E.team_sync();      // the previous env's stores to this workspace are done
@@ -230,7 +230,7 @@ __device__ __forceinline__ void b2_env_body(const DevModel& P, const BatchView& 
 struct NoTask {
   static constexpr int OBS = 0, ACT = 0, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 0, NTI = 0, NTF = 0, NINJ = 1, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 80, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 6, EPISODE_SLOT = -1, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = -1;
-  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = true, CONVEX_PAIRS = true;
   template <class EN> __device__ static void apply_action(EN&, const TaskParams&, const float*, float*) {}
   template <class EN> __device__ static void pre_physics(EN&, const TaskParams&, int*, float*) {}
   template <class EN> __device__ static void after_settle(EN&, const TaskParams&, int*, float*) {}
@@ -411,11 +411,11 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   b->m = m; b->n_envs = n_envs;
   struct Guard { B2Batch* b; ~Guard() { if (b) b2_batch_destroy(b); } } guard{b};      // released on success
   memset(&b->tp, 0, sizeof(b->tp));
-  int task_solver = -1, keep_frames = 0; bool task_c6 = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6, task_lockstep = 0, task_arena = 0; bool cold = false; b->ninj = 1;
+  int task_solver = -1, keep_frames = 0; bool task_c6 = true, task_cvx = true; int xfrc_body = -1, arena_rows = 80, task_con_cap = 32, arena_span = 0, max_epb = 6, task_lockstep = 0, task_arena = 0; bool cold = false; b->ninj = 1;
   if (task) { b->tp.task = task->task; memcpy(b->tp.ids, task->ids, sizeof(task->ids)); memcpy(b->tp.act_lo, task->act_lo, sizeof(task->act_lo)); memcpy(b->tp.act_hi, task->act_hi, sizeof(task->act_hi)); memcpy(b->tp.aux_i, task->aux_i, sizeof(task->aux_i)); memcpy(b->tp.aux_f, task->aux_f, sizeof(task->aux_f)); }
   switch (b->tp.task) {
     case TASK_NONE: b->obs_dim = 0; b->act_dim = 0; b->nti = 0; b->ntf = 0; b->episode_slot = -1; break;
-#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; b->episode_slot = T::EPISODE_SLOT; task_lockstep = T::LOCKSTEP; task_arena = T::ARENA_FLOATS; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
+#define B2_TASK_DIMS(T) task_solver = T::SOLVER; task_c6 = T::CONDIM6; task_cvx = T::CONVEX_PAIRS; b->obs_dim = T::OBS; b->act_dim = T::ACT; b->nti = T::NTI; b->ntf = T::NTF; b->ninj = T::NINJ; keep_frames = T::KEEP_FRAMES; cold = T::COLD_PAIRS; arena_rows = T::ARENA_ROWS; task_con_cap = T::CON_CAP; arena_span = T::ARENA_SPAN; max_epb = T::MAX_EPB; b->episode_slot = T::EPISODE_SLOT; task_lockstep = T::LOCKSTEP; task_arena = T::ARENA_FLOATS; xfrc_body = T::XFRC_SLOT >= 0 ? b->tp.ids[T::XFRC_SLOT >= 0 ? T::XFRC_SLOT : 0] : -1
     case TASK_QUADRUPED_PARKOUR: B2_TASK_DIMS(QuadrupedTask); break;
     case TASK_HUMANOID_DANCING: B2_TASK_DIMS(DancingTask); break;
     case TASK_HUMANOID_SOCCER: B2_TASK_DIMS(SoccerTask); break;
@@ -428,6 +428,14 @@ int b2_batch_create(B2Model* m, const B2TaskDesc* task, int n_envs, uint64_t see
   const int* dim = m->dm.dim;
   if (m->condim6 && !task_c6) { return fail(B2_ERR_UNSUPPORTED, "the model has condim-6 pairs but the task kernel is built for 4-row pyramids"); }
   if (task_solver >= 0 && task_solver != dim[DD_solver]) { return fail(B2_ERR_UNSUPPORTED, "the task kernel is compiled for a different <option solver> than the model's"); }
+  if (!task_cvx) {      // the task's kernel is built without the convex (MPR) path: the model must not need it
+    const int* hi = m->h_ints.data(); const int* c1 = hi + m->dm.ioff[DI_pair_cg1]; const int* c2 = hi + m->dm.ioff[DI_pair_cg2]; const int* ct = hi + m->dm.ioff[DI_cg_type];
+    for (int p = 0; p < dim[DD_npair]; p++) {
+      const int t1 = ct[c1[p]], t2 = ct[c2[p]];
+      if ((t1 == GT_CAPSULE && t2 == GT_CYLINDER) || (t1 == GT_CYLINDER && (t2 == GT_CYLINDER || t2 == GT_BOX)))
+        return fail(B2_ERR_UNSUPPORTED, "the model has capsule-cylinder / cylinder-cylinder / cylinder-box candidate pairs but the task kernel is built without the convex path");
+    }
+  }
   BatchView& v = b->v; memset(&v, 0, sizeof(v));
   v.n_envs = n_envs; v.nqp = r4(dim[DD_nq]); v.nvp = r4(dim[DD_nv]); v.nup = r4(dim[DD_nu] > 0 ? dim[DD_nu] : 1);
   v.nti = b->nti > 0 ? b->nti : 1; v.ntf = b->ntf > 0 ? b->ntf : 1; v.obs_dim = b->obs_dim; v.act_dim = b->act_dim;

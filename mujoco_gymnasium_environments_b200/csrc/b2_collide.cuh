@@ -335,7 +335,10 @@ __device__ __noinline__ int c_box_box(float* dst, V3 p1, const float* m1, const 
 #include "b2_mpr.cuh"
 namespace b2 {
 
-// ---- dispatch: geom 1 has the lower type id
+// ---- dispatch: geom 1 has the lower type id.  CVX = false compiles the convex (MPR) call out: the mere presence of that
+// out-of-line fp64 function constrains the register allocation of the whole narrow-phase loop (quadruped: -4 %), so kernels of
+// models without convex candidate pairs are built without it (b2_batch_create checks the model against the task's trait)
+template <bool CVX = true>
 __device__ __forceinline__ int collide_pair(int t1, int t2, V3 p1, const float* m1, const float* s1, V3 p2, const float* m2,
                                             const float* s2, float margin, float* dst, int maxn) {
   if (t1 == GT_PLANE) {
@@ -356,10 +359,10 @@ __device__ __forceinline__ int collide_pair(int t1, int t2, V3 p1, const float* 
   if (t1 == GT_CAPSULE) {
     if (t2 == GT_CAPSULE) return c_capsule_capsule(dst, p1, m1, s1, p2, m2, s2, margin);
     if (t2 == GT_BOX) return c_capsule_box(dst, p1, m1, s1, p2, m2, s2, margin);
-    if (t2 == GT_CYLINDER) return convex_far_apart(t1, p1, m1, s1, t2, p2, m2, s2, margin) ? 0 : c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
+    if (t2 == GT_CYLINDER) { if (!CVX) return 0; return convex_far_apart(t1, p1, m1, s1, t2, p2, m2, s2, margin) ? 0 : c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin); }
     return 0;
   }
-  if (t1 == GT_CYLINDER && (t2 == GT_BOX || t2 == GT_CYLINDER))
+  if (CVX && t1 == GT_CYLINDER && (t2 == GT_BOX || t2 == GT_CYLINDER))
     return convex_far_apart(t1, p1, m1, s1, t2, p2, m2, s2, margin) ? 0 : c_convex_mpr(dst, t1, p1, m1, s1, t2, p2, m2, s2, margin);
   if (t1 == GT_BOX && t2 == GT_BOX) return c_box_box(dst, p1, m1, s1, p2, m2, s2, margin);
   return 0;

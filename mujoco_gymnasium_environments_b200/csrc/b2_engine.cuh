@@ -172,7 +172,8 @@ __host__ __device__ inline int dead_block_floats(const int* dim, int keep_frames
 // C6: the model has condim-6 pairs (10-row pyramids: two tangential, one torsional, two rolling directions); otherwise every
 // contact is a 4-row pyramid and the row bookkeeping uses the cheaper fixed-size arithmetic.
 // TEAMND: Newton islands with more dofs than this are solved by the whole team, smaller ones by one warp each.
-template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1, bool C6 = false, int TEAMND = 16>
+// CVX: the model has candidate pairs that take the convex (MPR) path.
+template <int W, bool HOIST = true, int COOPMIN = 32, bool COLD = false, bool DYN = true, int SOLVER = -1, bool C6 = false, int TEAMND = 16, bool CVX = true>
 struct Engine {
   const DevModel& P;
   const BatchView& B;
@@ -599,7 +600,7 @@ struct Engine {
       if (araw[k] >= 0) {
         V3 p1, p2; float m1[9], m2[9];
         geom_pose(g1, p1, m1); geom_pose(g2, p2, m2);
-        n = collide_pair(cgtype[g1], cgtype[g2], p1, m1, cgsize + 3 * g1, p2, m2, cgsize + 3 * g2, margin,
+        n = collide_pair<CVX>(cgtype[g1], cgtype[g2], p1, m1, cgsize + 3 * g1, p2, m2, cgsize + 3 * g2, margin,
                          rdata + B2_RAW * araw[k], pmax[p]);
       }
       rcount[k] = n;

@@ -161,15 +161,26 @@ __device__ __forceinline__ V3 support_f32(int type, const float* mat, const floa
   } else r = v3(ld.x < 0.f ? -size[0] : size[0], ld.y < 0.f ? -size[1] : size[1], ld.z < 0.f ? -size[2] : size[2]);
   return mulmat(mat, r);
 }
-// Pure pruning in front of the fp64 path: the centre-to-centre direction is MPR's own first search direction; if the two
-// geoms are separated along it by more than the margin (with 1e-5 to spare for fp32 rounding), discoverPortal would return
-// "no intersection" from its first support point, so the pair is dropped without the call.  Cannot change a result.
+// Pure pruning in front of the fp64 path.  Two convex sets whose supports leave a gap along ANY direction do not intersect, and
+// MPR reports "no intersection" for them (from its first support point when the direction is the centre-to-centre one, after a
+// few portal steps otherwise).  A handful of cheap fp32 candidates are tried: the centre direction, the axes of the cylinders
+// (a wide flat disc -- the dancer's floor and stage -- is inside the bounding sphere of everything above it, and only its own
+// axis separates it from a geom hovering over its rim) and the face normals of a box, each signed towards the other geom.  The
+// gap must exceed the margin by 1e-5 (fp32 rounding of the supports), so a pair MPR could call touching is never dropped.
+__device__ __forceinline__ bool convex_gap_along(int t1, const float* m1, const float* s1, int t2, const float* m2, const float* s2, V3 c, V3 d, float margin) {
+  if (dot(c, d) < 0.f) d = d * -1.f;      // from geom 1 towards geom 2
+  return dot(support_f32(t1, m1, s1, d), d) - dot(support_f32(t2, m2, s2, d * -1.f), d) + margin + 1e-5f < dot(c, d);
+}
 __device__ __forceinline__ bool convex_far_apart(int t1, V3 pos1, const float* m1, const float* s1, int t2, V3 pos2, const float* m2, const float* s2, float margin) {
   const V3 c = pos2 - pos1; const float len = norm(c);
-  if (len < 1e-6f) return false;
-  const V3 d = c * (1.0f / len);
-  // extent of geom 1 towards geom 2 plus extent of geom 2 towards geom 1, against the centre distance
-  return dot(support_f32(t1, m1, s1, d), d) - dot(support_f32(t2, m2, s2, d * -1.f), d) + margin + 1e-5f < len;
+  if (len > 1e-6f && convex_gap_along(t1, m1, s1, t2, m2, s2, c, c * (1.0f / len), margin)) return true;
+  if (t1 == 5 && convex_gap_along(t1, m1, s1, t2, m2, s2, c, matcol(m1, 2), margin)) return true;
+  if (t2 == 5 && convex_gap_along(t1, m1, s1, t2, m2, s2, c, matcol(m2, 2), margin)) return true;
+  if (t2 == 6) {
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) if (convex_gap_along(t1, m1, s1, t2, m2, s2, c, matcol(m2, k), margin)) return true;
+  }
+  return false;
 }
 
 // ccdMPRPenetration + mjc_MPRIteration: writes at most one raw contact, normal from geom 1 to geom 2

@@ -34,7 +34,7 @@ struct TaskParams {
 struct QuadrupedTask {
   static constexpr int OBS = 95, ACT = 16, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 6000, NTI = 8, NTF = 4, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 72, CON_CAP = 48, ARENA_SPAN = 0, MAX_EPB = 4, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false;    // robot and obstacles only ever touch the planes
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = true, COLD_PAIRS = false, DYN_ISLANDS = false, CONVEX_PAIRS = false;    // robot and obstacles only ever touch the planes
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -175,7 +175,7 @@ struct QuadrupedTask {
 struct DancingTask {
   static constexpr int OBS = 94, ACT = 29, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 3600, NTI = 12, NTF = 60, NINJ = 40, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 1 << 20, ARENA_ROWS = 60, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 5, EPISODE_SLOT = 4, LOCKSTEP = 1, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false;   // a single kinematic tree
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = false, CONVEX_PAIRS = true;   // a single kinematic tree
   static constexpr int NJ = 29, NSEQ = 20;
   static constexpr double DT = 0.01667, BEAT = 0.5;
 
@@ -359,7 +359,7 @@ struct DancingTask {
 struct SoccerTask {
   static constexpr int OBS = 80, ACT = 33, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 5000, NTI = 8, NTF = 16, NINJ = 36, KEEP_FRAMES = 2, XFRC_SLOT = 1, COOP_MIN = 32, ARENA_ROWS = 84, CON_CAP = 32, ARENA_SPAN = 0, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true, CONVEX_PAIRS = false;
   static constexpr int NJOINT = 29, NOBSJ = 25;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -532,7 +532,7 @@ struct SoccerTask {
 struct RescueTask {
   static constexpr int OBS = 102, ACT = 26, FRAME_SKIP = 1, SETTLE = 10, MAX_STEPS = 10000, NTI = 12, NTF = 12, NINJ = 12, KEEP_FRAMES = 1, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 48, ARENA_SPAN = 40, MAX_EPB = 3, EPISODE_SLOT = 4, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 7400;
   static constexpr int SOLVER = 0;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true, CONVEX_PAIRS = true;
   static constexpr int NVICT = 5;
 
   template <class EN> __device__ static __forceinline__ bool upright(EN& E, int torso) {
@@ -688,7 +688,7 @@ struct RescueTask {
 struct ConstructionTask {
   static constexpr int OBS = 135, ACT = 33, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 3000, NTI = 4, NTF = 8, NINJ = 4, KEEP_FRAMES = 0, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 96, ARENA_SPAN = 40, MAX_EPB = 2, EPISODE_SLOT = 2, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 14000;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true, CONVEX_PAIRS = false;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -772,7 +772,7 @@ struct ConstructionTask {
 struct MartialArtsTask {
   static constexpr int OBS = 113, ACT = 28, FRAME_SKIP = 1, SETTLE = 0, MAX_STEPS = 6000, NTI = 4, NTF = 4, NINJ = 2, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 92, CON_CAP = 80, ARENA_SPAN = 47, MAX_EPB = B2_MARTIAL_EPB, EPISODE_SLOT = 2, LOCKSTEP = 0, NEWTON_TEAM_ND = 16, ARENA_FLOATS = 0;
   static constexpr int SOLVER = 2;      // compile-time copy of the model's <option solver>; b2_batch_create checks it
-  static constexpr bool CONDIM6 = false, RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = false, RESET_FORWARD = true, PGS_HOIST = false, COLD_PAIRS = false, DYN_ISLANDS = true, CONVEX_PAIRS = true;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
@@ -858,7 +858,7 @@ struct MartialArtsTask {
 struct ArmTask {
   static constexpr int OBS = 110, ACT = 9, FRAME_SKIP = 10, SETTLE = 10, MAX_STEPS = 150000, NTI = 16, NTF = 4, NINJ = 1, KEEP_FRAMES = 2, XFRC_SLOT = -1, COOP_MIN = 32, ARENA_ROWS = 128, CON_CAP = 128, ARENA_SPAN = 9, MAX_EPB = 4, EPISODE_SLOT = 2, LOCKSTEP = 1, NEWTON_TEAM_ND = B2_ARM_TEAM_ND, ARENA_FLOATS = 4000;
   static constexpr int SOLVER = 2;
-  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true;
+  static constexpr bool CONDIM6 = true, RESET_FORWARD = false, PGS_HOIST = false, COLD_PAIRS = true, DYN_ISLANDS = true, CONVEX_PAIRS = true;
 
   template <class EN> __device__ static void apply_action(EN& E, const TaskParams& tp, const float* act, float* act_clipped) {
     for (int i = E.lane; i < ACT; i += 32) {
