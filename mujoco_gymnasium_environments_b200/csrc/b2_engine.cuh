@@ -557,6 +557,12 @@ struct Engine {
     int* alist = (int*)p_arena(); int* araw = alist + acap; int* rcount = araw + acap; float* rdata = p_arena() + 3 * acap;
     const unsigned lt = (1u << lane) - 1u;
     int nact = 0, dropped = 0;
+#ifdef B2_PHASE_TIMING
+    long long tc_ = clock64();      // [4] cull + slot hand-out, [5] narrow phase; the rest of [8] is the ordered compaction
+#define B2_CT(slot) do { if (lane == 0 && B.phase_cycles) { const long long t_ = clock64(); atomicAdd(&B.phase_cycles[slot], (unsigned long long)(t_ - tc_)); tc_ = t_; } } while (0)
+#else
+#define B2_CT(slot) do { } while (0)
+#endif
     for (int p0 = 0; p0 < npair; p0 += 32) {
       int p = p0 + lane; bool keep = false;
       if (p < npair) {
@@ -594,6 +600,7 @@ struct Engine {
       rbase += __shfl_sync(B2_FULL, incl, 31);
     }
     sync();
+    B2_CT(4);
     for (int k = lane; k < nact; k += 32) {
       int p = alist[k], g1 = pc1[p], g2 = pc2[p]; float margin = prm[B2DEV_PRM_STRIDE * pprm[p]];
       int n = 0;
@@ -606,6 +613,7 @@ struct Engine {
       rcount[k] = n;
     }
     sync();
+    B2_CT(5);
     // tier of this forward pass: more contacts than the on-chip buffer holds -> wide workspace (nothing is dropped)
     {
       int tot = 0;
@@ -945,40 +953,13 @@ struct Engine {
       }
     }
     team_sync();
-    // J entries
-    for (int k = 0; k < nisl; k++) {
-      int n = p_isl_n()[k]; if (!n) continue;
-      int nd = p_isl_nd()[k], ldj = p_isl_ldj()[k]; float* J = xs_J<WD>(k); const int blk = jblk(ldj);
-      int e0 = p_isl_adr()[k]; const Cols cols = island_cols(k);
-      for (int item = tl; item < n * nd; item += TEAM) {
-        int i = item / nd, c = item - i * nd, d = cols.dof(c);
-        int info = rinfo[e0 + i]; float val = 0.f;
-        if (info & 0x40000000) {
-          int ci = (info >> 4) & 0x03ffffff, dir = info & 15;
-          const float* con = conbuf + B2_CON_STRIDE * ci;
-          int p = __float_as_int(con[13]);
-          int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
-          int in1 = (cmask[b1 * nmw + (d >> 5)] >> (d & 31)) & 1, in2 = (cmask[b2 * nmw + (d >> 5)] >> (d & 31)) & 1;
-          int sgn = in2 - in1;
-          if (sgn) {
-            const float* pr = prm + B2DEV_PRM_STRIDE * pprm[p];
-            const int kd = dir >> 1;       // 0, 1: translation along t1, t2; 2, 3, 4 (condim 6): rotation about n, t1, t2
-            float mu = pr[2 + kd]; mu = (dir & 1) ? -mu : mu;
-            V3 nrm = ld3(con + 4);
-            S6 cd = ld6(p_cdof() + 6 * d);
-            V3 off = ld3(con + 1) - ld3(p_rootcom() + 3 * ridx[dbody[d]]);
-            V3 lin = cd.l + cross(cd.a, off);
-            if (!C6 || kd < 2) val = (float)sgn * dot(nrm + ld3(con + 7 + 3 * kd) * mu, lin);
-            else val = (float)sgn * (dot(nrm, lin) + mu * dot(kd == 2 ? nrm : ld3(con + 7 + 3 * (kd - 3)), cd.a));
-          }
-        } else {
-          int j = info >> 4;
-          if (jd[j] == d) val = (info & 1) ? -1.f : 1.f;
-        }
-        J[jr<WD>(i, blk, ldj) + c] = val;
-      }
-    }
-    team_sync();
+    // One thread per row: the row's parameters (impedance, R, reference acceleration) and its J entries, with the products of
+    // the row with qvel, qacc_smooth and qacc_warmstart accumulated while the entries are formed.  Everything that depends on
+    // the row only (contact record, pair parameters, the direction the pyramid row pushes along, the lever arms to the two
+    // bodies' tree roots) is loaded once per row; an entry then costs the chain-mask test, one 6-float cdof load, a cross
+    // product and a dot product: J_ed = sgn (u . (cdof_lin + cdof_ang x off)), the same arithmetic as before.
+    // (Round 2's first form took one (row, dof) entry per thread and re-walked the chain rinfo -> contact -> pair -> bodies ->
+    // masks -> parameters for each: eight dependent shared-memory loads per entry, 30-40 % of the arm's sub-step.)
     // per-row parameters
     int nefc = p_misc()[MISC_NEFC];
     for (int e = tl; e < nefc; e += TEAM) {
@@ -1026,11 +1007,42 @@ struct Engine {
         float tc = fmaxf(solref0, 2.f * timestep);
         K = 1.f / fmaxf(dmax * dmax * tc * tc * solref1 * solref1, B2_MINVAL); B = 2.f / fmaxf(dmax * tc, B2_MINVAL);
       } else { K = -solref0 / (dmax * dmax); B = -solref1 / dmax; }
-      // J row products with qvel, qacc_smooth, qacc_warmstart
+      // J row and its products with qvel, qacc_smooth, qacc_warmstart
       int nd = p_isl_nd()[isl], ldj = p_isl_ldj()[isl]; const Cols cols = island_cols(isl);
-      const float* Jr = xs_J<WD>(isl) + jr<WD>(e - p_isl_adr()[isl], jblk(ldj), ldj);
+      float* Jr = xs_J<WD>(isl) + jr<WD>(e - p_isl_adr()[isl], jblk(ldj), ldj);
       float vel = 0.f, ja = 0.f, jw = 0.f;
-      for (int c = 0; c < nd; c++) { float jv = Jr[c]; int d = cols.dof(c); vel = fmaf(jv, p_qvel()[d], vel); ja = fmaf(jv, p_qas()[d], ja); jw = fmaf(jv, p_warm()[d], jw); }
+      if (iscon) {
+        const int ci = (info >> 4) & 0x03ffffff, dir = info & 15, kd = dir >> 1;      // kd 0, 1: translation along t1, t2; 2, 3, 4 (condim 6): rotation about n, t1, t2
+        const float* con = conbuf + B2_CON_STRIDE * ci; const int p = __float_as_int(con[13]);
+        const int b1 = cgbody[pc1[p]], b2 = cgbody[pc2[p]];
+        float mu = (prm + B2DEV_PRM_STRIDE * pprm[p])[2 + kd]; mu = (dir & 1) ? -mu : mu;
+        const V3 nrm = ld3(con + 4), cpos = ld3(con + 1);
+        // direction the row pushes along (translation rows) / the axis it turns about (condim-6 rotation rows), and the lever
+        // arms from the two bodies' tree roots; the entry itself is formed exactly as mj_jac does: u . (cdof_lin + cdof_ang x off)
+        V3 u = nrm, rot = v3(0.f, 0.f, 0.f);
+        if (!C6 || kd < 2) u = nrm + ld3(con + 7 + 3 * kd) * mu;
+        else rot = (kd == 2 ? nrm : ld3(con + 7 + 3 * (kd - 3)));
+        // (a static body has no tree root: rootidx -1, and no dof in its chain mask, so its lever arm is never used)
+        const V3 off1 = cpos - ld3(p_rootcom() + 3 * max(ridx[b1], 0)), off2 = cpos - ld3(p_rootcom() + 3 * max(ridx[b2], 0));
+        const int* m1 = cmask + b1 * nmw; const int* m2 = cmask + b2 * nmw;
+        for (int c = 0; c < nd; c++) {
+          const int d = cols.dof(c);
+          const int in1 = (m1[d >> 5] >> (d & 31)) & 1, in2 = (m2[d >> 5] >> (d & 31)) & 1;
+          float val = 0.f;
+          if (in1 != in2) {
+            const S6 cd = ld6(p_cdof() + 6 * d);
+            const V3 lin = cd.l + cross(cd.a, in2 ? off2 : off1);
+            val = (!C6 || kd < 2) ? dot(u, lin) : dot(nrm, lin) + mu * dot(rot, cd.a);
+            if (in1) val = -val;
+            vel = fmaf(val, p_qvel()[d], vel); ja = fmaf(val, p_qas()[d], ja); jw = fmaf(val, p_warm()[d], jw);
+          }
+          Jr[c] = val;
+        }
+      } else {
+        const int dj = jd[info >> 4]; const float sg = (info & 1) ? -1.f : 1.f;
+        for (int c = 0; c < nd; c++) Jr[c] = cols.dof(c) == dj ? sg : 0.f;
+        vel = sg * p_qvel()[dj]; ja = sg * p_qas()[dj]; jw = sg * p_warm()[dj];
+      }
       float aref = -B * vel - K * imp * (pos - margin);
       rowR[e] = R;
       rowb[e] = ja - aref;
@@ -1040,6 +1052,7 @@ struct Engine {
     }
     team_sync();
   }
+
 
   // ---- layout of an island's A = J M^-1 J' + R: 4x4 tiles of the lower block triangle, tile (ti, tj <= ti) at
   // 16 * (tri(ti) + tj) floats.  Row c of a tile (4 floats = one 128-bit load) sits at chunk slot c ^ ((tile >> 1) & 3), so
@@ -2465,7 +2478,14 @@ struct Engine {
         for (int pass = 0; pass < npass; pass++) {
           if (pass == 0) {
             if (wl == 0) { vel_pass(); backward_pass(); mass_and_smooth(); }
+#ifdef B2_PHASE_TIMING
+            if (wl == (1 % W)) {      // the contact chain's own clock: [8] collision, [6] make_rows
+              const long long c0 = clock64(); collision(counters); const long long c1 = clock64(); make_rows(counters); const long long c2 = clock64();
+              if (lane == 0 && B.phase_cycles) { atomicAdd(&B.phase_cycles[8], (unsigned long long)(c1 - c0)); atomicAdd(&B.phase_cycles[6], (unsigned long long)(c2 - c1)); }
+            }
+#else
             if (wl == (1 % W)) { collision(counters); make_rows(counters); }
+#endif
             if (W == 3 && npass == 3) {
               // mj_Euler's factor of M + h D does not depend on the constraint solve: the team's third warp builds it
               // as soon as M exists (a two-warp named barrier hands M over), beside warp 0's factor of M
@@ -2476,7 +2496,7 @@ struct Engine {
             if (wide) { wide_pass(counters); B2_TICK(12); }      // cold path, out of line
             else {
               if (p_misc()[MISC_NEFC] > 0) {
-                fill_rows<false>(); B2_TICK(9);
+                B2_TICK(7); fill_rows<false>(); B2_TICK(9);
                 if (newton()) solve_newton<false>(counters);
                 else { build_A(); B2_TICK(10); solve_pgs(counters); }
                 B2_TICK(11);

@@ -40,6 +40,9 @@ if out[20]:
     print(f"  Newton islands > 8 dofs: {nb} solves ({nb/max(st['substeps'],1):.2f}/substep), {out[21]/nb:.2f} iterations, {tb/nb:.0f} cycles each:")
     for nm, c in (("setup", 22), ("J a + gradient", 23), ("H build", 24), ("+ M, scaling", 25), ("Cholesky", 26), ("triangular solves", 27), ("M s, J s", 28), ("line search", 29), ("update, exit tests", 30), ("finish", 31)):
         print(f"     {nm:20s} {100*out[c]/tb:5.1f}%  {out[c]/nb:9.0f} cycles/solve")
+if not out[15]:
+    ss = max(st["substeps"], 1)
+    print(f"  contact chain (the team's second warp, beside the dynamics chain): collision {out[8]/ss:.0f} (cull + slots {out[4]/ss:.0f}, narrow phase {out[5]/ss:.0f}), make_rows {out[6]/ss:.0f} cycles/substep; warp 0 waiting for it at the end of pass 0: {out[7]/ss:.0f}")
 out = list(out); out[4] = out[5] = out[6] = out[7] = out[8] = 0
 for n, v in zip(names, out[:14]):
     print(f"{n:32s} {100*v/tot:5.1f}%  {v/max(st['substeps'],1):10.0f} cycles/substep")
