@@ -41,13 +41,12 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the task's default size, from the
 # `ncu --set full` captures summarised under profiles/r02_h_<task>.txt (step 104 of a full-range rollout, final round-2 kernel).
-# Near or below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2; rescue's 71 MB
-# of writes are its wide-tier workspace (J and M^-1 J' blocks of the over-capacity passes) being evicted from L2, dancing's
-# extra 6 MB of reads are the model tables and terminal-step snapshots of 8 192 envs.
-NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.763648e6 + 160.0e3), "humanoid_dancing": (8192, 16.151808e6 + 1.593344e6),
-               "humanoid_soccer": (4096, 5.077248e6 + 1.28e3), "bipedal_rescue": (2048, 5.824e6 + 70.8672e6),
-               "humanoid_construction": (2048, 4.829184e6 + 118.784e3), "humanoid_martial_arts": (4096, 6.539008e6 + 23.808e3),
-               "robotic_arm_assembly": (2048, 8.622848e6 + 929.28e3)}
+# Near or below the algorithmic bytes because the state written by the previous launch is still in the 126 MB L2; rescue's 69 MB
+# of writes are its wide-tier workspace (J and M^-1 J' blocks of the over-capacity passes) being evicted from L2.
+NCU_TRAFFIC = {"quadruped_parkour": (4096, 4.445952e6 + 111.36e3), "humanoid_dancing": (8192, 9.742592e6 + 331.008e3),
+               "humanoid_soccer": (4096, 5.018624e6 + 256.0), "bipedal_rescue": (2048, 5.699072e6 + 69.081856e6),
+               "humanoid_construction": (2048, 4.817408e6 + 113.664e3), "humanoid_martial_arts": (4096, 6.47168e6 + 29.696e3),
+               "robotic_arm_assembly": (2048, 8.638976e6 + 1.151488e6)}
 TASK = "quadruped_parkour"
 WORKLOAD = WORKLOADS[TASK][2]
 
@@ -181,9 +180,9 @@ def _finite(x):
 # issue-slot utilisation of the step kernel (sm__inst_issued / cycle / 4 schedulers) from the committed `ncu --set full`
 # captures of one launch at the task's BASELINE size: the secondary bound of a path that is four orders of magnitude away from
 # its HBM roofline.  Static, like NCU_TRAFFIC: a bench run takes no profile.
-NCU_ISSUE_PCT = {t: (v, f"profiles/r02_h_{t}.txt") for t, v in (("quadruped_parkour", 27.89), ("humanoid_dancing", 20.07), ("humanoid_soccer", 27.20),
-                                                               ("bipedal_rescue", 23.03), ("humanoid_construction", 16.11),
-                                                               ("humanoid_martial_arts", 17.56), ("robotic_arm_assembly", 32.02))}
+NCU_ISSUE_PCT = {t: (v, f"profiles/r02_h_{t}.txt") for t, v in (("quadruped_parkour", 27.90), ("humanoid_dancing", 21.07), ("humanoid_soccer", 27.48),
+                                                               ("bipedal_rescue", 22.76), ("humanoid_construction", 15.13),
+                                                               ("humanoid_martial_arts", 17.06), ("robotic_arm_assembly", 30.40))}
 PREROLL = 100     # un-timed control steps before the warm-up: the bench times the stationary regime, not the first seconds after reset
 
 
