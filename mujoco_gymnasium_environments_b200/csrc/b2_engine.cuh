@@ -1766,22 +1766,46 @@ struct Engine {
       B2_NTT(23);
       if (scale * sqrtf(g2) < tol) break;
       if (nres == 0.f) break;      // every gradient entry below the rounding noise of its own terms (see the one-warp loop)
-      // H = M + J' diag(D active) J, lower triangle, one entry per thread; jv holds D of the active rows and zero for the
-      // others, so the inner loop has no branch
-      for (int q = tl; q < nh; q += TEAM) {
-        int r = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-        while (r * (r + 1) / 2 > q) r--;
-        while ((r + 1) * (r + 2) / 2 <= q) r++;
-        const int c = q - r * (r + 1) / 2; float h0 = Md[q], h1 = 0.f;
-        const float* Jr = J + r; const float* Jc = J + c;
-        int i = 0;
-        for (; i + 1 < n; i += 2) {
-          h0 = fmaf(Jr[i * ldj] * jv[i], Jc[i * ldj], h0); h1 = fmaf(Jr[(i + 1) * ldj] * jv[i + 1], Jc[(i + 1) * ldj], h1);
+      // H = M + J' diag(D active) J, lower triangle, one 4 x 4 tile per thread: a row of J contributes sixteen multiply-adds for
+      // nine shared-memory loads (four entries of each of the tile's two column groups and the row's D), where one entry per
+      // thread paid three loads per multiply-add and was bound by shared-memory bandwidth.  jv holds D of the active rows and
+      // zero for the others, so the inner loop has no branch.
+      {
+        const int nt = (nd + 3) >> 2, ntile = nt * (nt + 1) / 2;
+        for (int q = tl; q < ntile; q += TEAM) {
+          int tr = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+          while (tr * (tr + 1) / 2 > q) tr--;
+          while ((tr + 1) * (tr + 2) / 2 <= q) tr++;
+          const int tc = q - tr * (tr + 1) / 2, r0 = 4 * tr, c0 = 4 * tc;
+          // columns past nd read the row's last valid column and are never stored
+          const int ra = min(r0, nd - 1), rb = min(r0 + 1, nd - 1), rc = min(r0 + 2, nd - 1), rd = min(r0 + 3, nd - 1);
+          const int ca = min(c0, nd - 1), cb = min(c0 + 1, nd - 1), cc = min(c0 + 2, nd - 1), cd = min(c0 + 3, nd - 1);
+          float h[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) h[u][v] = 0.f;
+#pragma unroll 2
+          for (int i = 0; i < n; i++) {
+            const float* Ji = J + i * ldj; const float w = jv[i];
+            const float a0 = Ji[ra] * w, a1 = Ji[rb] * w, a2 = Ji[rc] * w, a3 = Ji[rd] * w;
+            const float b0 = Ji[ca], b1 = Ji[cb], b2 = Ji[cc], b3 = Ji[cd];
+            h[0][0] = fmaf(a0, b0, h[0][0]); h[0][1] = fmaf(a0, b1, h[0][1]); h[0][2] = fmaf(a0, b2, h[0][2]); h[0][3] = fmaf(a0, b3, h[0][3]);
+            h[1][0] = fmaf(a1, b0, h[1][0]); h[1][1] = fmaf(a1, b1, h[1][1]); h[1][2] = fmaf(a1, b2, h[1][2]); h[1][3] = fmaf(a1, b3, h[1][3]);
+            h[2][0] = fmaf(a2, b0, h[2][0]); h[2][1] = fmaf(a2, b1, h[2][1]); h[2][2] = fmaf(a2, b2, h[2][2]); h[2][3] = fmaf(a2, b3, h[2][3]);
+            h[3][0] = fmaf(a3, b0, h[3][0]); h[3][1] = fmaf(a3, b1, h[3][1]); h[3][2] = fmaf(a3, b2, h[3][2]); h[3][3] = fmaf(a3, b3, h[3][3]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int r = r0 + u;
+            if (r < nd) {
+#pragma unroll
+              for (int v = 0; v < 4; v++) { const int c = c0 + v; if (c <= r) { const int x = r * (r + 1) / 2 + c; H[x] = h[u][v] + Md[x]; } }
+            }
+          }
         }
-        if (i < n) h0 = fmaf(Jr[i * ldj] * jv[i], Jc[i * ldj], h0);
-        H[q] = h0 + h1;
+        team_sync();
       }
-      team_sync();
       B2_NTT(24);
       for (int c = tl; c < nd; c += TEAM) Mv[c] = rsqrtf(fmaxf(H[c * (c + 1) / 2 + c], 1e-30f));   // Mv doubles as the scale vector here
       team_sync();
