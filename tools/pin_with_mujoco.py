@@ -77,6 +77,9 @@ def main():
     ap.add_argument("--reference", default=os.environ.get("B2_REFERENCE_ROOT", "/root/reference"))
     ap.add_argument("--write", action="store_true", help="replace the expected values in tests/golden/ by MuJoCo's")
     ap.add_argument("--tasks", default=",".join(TASKS))
+    ap.add_argument("--native-ccd", action="store_true",
+                    help="leave MuJoCo's native GJK/EPA convex path on (default from 3.2.3); by default it is switched off so that cylinder pairs "
+                         "take libccd's MPR, the algorithm oracle/mjstep_ref.c::mpr_convex and csrc/b2_mpr.cuh restate")
     a = ap.parse_args()
     try:
         import mujoco
@@ -93,6 +96,9 @@ def main():
     for task in a.tasks.split(","):
         xml = compose.COMPOSERS[task](a.reference)
         model = mujoco.MjModel.from_xml_string(xml)
+        native = getattr(getattr(mujoco, "mjtDisableBit", None), "mjDSBL_NATIVECCD", None)
+        if native is not None and not a.native_ccd:
+            model.opt.disableflags |= int(native)        # MuJoCo >= 3.2.3: route convex pairs through libccd MPR again
         t = load_tables(task)
         dims = {k: (int(getattr(t, k)), int(getattr(model, k))) for k in ("nq", "nv", "nu", "nbody", "ngeom")}
         bad = {k: v for k, v in dims.items() if v[0] != v[1]}
