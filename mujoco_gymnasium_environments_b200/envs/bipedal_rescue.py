@@ -23,6 +23,7 @@ class BipedalRescueEnv(_GymEnv):
         self.dt = 0.02; self.max_episode_steps = 10000
         self.num_victims = 5; self.carry_capacity = 2; self.energy_limit = 1000.0
         self.safe_zone_pos = np.array([20.0, 0.0, 0.0]); self.safe_zone_radius = 3.0
+        self.victim_priorities = [0.8, 1.0, 0.7, 0.9, 1.0]      # rescue_env.py:58
         self._vec = B200VectorEnv("bipedal_rescue", 1, device=kwargs.get("device", 0), seed=kwargs.get("seed", 0) or 0)
         self.model = self._vec.tables; self.data = self._vec.batch
         self.action_space = self._vec.single_action_space
@@ -64,6 +65,21 @@ class BipedalRescueEnv(_GymEnv):
         return {"episode_stats": stats, "robot_position": o[52:55].astype(np.float64), "victims_remaining": 5 - int(ti[11]),
                 "victims_carried": int(bin(int(ti[2])).count("1")), "energy_remaining": float(tf[1]),
                 "robot_upright": bool(q[0] ** 2 - q[1] ** 2 - q[2] ** 2 + q[3] ** 2 > 0.7)}
+
+    # rescue_env.py:59-60 keeps two Python lists; bipedal_rescue_env/test_rescue.py:298-299 tests membership in them.  The kernel keeps
+    # them as bit masks (task state ti[1] rescued, ti[2] carried), so the lists come back in victim-index order, not pick-up order
+    @property
+    def victims_rescued(self):
+        return self._victim_list(1)
+
+    @property
+    def victims_carried(self):
+        return self._victim_list(2)
+
+    def _victim_list(self, col: int):
+        ti, _ = self._vec.task_state()
+        bits = int(ti[0, col])
+        return [i for i in range(self.num_victims) if (bits >> i) & 1]
 
     def render(self):
         return None

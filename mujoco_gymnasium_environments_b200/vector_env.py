@@ -77,6 +77,7 @@ class B200VectorEnv:
         self._term = torch.empty((num_envs,), dtype=torch.uint8, device=self.device)
         self._trunc = torch.empty((num_envs,), dtype=torch.uint8, device=self.device)
         self._done = torch.zeros((num_envs,), dtype=torch.bool, device=self.device)
+        self._pending = None
 
     # ---- Gymnasium VectorEnv surface
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
@@ -113,6 +114,67 @@ class B200VectorEnv:
         self._done = term | trunc
         infos = LazyInfos(self, {"final_obs": self._final_obs, "_final_obs": self._done})
         return self._obs, self._rew, term, trunc, infos
+
+    # ---- the rest of gymnasium.vector.VectorEnv / AsyncVectorEnv's surface, for callers written against the reference's envs
+    # under AsyncVectorEnv (BASELINE.md section 3 harness B): step_async really is asynchronous here -- it enqueues the step on
+    # the batch's stream and returns -- and step_wait hands out the tensors without a host synchronisation
+    def step_async(self, actions):
+        if self._pending is not None:
+            raise RuntimeError(f"step_async called while a {self._pending[0]} is pending")
+        self._pending = ("step", self.step(actions))
+
+    def step_wait(self, timeout=None):
+        return self._take("step")
+
+    def reset_async(self, seed=None, options=None):
+        if self._pending is not None:
+            raise RuntimeError(f"reset_async called while a {self._pending[0]} is pending")
+        self._pending = ("reset", self.reset(seed=seed, options=options))
+
+    def reset_wait(self, timeout=None):
+        return self._take("reset")
+
+    def _take(self, kind):
+        if self._pending is None or self._pending[0] != kind:
+            raise RuntimeError(f"{kind}_wait called without a pending {kind}_async")
+        out = self._pending[1]; self._pending = None
+        return out
+
+    def get_attr(self, name: str):
+        """Tuple of one value per env, as ``AsyncVectorEnv.get_attr``: constants of the env class (``max_episode_steps``,
+        ``frame_skip``, ``render_mode``, the single-env spaces, ``metadata``) repeated, and the per-env quantities the reference keeps as
+        attributes and reports in ``info`` (``step_count``, ``episode_stats`` ...) read back from the device task state."""
+        consts = {"max_episode_steps": self.spec.max_episode_steps, "frame_skip": self.spec.frame_skip, "render_mode": None,
+                  "action_space": self.single_action_space, "observation_space": self.single_observation_space,
+                  "metadata": {"render_modes": [], "render_fps": self.spec.render_fps}}
+        if name in consts:
+            return (consts[name],) * self.num_envs
+        if name in self.spec.info_keys:
+            infos = LazyInfos(self, {})
+            if name in infos:
+                v = infos[name]
+                if isinstance(v, dict):
+                    cols = {k: c.cpu().tolist() for k, c in v.items()}
+                    return tuple({k: c[i] for k, c in cols.items()} for i in range(self.num_envs))
+                return tuple(v.cpu().tolist())
+        raise AttributeError(f"{self.spec.name}: no per-env attribute {name!r} (constants: {sorted(consts)}; per-env: {self.spec.info_keys})")
+
+    def set_attr(self, name: str, values):
+        """The env state lives in the batch, not in Python attributes: write it with ``batch.set_state`` / ``batch.set_task_state``."""
+        raise AttributeError(f"{self.spec.name}: attribute {name!r} cannot be set on device envs; use batch.set_state / batch.set_task_state")
+
+    def call(self, name: str, *args, **kwargs):
+        """``AsyncVectorEnv.call``: per-env results of a method, or the attribute itself when ``name`` is not callable."""
+        if name == "render":
+            return (None,) * self.num_envs
+        return self.get_attr(name)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close_extras(self, **kwargs):
+        pass
 
     def task_state(self, with_xpos: bool = False):
         """Per-env task state (ti, tf[, xpos]); rows of envs whose episode ended in the last step hold the finished episode's

@@ -169,3 +169,35 @@ def test_mixed_streams_are_ordered(torch):
     torch.cuda.synchronize()
     assert np.array_equal(o.cpu().numpy(), ho)
     e.close(); f.close()
+
+
+def test_async_pairs_and_get_attr_follow_the_device_state(torch):
+    """step_async / step_wait give the same trajectory as step (two batches from one seed), and get_attr reads the per-env
+    quantities the reference keeps as attributes (quadruped_parkour_env/parkour_env.py:797-813) from the device."""
+    a = make("quadruped_parkour", 12, seed=3); b = make("quadruped_parkour", 12, seed=3)
+    a.reset(seed=9); b.reset_async(seed=9); b.reset_wait()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for k in range(5):
+        act = (torch.rand((12, 16), device="cuda", generator=g) - 0.5) * 4.0
+        oa, ra, ta, ua, _ = a.step(act)
+        b.step_async(act); ob, rb, tb, ub, _ = b.step_wait()
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(ua, ub)
+    assert b.get_attr("step_count") == (5,) * 12 and b.get_attr("max_episode_steps") == (6000,) * 12
+    er = b.get_attr("episode_reward")
+    assert len(er) == 12 and all(isinstance(v, float) for v in er)
+    with pytest.raises(AttributeError):
+        b.get_attr("np_random")
+    a.close(); b.close()
+
+
+def test_rescue_class_exposes_the_victim_lists_the_reference_test_reads():
+    # bipedal_rescue_env/test_rescue.py:298-300 reads env.victims_rescued / victims_carried / victim_priorities
+    from mujoco_gymnasium_environments_b200.envs import BipedalRescueEnv
+    env = BipedalRescueEnv()
+    env.reset(seed=0)
+    assert env.victims_rescued == [] and env.victims_carried == [] and len(env.victim_priorities) == env.num_victims == 5
+    ti, tf = env._vec.batch.get_task_state()
+    ti[0, 1] = 0b00010; ti[0, 2] = 0b01001
+    env._vec.batch.set_task_state(ti, tf)
+    assert env.victims_rescued == [1] and env.victims_carried == [0, 3]
+    env.close()

@@ -74,6 +74,45 @@ def test_lazy_infos_builds_once_and_only_on_demand():
     assert set(infos.keys()) >= {"final_obs", "_final_obs", "step_count", "task_ti", "task_tf"}
 
 
+def _fake_vector_env(n=3):
+    """A B200VectorEnv without its device batch: enough for the host-side AsyncVectorEnv surface."""
+    from mujoco_gymnasium_environments_b200.vector_env import B200VectorEnv
+    env = B200VectorEnv.__new__(B200VectorEnv)
+    env.torch = torch; env.spec = TASKS["bipedal_rescue"]; env.tables = load_tables("bipedal_rescue"); env.num_envs = n
+    env.single_action_space = env.spec.action_space(env.tables); env.single_observation_space = env.spec.observation_space(env.tables)
+    env._pending = None
+    ti = torch.zeros((n, 64), dtype=torch.int32); tf = torch.zeros((n, 64)); ti[:, 11] = torch.arange(n); ti[1, 2] = 0b101
+    env.task_state = lambda with_xpos=False: (ti, tf, torch.zeros((n, env.tables.nbody, 3))) if with_xpos else (ti, tf)
+    steps = []
+    env.step = lambda a: steps.append(a) or ("obs", "rew", "term", "trunc", {})
+    env.reset = lambda seed=None, options=None: ("obs0", {"seed": seed})
+    return env, steps
+
+
+def test_async_vector_env_surface_get_attr_call_and_async_pairs():
+    # gymnasium.vector.AsyncVectorEnv's calling convention, as BASELINE.md section 3 harness B drives the reference's envs
+    env, steps = _fake_vector_env()
+    assert env.get_attr("max_episode_steps") == (10000, 10000, 10000) and env.get_attr("render_mode") == (None,) * 3
+    assert env.get_attr("victims_remaining") == (5, 4, 3) and env.get_attr("victims_carried") == (0, 2, 0)
+    stats = env.get_attr("episode_stats")
+    assert len(stats) == 3 and [s["victims_rescued"] for s in stats] == [0, 1, 2]
+    assert env.call("render") == (None,) * 3 and env.call("frame_skip") == (1, 1, 1)
+    with pytest.raises(AttributeError):
+        env.get_attr("no_such_attribute")
+    with pytest.raises(AttributeError):
+        env.set_attr("victims_rescued", [[], [], []])
+    env.step_async("a0")
+    with pytest.raises(RuntimeError):
+        env.step_async("a1")
+    with pytest.raises(RuntimeError):
+        env.reset_wait()
+    assert env.step_wait()[0] == "obs" and steps == ["a0"]
+    with pytest.raises(RuntimeError):
+        env.step_wait()
+    env.reset_async(seed=7)
+    assert env.reset_wait() == ("obs0", {"seed": 7}) and env.unwrapped is env
+
+
 def test_batch_opts_struct_is_eight_ints_with_the_documented_fields():
     names = [f[0] for f in capi.B2BatchOpts._fields_]
     assert names == ["envs_per_block", "arena_floats", "con_cap", "row_cap", "warps_per_env", "disable_wide", "warmstart_once_per_step", "fifo_queue"]
