@@ -245,7 +245,7 @@ def run_task(task, N, K, warmup, preroll, action_scale, rank, world, local, peak
     achieved = spec.bytes_per_env_step * N / (kern_ms * 1e-3) / 1e9
     out["roofline"] = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                            traffic=(NCU_TRAFFIC[task][1] if NCU_TRAFFIC.get(task, (0, 0))[0] == N else None),
-                           traffic_source="static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, copied from profiles/r02_f_<task>.txt (not measured by this run)",
+                           traffic_source="static: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, copied from profiles/r02_h_<task>.txt (not measured by this run)",
                            peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                            bytes_per_env_step=spec.bytes_per_env_step, kernel_ms=kern_ms,
                            fp32_issue=dict(issue_slots_busy_pct=NCU_ISSUE_PCT[task][0], source="static: " + NCU_ISSUE_PCT[task][1]),
