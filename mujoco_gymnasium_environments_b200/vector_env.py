@@ -160,8 +160,34 @@ class B200VectorEnv:
         raise AttributeError(f"{self.spec.name}: no per-env attribute {name!r} (constants: {sorted(consts)}; per-env: {self.spec.info_keys})")
 
     def set_attr(self, name: str, values):
-        """The env state lives in the batch, not in Python attributes: write it with ``batch.set_state`` / ``batch.set_task_state``."""
-        raise AttributeError(f"{self.spec.name}: attribute {name!r} cannot be set on device envs; use batch.set_state / batch.set_task_state")
+        """``AsyncVectorEnv.set_attr`` for the per-env quantities that ARE task-state columns (``step_count``, ``episode_reward``,
+        ``energy_remaining``, the leaves of ``episode_stats`` ...): one value (or dict of values) per env, or a single one for all.
+        Derived quantities (``course_completion``, ``victims_remaining`` ...) and class constants cannot be set; the physics state
+        is written with ``batch.set_state``."""
+        t = self.torch
+        ti, tf = self.batch.get_task_state()
+        target = self.spec.vector_info(t, ti, tf, self.batch.xpos(), self.tables).get(name) if name in self.spec.info_keys else None
+        if target is None:
+            raise AttributeError(f"{self.spec.name}: {name!r} is not a settable per-env attribute (per-env: {self.spec.info_keys})")
+
+        def write(col, vals, what):
+            if getattr(col, "_base", None) is not ti and getattr(col, "_base", None) is not tf:
+                raise AttributeError(f"{self.spec.name}: {what!r} is derived from the task state, not stored in it; it cannot be set")
+            col.copy_(t.as_tensor(vals, device=col.device).to(col.dtype).expand_as(col))
+
+        if isinstance(target, dict):
+            rows = [values] * self.num_envs if isinstance(values, dict) else list(values)
+            if len(rows) != self.num_envs:
+                raise ValueError(f"{name}: expected {self.num_envs} dicts, got {len(rows)}")
+            for k in rows[0]:
+                if k not in target:
+                    raise AttributeError(f"{self.spec.name}: {name!r} has no entry {k!r}")
+                write(target[k], [r[k] for r in rows], f"{name}.{k}")
+        else:
+            if not isinstance(values, (int, float)) and len(values) != self.num_envs:
+                raise ValueError(f"{name}: expected {self.num_envs} values, got {len(values)}")
+            write(target, values, name)
+        self.batch.set_task_state(ti, tf)
 
     def call(self, name: str, *args, **kwargs):
         """``AsyncVectorEnv.call``: per-env results of a method, or the attribute itself when ``name`` is not callable."""

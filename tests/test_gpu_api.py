@@ -201,3 +201,22 @@ def test_rescue_class_exposes_the_victim_lists_the_reference_test_reads():
     env._vec.batch.set_task_state(ti, tf)
     assert env.victims_rescued == [1] and env.victims_carried == [0, 3]
     env.close()
+
+
+def test_set_attr_writes_task_state_columns_the_kernel_then_uses(torch):
+    """set_attr("step_count", ...) lands in the device task state: the episode is truncated when the counter reaches the
+    reference's max_episode_steps (the test is made before the increment, b2_tasks.cuh QuadrupedTask): on the fifth step after 5 996."""
+    env = make("quadruped_parkour", 8, seed=2)
+    env.reset(seed=2)
+    env.set_attr("step_count", 5996)
+    assert env.get_attr("step_count") == (5996,) * 8
+    env.set_attr("episode_reward", [float(i) for i in range(8)])
+    zero = torch.zeros((8, 16), device="cuda")
+    for k in range(5):
+        _, rew, term, trunc, _ = env.step(zero)
+        assert not bool(term.any())
+        assert bool(trunc.all()) == (k == 4), k
+    assert env.get_attr("step_count") == (6001,) * 8          # the finished episode's value on the terminal step
+    with pytest.raises(AttributeError):
+        env.set_attr("course_completion", 0.5)                # derived from xpos
+    env.close()

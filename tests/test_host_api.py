@@ -83,6 +83,13 @@ def _fake_vector_env(n=3):
     env._pending = None
     ti = torch.zeros((n, 64), dtype=torch.int32); tf = torch.zeros((n, 64)); ti[:, 11] = torch.arange(n); ti[1, 2] = 0b101
     env.task_state = lambda with_xpos=False: (ti, tf, torch.zeros((n, env.tables.nbody, 3))) if with_xpos else (ti, tf)
+    written = []
+
+    class FakeBatch:
+        get_task_state = staticmethod(lambda: (ti, tf))
+        xpos = staticmethod(lambda: torch.zeros((n, env.tables.nbody, 3)))
+        set_task_state = staticmethod(lambda a, b: written.append((a.clone(), b.clone())))
+    env.batch = FakeBatch(); env._written = written
     steps = []
     env.step = lambda a: steps.append(a) or ("obs", "rew", "term", "trunc", {})
     env.reset = lambda seed=None, options=None: ("obs0", {"seed": seed})
@@ -100,7 +107,17 @@ def test_async_vector_env_surface_get_attr_call_and_async_pairs():
     with pytest.raises(AttributeError):
         env.get_attr("no_such_attribute")
     with pytest.raises(AttributeError):
-        env.set_attr("victims_rescued", [[], [], []])
+        env.set_attr("victims_rescued", [[], [], []])        # a Python list in the reference, a bit mask here: not an info column
+    with pytest.raises(AttributeError):
+        env.set_attr("victims_remaining", [1, 2, 3])         # derived (5 - rescued), not stored
+    env.set_attr("energy_remaining", [10.0, 20.0, 30.0])
+    assert env._written[-1][1][:, 1].tolist() == [10.0, 20.0, 30.0] and env.get_attr("energy_remaining") == (10.0, 20.0, 30.0)
+    env.set_attr("energy_remaining", 500.0)
+    assert env.get_attr("energy_remaining") == (500.0,) * 3
+    env.set_attr("episode_stats", {"falls": 2})
+    assert [s["falls"] for s in env.get_attr("episode_stats")] == [2, 2, 2] and len(env._written) == 3
+    with pytest.raises(ValueError):
+        env.set_attr("energy_remaining", [1.0, 2.0])
     env.step_async("a0")
     with pytest.raises(RuntimeError):
         env.step_async("a1")
