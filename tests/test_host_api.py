@@ -31,6 +31,28 @@ def test_registration_table_matches_the_reference_ids():
         assert registration.register_all() == []
 
 
+def test_package_helpers_follow_the_reference_packages():
+    # humanoid_soccer_env/__init__.py:31-56 (make_env, get_env_info), bipedal_rescue_env/rescue_env.py:803-814 (register_env)
+    info = registration.get_env_info("humanoid_soccer")
+    assert info["name"] == "HumanoidSoccer-v0" and info["max_episode_steps"] == 2500 and info["class_max_episode_steps"] == 5000
+    assert info["action_space"].startswith("Box(33,)") and info["observation_space"] == "Box(80,)" and info["reward_threshold"] == 8000.0
+    assert registration.get_env_info("bipedal_rescue")["name"] == "BipedalRescue-v0"
+    assert registration.get_env_info("humanoid_martial_arts")["name"] is None            # the package registers nothing
+    assert set(registration.ON_DEMAND) == {"bipedal_rescue", "humanoid_dancing"}
+    assert registration.ON_DEMAND["humanoid_dancing"]["max_episode_steps"] == TASKS["humanoid_dancing"].max_episode_steps == 3600
+    try:
+        import gymnasium  # noqa: F401
+        assert registration.register_env("bipedal_rescue", prefix="B200Test/") == "B200Test/BipedalRescue-v0"
+        assert registration.register_env("bipedal_rescue", prefix="B200Test/") == "B200Test/BipedalRescue-v0"     # twice is fine
+    except ImportError:
+        assert registration.register_env("bipedal_rescue") == ""
+    with pytest.raises(NotImplementedError):
+        registration.make_env("humanoid_soccer", render_mode="human")                     # no renderer in the engine
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.B2Error):
+            registration.make_env("quadruped_parkour")                                    # no CPU fallback
+
+
 @pytest.mark.parametrize("task", list(TASKS))
 def test_vector_info_has_the_reference_keys_and_env_shaped_values(task):
     spec = TASKS[task]; t = load_tables(task); n = 5
