@@ -5,7 +5,9 @@ python bench.py --task humanoid_dancing ...              BASELINE.json configs[2
 python bench.py --impl reference ...                     the CPU arm: the reference's algorithm restated (oracle port),
                                                          one process per env on all host cores
 One "step" = one env.step over the whole batch (clip, frame_skip x mj_step, obs, reward, termination, same-step auto-reset).
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  `value` is device-timed with the actions resident in HBM; `e2e` goes through the host-buffer C-ABI call
+(b2_step_host) with the pinned host buffers the library hands out once -- actions written into them, one H2D copy, the launch, one packed
+D2H copy, all inside the timed region -- and `e2e.pageable_value` is the same loop with the caller's own pageable numpy arrays.
 """
 import argparse
 import json
